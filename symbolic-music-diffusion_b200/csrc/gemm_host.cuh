@@ -1,0 +1,123 @@
+// Host side of the tcgen05 GEMM: tensor-map construction (cuTensorMapEncodeTiled through the runtime's
+// driver-entry-point lookup, so libsmd.so has no link-time dependency on libcuda) and the launcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <atomic>
+#include <string>
+#include "gemm_tcgen05.cuh"
+
+namespace smd {
+
+extern std::atomic<long long> g_launches;
+void set_error(const std::string& msg);
+
+inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+// bf16 row-major matrix [rows][cols]; box = box_rows x 64 columns (128 bytes, SWIZZLE_128B).
+inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return false; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: code " + std::to_string(static_cast<int>(r)) + " rows=" +
+              std::to_string(rows) + " cols=" + std::to_string(cols) + " box_rows=" + std::to_string(box_rows));
+    return false;
+  }
+  return true;
+}
+
+struct GemmOp {
+  CUtensorMap tmA, tmB;
+  int N = 0, K = 0, BN = 0, cg = 1, a_mn = 0, b_mn = 0;
+};
+
+inline int choose_bn(int N, int cg) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  const int q = 16 * cg;
+  if (N < 256) return ((N + q - 1) / q) * q;
+  return 256;
+}
+
+// A: K-major [a_rows][K] (a_mn=0) or MN-major [K][a_rows] (a_mn=1); same for B with N rows.
+inline bool make_gemm_op(GemmOp* op, const void* A, uint64_t a_rows, const void* B, uint64_t b_rows_total, int N,
+                         int K, int BN, int cg, int a_mn, int b_mn, uint64_t k_rows_a = 0, uint64_t k_rows_b = 0) {
+  op->N = N; op->K = K; op->BN = BN; op->cg = cg; op->a_mn = a_mn; op->b_mn = b_mn;
+  if (K % 64 != 0) { set_error("GEMM K must be a multiple of 64"); return false; }
+  if (BN % (16 * cg) != 0 || BN > 256 || BN < 16 * cg) { set_error("bad BN " + std::to_string(BN)); return false; }
+  if (b_mn && (BN / cg) % 64 != 0) { set_error("MN-major B needs BN/cta_group % 64 == 0"); return false; }
+  bool ok;
+  if (!a_mn) ok = make_tmap_bf16(&op->tmA, A, a_rows, static_cast<uint64_t>(K), 128);
+  else ok = make_tmap_bf16(&op->tmA, A, k_rows_a ? k_rows_a : static_cast<uint64_t>(K), a_rows, 64);
+  if (!ok) return false;
+  if (!b_mn) ok = make_tmap_bf16(&op->tmB, B, b_rows_total, static_cast<uint64_t>(K), static_cast<uint32_t>(BN / cg));
+  else ok = make_tmap_bf16(&op->tmB, B, k_rows_b ? k_rows_b : static_cast<uint64_t>(K), b_rows_total, 64);
+  return ok;
+}
+
+inline int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int kCG>
+inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
+  using SM = GemmSmem<kCG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SM::kTotal);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  GemmShape sh;
+  sh.M = M; sh.N = op.N; sh.K = op.K; sh.BN = op.BN; sh.a_mn = op.a_mn; sh.b_mn = op.b_mn;
+  const int rows_per_tile = kBM * kCG;
+  const int tiles = ((M + rows_per_tile - 1) / rows_per_tile) * ((op.N + op.BN - 1) / op.BN);
+  int groups = device_sm_count() / kCG;
+  if (tiles < groups) groups = tiles;
+  if (groups < 1) groups = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * kCG));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = SM::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kCG;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCG>, op.tmA, op.tmB, sh, ep);
+}
+
+inline cudaError_t launch_gemm(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
+  return op.cg == 2 ? launch_gemm_cg<2>(op, M, ep, st) : launch_gemm_cg<1>(op, M, ep, st);
+}
+
+}  // namespace smd

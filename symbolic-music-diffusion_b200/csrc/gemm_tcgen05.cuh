@@ -1,0 +1,356 @@
+// Persistent, warp-specialised bf16 x bf16 -> fp32 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (accumulators in TMEM,
+//   double-buffered) -> tcgen05.ld epilogue fused with bias / residual / activation / LayerNorm / row statistics.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T     (both operands may independently be K-major or MN-major in global memory)
+//
+// kCG = 1: one CTA per 128 x BN tile.   kCG = 2: a CTA pair (cluster of 2) per 256 x BN tile using
+// tcgen05.mma.cta_group::2 (each CTA stages its own 128 rows of A and BN/2 rows of B).
+//
+// This is the kernel behind every Dense layer on the hot path (reference: flax.nn.Dense call sites
+// models/ncsn.py:155-178, models/shared.py:65,69).
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace smd {
+
+enum : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SWISH = 2 };
+
+struct GemmEpilogue {
+  const float* bias;            // [N] or null
+  const float* residual;        // fp32 [M][ld_res] or null  (v = acc + bias + residual)
+  int ld_res;
+  float* out_f32;               // fp32 [M][ld_f32] <- v, or null
+  int ld_f32;
+  __nv_bfloat16* out_bf16;      // bf16 [M][ld_bf16] <- act(v)   (or LayerNorm(v) when ln_gamma != null), or null
+  int ld_bf16;
+  int act;                      // activation applied on the bf16 output path
+  float* row_stats;             // [M][2] += (sum v, sum v^2) over this tile's columns (atomics), or null
+  const float* ln_gamma;        // full-row LayerNorm (requires N <= BN, a single n-tile): bf16 out = LN(v)*g+b
+  const float* ln_beta;
+  __nv_bfloat16* out_bf16_pre;  // bf16 [M][ld_bf16] <- v before the activation (training saves), or null
+  float out_scale;              // v is multiplied by out_scale before everything else if != 0 (0 means 1)
+};
+
+struct GemmShape {
+  int M, N, K;     // logical problem; K % 64 == 0
+  int BN;          // n-tile width: multiple of 16 (kCG=1) / 32 (kCG=2), <= 256
+  int a_mn, b_mn;  // 0: operand is K-major ([rows][K], K contiguous); 1: MN-major ([K][rows], rows contiguous)
+};
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;
+static constexpr int kTmemCols = 512;
+static constexpr int kAccCols = 256;
+
+template <int kCG>
+struct GemmSmem {
+  static constexpr int kBRowsMax = 256 / kCG;
+  static constexpr int kABytes = kBM * kBK * 2;            // 16 KB
+  static constexpr int kBBytes = kBRowsMax * kBK * 2;      // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kCG == 1) ? 4 : 6;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_GELU_TANH) {
+    const float c = 0.7978845608028654f;
+    float u = c * (v + 0.044715f * v * v * v);
+    return 0.5f * v * (1.0f + tanhf(u));
+  } else if (act == ACT_SWISH) {
+    return v / (1.0f + __expf(-v));
+  }
+  return v;
+}
+
+template <int kCG>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmShape sh, const GemmEpilogue ep) {
+  using SM = GemmSmem<kCG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kStages * SM::kStageBytes);
+  uint64_t* full_bar = bars;                         // [kStages]
+  uint64_t* empty_bar = bars + SM::kStages;          // [kStages]
+  uint64_t* tmem_full = bars + 2 * SM::kStages;      // [2]
+  uint64_t* tmem_empty = bars + 2 * SM::kStages + 2; // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * SM::kStages + 4);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+
+  const int BN = sh.BN;
+  const int rows_per_tile = kBM * kCG;
+  const int num_m = (sh.M + rows_per_tile - 1) / rows_per_tile;
+  const int num_n = (sh.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = sh.K / kBK;
+  const int group = blockIdx.x / kCG;
+  const int num_groups = gridDim.x / kCG;
+  const int b_rows = BN / kCG;  // B rows staged by this CTA
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < SM::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4 * kCG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kCG>(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish<kCG>();
+  }
+  tcgen05_fence_before();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t stage_tx = static_cast<uint32_t>((kBM + b_rows) * kBK * 2);
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        const int m_row0 = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM;
+        const int n_row0 = (tile % num_n) * BN + static_cast<int>(rank) * b_rows;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sA = smem + stage * SM::kStageBytes;
+          uint8_t* sB = sA + SM::kABytes;
+          const int k0 = kb * kBK;
+          if constexpr (kCG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            if (!sh.a_mn) tma_load_2d(&tmA, &full_bar[stage], sA, k0, m_row0);
+            else
+              for (int j = 0; j < kBM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sA + j * 8192, m_row0 + 64 * j, k0);
+            if (!sh.b_mn) tma_load_2d(&tmB, &full_bar[stage], sB, k0, n_row0);
+            else
+              for (int j = 0; j < b_rows / 64; ++j) tma_load_2d(&tmB, &full_bar[stage], sB + j * 8192, n_row0 + 64 * j, k0);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_tx);
+            const uint32_t bar_addr = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (!sh.a_mn) tma_load_2d_2sm(&tmA, bar_addr, sA, k0, m_row0);
+            else
+              for (int j = 0; j < kBM / 64; ++j) tma_load_2d_2sm(&tmA, bar_addr, sA + j * 8192, m_row0 + 64 * j, k0);
+            if (!sh.b_mn) tma_load_2d_2sm(&tmB, bar_addr, sB, k0, n_row0);
+            else
+              for (int j = 0; j < b_rows / 64; ++j) tma_load_2d_2sm(&tmB, bar_addr, sB + j * 8192, n_row0 + 64 * j, k0);
+          }
+          if (++stage == SM::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane of the leader CTA) =====================
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kBM * kCG, static_cast<uint32_t>(BN), sh.a_mn, sh.b_mn);
+      // per-UMMA_K (16 elements) advance of the descriptor start address, in bytes
+      const uint32_t a_kadv = sh.a_mn ? 2048u : 32u;
+      const uint32_t b_kadv = sh.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = sh.a_mn ? 8192u : 0u;
+      const uint32_t b_lbo = sh.b_mn ? 8192u : 0u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        if constexpr (kCG == 2) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);
+        else mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * SM::kStageBytes);
+          const uint32_t sB = sA + SM::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kadv, a_lbo, 1024u);
+            const uint64_t bdesc = make_smem_desc_sw128(sB + k * b_kadv, b_lbo, 1024u);
+            umma_bf16<kCG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<kCG>(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          if (++stage == SM::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit<kCG>(&tmem_full[acc]);       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    const float oscale = (ep.out_scale != 0.0f) ? ep.out_scale : 1.0f;
+    for (int tile = group; tile < num_tiles; tile += num_groups) {
+      const int row = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u + lane);
+      const int n0 = (tile % num_n) * BN;
+      const bool row_ok = row < sh.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
+      const bool do_ln = (ep.ln_gamma != nullptr);
+      float s1 = 0.f, s2 = 0.f;
+      float mean = 0.f, rstd = 0.f;
+      const int npass = do_ln ? 2 : 1;
+      for (int pass = 0; pass < npass; ++pass) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row guard below
+          uint32_t r[32];
+          const bool half = (BN - c0) < 32;  // 16-column tail
+          if (!half) {
+            tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x16(taddr + static_cast<uint32_t>(c0), r16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
+          }
+          tmem_ld_wait();
+          const int ncols = half ? 16 : 32;
+          const int col0 = n0 + c0;
+          if (!row_ok) continue;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
+          const bool full_chunk = (col0 + ncols <= sh.N);
+          if (ep.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols && col0 + i < sh.N) v[i] += __ldg(ep.bias + col0 + i);
+          }
+          if (ep.residual != nullptr) {
+            const float* rp = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
+            if (full_chunk && (ep.ld_res & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (i < ncols) {
+                  const float4 t = *reinterpret_cast<const float4*>(rp + i);
+                  v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols && col0 + i < sh.N) v[i] += rp[i];
+            }
+          }
+          if (pass == 0) {
+            if (ep.row_stats != nullptr || do_ln) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols && col0 + i < sh.N) { s1 += v[i]; s2 += v[i] * v[i]; }
+            }
+            if (ep.out_f32 != nullptr) {
+              float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+              if (full_chunk && (ep.ld_f32 & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  if (i < ncols) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) op[i] = v[i];
+              }
+            }
+            if (ep.out_bf16_pre != nullptr) {
+              __nv_bfloat16* op = ep.out_bf16_pre + static_cast<size_t>(row) * ep.ld_bf16 + col0;
+              if (full_chunk && (ep.ld_bf16 & 7) == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  if (i < ncols) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(op + i) = pk;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(v[i]);
+              }
+            }
+          }
+          const bool write_bf16 = (ep.out_bf16 != nullptr) && (do_ln ? (pass == 1) : true);
+          if (write_bf16) {
+            float w[32];
+            if (do_ln) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = (col0 + i < sh.N) ? (col0 + i) : 0;
+                w[i] = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + c)) + __ldg(ep.ln_beta + c);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] = act_apply(v[i], ep.act);
+            }
+            __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
+            if (full_chunk && (ep.ld_bf16 & 7) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (i < ncols) {
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(w[i], w[i + 1]);
+                  __nv_bfloat162 p1 = __floats2bfloat162_rn(w[i + 2], w[i + 3]);
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(w[i + 4], w[i + 5]);
+                  __nv_bfloat162 p3 = __floats2bfloat162_rn(w[i + 6], w[i + 7]);
+                  uint4 pk;
+                  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                  *reinterpret_cast<uint4*>(op + i) = pk;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(w[i]);
+            }
+          }
+        }  // column chunks
+        if (pass == 0 && do_ln) {
+          // flax LayerNorm: var = E[x^2] - E[x]^2, eps = 1e-6
+          const float inv_n = 1.0f / static_cast<float>(sh.N);
+          mean = s1 * inv_n;
+          const float var = s2 * inv_n - mean * mean;
+          rstd = rsqrtf(var + 1e-6f);
+        }
+      }  // passes
+      if (ep.row_stats != nullptr && row_ok) {
+        atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row), s1);
+        atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row) + 1, s2);
+      }
+      // release this accumulator stage back to the MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  // ===================== teardown =====================
+  __syncwarp();  // reconverge single-lane roles before the (aligned) block / cluster barrier
+  tcgen05_fence_before();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<kCG>(tmem_base, kTmemCols);
+}
+
+}  // namespace smd

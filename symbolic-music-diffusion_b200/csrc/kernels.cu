@@ -1,0 +1,397 @@
+// SIMT kernels of the DDPM hot path (see kernels.cuh for the contract of each launcher).
+#include "kernels.cuh"
+
+namespace smd {
+
+// ---------------------------------------------------------------------------------------------------
+// q_sample (utils/losses.py:295-300)
+// ---------------------------------------------------------------------------------------------------
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ eps,
+                                const float* __restrict__ ua, float* __restrict__ xt, float* __restrict__ cond, int B,
+                                int per_sample) {
+  const size_t total = static_cast<size_t>(B) * per_sample;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_sample);
+    const float a = ua[b];
+    const float sa = sqrtf(a), sb = sqrtf(1.0f - a);
+    xt[i] = __fadd_rn(__fmul_rn(sa, x0[i]), __fmul_rn(sb, eps[i]));
+    if (i % per_sample == 0) cond[b] = sa;
+  }
+}
+void launch_q_sample(const float* x0, const float* eps, const float* used_alpha, float* xt, float* cond, int B,
+                     int per_sample, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * per_sample;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  q_sample_kernel<<<blocks, 256, 0, st>>>(x0, eps, used_alpha, xt, cond, B, per_sample);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// embed: C -> 128 projection + positional encoding + first LayerNorm (one warp per token)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+             const float* __restrict__ posenc, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+             float* __restrict__ h, __nv_bfloat16* __restrict__ a, int M, int C, int S) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int m = warp;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xr = x + static_cast<size_t>(m) * C;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const float xl = (c0 + lane < C) ? xr[c0 + lane] : 0.f;
+    const int lim = min(32, C - c0);
+    for (int cc = 0; cc < lim; ++cc) {
+      const float xv = __shfl_sync(0xffffffffu, xl, cc);
+      const float* wr = W + static_cast<size_t>(c0 + cc) * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, __ldg(wr + lane + 32 * j), acc[j]);
+    }
+  }
+  const int s = m % S;
+  float v[4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = lane + 32 * j;
+    v[j] = acc[j] + bias[o] + posenc[s * 128 + o];
+    s1 += v[j]; s2 += v[j] * v[j];
+    h[static_cast<size_t>(m) * 128 + o] = v[j];
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  const float mean = s1 * (1.0f / 128.0f);
+  const float var = s2 * (1.0f / 128.0f) - mean * mean;
+  const float rstd = rsqrtf(var + 1e-6f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = lane + 32 * j;
+    a[static_cast<size_t>(m) * 128 + o] = __float2bfloat16_rn((v[j] - mean) * (rstd * ln_g[o]) + ln_b[o]);
+  }
+}
+void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
+                  const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st) {
+  const int blocks = (M + 7) / 8;
+  embed_kernel<<<blocks, 256, 0, st>>>(x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention: one CTA per sample, one warp per head, lane = query position (S = 32)
+// ---------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
+                                 float* __restrict__ probs, int B, int H) {
+  __shared__ float sK[32 * 128];
+  __shared__ float sV[32 * 128];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* base = qkv + static_cast<size_t>(b) * 32 * 384;
+  for (int i = tid; i < 32 * 128 / 4; i += blockDim.x) {
+    const int row = i / 32, c4 = (i % 32) * 4;
+    *reinterpret_cast<float4*>(&sK[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 128 + c4);
+    *reinterpret_cast<float4*>(&sV[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 256 + c4);
+  }
+  __syncthreads();
+  const int h = tid >> 5, lane = tid & 31;
+  if (h >= H) return;
+  float q[DH];
+  const float qs = rsqrtf(static_cast<float>(DH));
+  const float* qr = base + lane * 384 + h * DH;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) q[d] = qr[d] * qs;   // flax: query / sqrt(depth) before the dot
+  float sc[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(q[d], sK[j * 128 + h * DH + d], s);
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.0f / sum;
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float p = sc[j] * inv;
+    sc[j] = p;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, sV[j * 128 + h * DH + d], acc[d]);
+  }
+  __nv_bfloat16* orow = o + (static_cast<size_t>(b) * 32 + lane) * 128 + h * DH;
+#pragma unroll
+  for (int d = 0; d < DH; d += 2) {
+    *reinterpret_cast<__nv_bfloat162*>(orow + d) = __floats2bfloat162_rn(acc[d], acc[d + 1]);
+  }
+  if (probs != nullptr) {
+    float* pr = probs + ((static_cast<size_t>(b) * H + h) * 32 + lane) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(pr + j) = make_float4(sc[j], sc[j + 1], sc[j + 2], sc[j + 3]);
+  }
+}
+void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st) {
+  const int dh = 128 / H;
+  if (dh == 16) attention_kernel<16><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
+  else if (dh == 8) attention_kernel<8><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
+  else if (dh == 32) attention_kernel<32><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
+  else if (dh == 4) attention_kernel<4><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm-apply + FiLM + activation -> bf16 (one warp per row)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ g,
+                   const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
+                   int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float* ur = u + static_cast<size_t>(m) * N;
+  float s1, s2;
+  if (stats != nullptr) {
+    s1 = stats[2 * static_cast<size_t>(m)];
+    s2 = stats[2 * static_cast<size_t>(m) + 1];
+  } else {
+    s1 = 0.f; s2 = 0.f;
+    for (int c = lane * 4; c < N; c += 128) {
+      const float4 t = *reinterpret_cast<const float4*>(ur + c);
+      s1 += t.x + t.y + t.z + t.w;
+      s2 += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+  }
+  const float inv_n = 1.0f / static_cast<float>(N);
+  const float mean = s1 * inv_n;
+  const float var = s2 * inv_n - mean * mean;
+  const float rstd = rsqrtf(var + 1e-6f);
+  const size_t frow = film_bcast ? 0 : static_cast<size_t>(m / S);
+  const float* sc = scale ? scale + frow * film_ld : nullptr;
+  const float* sh = shift ? shift + frow * film_ld : nullptr;
+  __nv_bfloat16* orow = out + static_cast<size_t>(m) * N;
+  for (int c = lane * 4; c < N; c += 128) {
+    const float4 t = *reinterpret_cast<const float4*>(ur + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(g + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(bta + c);
+    float y[4] = {(t.x - mean) * (rstd * g4.x) + b4.x, (t.y - mean) * (rstd * g4.y) + b4.y,
+                  (t.z - mean) * (rstd * g4.z) + b4.z, (t.w - mean) * (rstd * g4.w) + b4.w};
+    if (sc != nullptr) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + c);
+      const float4 h4 = *reinterpret_cast<const float4*>(sh + c);
+      y[0] = s4.x * y[0] + h4.x; y[1] = s4.y * y[1] + h4.y; y[2] = s4.z * y[2] + h4.z; y[3] = s4.w * y[3] + h4.w;
+    }
+    if (act == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = swishf(y[i]);
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(orow + c) = pk;
+  }
+}
+void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
+                        const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
+                        int S, cudaStream_t st) {
+  const int blocks = (M + 7) / 8;
+  ln_film_act_kernel<<<blocks, 256, 0, st>>>(u, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N, S);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FiLM generator pieces
+// ---------------------------------------------------------------------------------------------------
+__global__ void noise_encoding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
+                                      float* __restrict__ enc, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 64) return;
+  const int r = i / 64, j = i % 64;
+  const float arg = __fmul_rn(__fmul_rn(5000.0f, t[r]), freqs[j]);  // (5000 * noise) * freq, in that order
+  enc[r * 128 + j] = sinf(arg);
+  enc[r * 128 + 64 + j] = cosf(arg);
+}
+void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R, cudaStream_t st) {
+  noise_encoding_kernel<<<(R * 64 + 127) / 128, 128, 0, st>>>(t, freqs, enc, R);
+}
+
+// y[r, n] = act(sum_k x[r,k] W[k,n] + b[n]);  block: 128 columns x 8 rows
+__global__ void __launch_bounds__(128)
+small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                    float* __restrict__ y, int R, int K, int N, int act) {
+  extern __shared__ float sx[];  // [8][K]
+  const int r0 = blockIdx.y * 8;
+  const int nr = min(8, R - r0);
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+    const int rr = i / K;
+    sx[i] = (rr < nr) ? x[static_cast<size_t>(r0 + rr) * K + (i % K)] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float w = __ldg(W + static_cast<size_t>(k) * N + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(sx[i * K + k], w, acc[i]);
+  }
+  const float bb = b ? b[n] : 0.f;
+  for (int i = 0; i < nr; ++i) {
+    float v = acc[i] + bb;
+    if (act == 2) v = v / (1.0f + expf(-v));
+    y[static_cast<size_t>(r0 + i) * N + n] = v;
+  }
+}
+void launch_small_linear(const float* x, const float* W, const float* b, float* y, int R, int K, int N, int act,
+                         cudaStream_t st) {
+  dim3 grid((N + 127) / 128, (R + 7) / 8);
+  small_linear_kernel<<<grid, 128, 8 * K * sizeof(float), st>>>(x, W, b, y, R, K, N, act);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int K, int N) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? src[static_cast<size_t>(k) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) dst[static_cast<size_t>(n) * K + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int N, cudaStream_t st) {
+  dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+  pack_transpose_bf16_kernel<<<grid, block, 0, st>>>(src, dst, K, N);
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  cast_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reverse-diffusion step after the network call (utils/ebm_utils.py:332-394)
+// thread = (sample n, channel c); loops over the S positions so the axis=1 norms reduce in registers
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reverse_step_kernel(const ReverseStepArgs a) {
+  const int t = a.t_ptr ? *a.t_ptr : a.t;
+  const float* cf = a.coef + 8 * t;
+  const float sqrt_recip = cf[0], sqrt_m1 = cf[1], mu1 = cf[2], mu2 = cf[3], sigma = cf[4], sqrt_ap = cf[5],
+              sqrt_1m = cf[6], alpha_prod = cf[7];
+  uint32_t k0 = a.key0, k1 = a.key1, ik0 = 0, ik1 = 0;
+  if (a.key_tab) { k0 = a.key_tab[4 * t]; k1 = a.key_tab[4 * t + 1]; ik0 = a.key_tab[4 * t + 2]; ik1 = a.key_tab[4 * t + 3]; }
+  const int NC = a.N * a.C;
+  const uint32_t total = static_cast<uint32_t>(a.N) * a.S * a.C;
+  const int slot = (a.slot_tab && a.collection) ? a.slot_tab[t] : -1;
+  float m_eps = 0.f, m_step = 0.f, m_noise = 0.f;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < NC) {
+    const int n = i / a.C, c = i % a.C;
+    float e2 = 0.f, st2 = 0.f, nz2 = 0.f;
+    for (int s = 0; s < a.S; ++s) {
+      const uint32_t idx = (static_cast<uint32_t>(n) * a.S + s) * a.C + c;
+      const float x = a.x[idx];
+      const float eh = a.eps_hat[idx];
+      float z = 0.f;
+      if (t > 0) z = a.z ? a.z[idx] : jax_normal_from_bits(jax_random_bits(k0, k1, idx, total));
+      const float noise = z * sigma;
+      float recon = __fsub_rn(__fmul_rn(sqrt_recip, x), __fmul_rn(sqrt_m1, eh));
+      recon = fminf(fmaxf(recon, -1.0f), 1.0f);
+      float nx = __fadd_rn(__fadd_rn(__fmul_rn(mu1, recon), __fmul_rn(mu2, x)), noise);
+      if (a.infill_mask) {
+        const float mk = a.infill_mask[idx];
+        const float ix = a.infill_x[idx];
+        float y = ix;
+        if (t > 0) {
+          const float iz = a.infill_z ? a.infill_z[idx] : jax_normal_from_bits(jax_random_bits(ik0, ik1, idx, total));
+          y = sqrt_ap * ix + sqrt_1m * iz;
+        }
+        nx = nx * (1.0f - mk) + y * mk;
+      }
+      const float stp = x - nx;
+      e2 += eh * eh; st2 += stp * stp; nz2 += noise * noise;
+      a.x_next[idx] = nx;
+      if (slot >= 0) a.collection[static_cast<size_t>(slot) * total + idx] = nx;
+    }
+    m_eps = sqrtf(e2 + 1e-10f); m_step = sqrtf(st2 + 1e-10f); m_noise = sqrtf(nz2 + 1e-10f);
+  }
+  if (a.metrics) {
+    __shared__ float red[3][8];
+    m_eps = warp_sum(m_eps); m_step = warp_sum(m_step); m_noise = warp_sum(m_noise);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = m_eps; red[1][w] = m_step; red[2][w] = m_noise; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float v = 0.f;
+      for (int j = 0; j < (blockDim.x >> 5); ++j) v += red[threadIdx.x][j];
+      const int si = a.T - 1 - t;
+      const int row = (threadIdx.x == 0) ? 0 : (threadIdx.x == 1 ? 1 : 3);
+      atomicAdd(a.metrics + row * a.T + si, v / static_cast<float>(NC));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 3) a.metrics[2 * a.T + (a.T - 1 - t)] = alpha_prod;
+  }
+}
+void launch_reverse_step(const ReverseStepArgs& a, cudaStream_t st) {
+  const int NC = a.N * a.C;
+  reverse_step_kernel<<<(NC + 255) / 256, 256, 0, st>>>(a);
+}
+__global__ void step_advance_kernel(int* t_ptr) { *t_ptr -= 1; }
+void launch_step_advance(int* t_ptr, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(t_ptr); }
+__global__ void fill_cond_kernel(const float* coef, const int* t_ptr, float* cond, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cond[i] = coef[8 * (*t_ptr) + 5];
+}
+void launch_fill_cond(const float* coef, const int* t_ptr, float* cond, int n, cudaStream_t st) {
+  fill_cond_kernel<<<(n + 255) / 256, 256, 0, st>>>(coef, t_ptr, cond, n);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// loss (utils/losses.py:304-308)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddpm_loss_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
+                 float* __restrict__ dpred, float gscale, int per_sample) {
+  const int b = blockIdx.x;
+  const size_t base = static_cast<size_t>(b) * per_sample;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < per_sample; i += blockDim.x) {
+    const float d = eps[base + i] - pred[base + i];
+    s += d * d;
+    if (dpred) dpred[base + i] = -2.0f * d * gscale;
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int j = 0; j < 8; ++j) v += red[j];
+    loss[b] = v / static_cast<float>(per_sample);
+  }
+}
+void launch_ddpm_loss(const float* eps, const float* pred, float* loss_per_example, float* dpred_or_null,
+                      float gscale, int B, int per_sample, cudaStream_t st) {
+  ddpm_loss_kernel<<<B, 256, 0, st>>>(eps, pred, loss_per_example, dpred_or_null, gscale, per_sample);
+}
+
+}  // namespace smd

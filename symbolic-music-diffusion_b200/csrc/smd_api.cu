@@ -1,0 +1,777 @@
+// libsmd C ABI implementation: plan / parameter arena / workspace carving, the score-network forward,
+// objective, sampler, jax-compatible RNG helpers and test hooks.  See include/smd.h.
+#include "../../include/smd.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gemm_host.cuh"
+#include "kernels.cuh"
+#include "train.cuh"
+
+namespace smd {
+
+std::atomic<long long> g_launches{0};
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+#define SMD_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+      return SMD_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+#define SMD_LAUNCH_CHECK(what)                                                                      \
+  do {                                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) {                                                                        \
+      set_error(std::string(what) + ": " + cudaGetErrorString(_e));                                \
+      return SMD_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+#define CNT() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+struct TensorInfo {
+  std::string name;
+  long long offset;
+  int shape[4];
+  int ndim;
+  long long size() const {
+    long long n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    return n;
+  }
+};
+
+static constexpr int kE = 128;       // embed_channels (models/ncsn.py:151)
+static constexpr int kFilmEmb = 128; // DenseFiLM embedding_channels (models/ncsn.py:174)
+static constexpr int kFilmHid = 512; // embedding_channels * 4
+static constexpr int kMaxT = 8192;
+
+}  // namespace smd
+
+using namespace smd;
+
+struct smd_plan {
+  smd_config cfg;
+  std::vector<TensorInfo> tensors;
+  std::map<std::string, long long> off;
+  long long arena = 0;
+  int Mp = 0;  // padded token rows
+  int K = 0;   // number of FiLM res-blocks (num_mlp_layers, or num_layers for DenseDDPM)
+  // ---- workspace carve (byte offsets) ----
+  std::map<std::string, size_t> ws_off;
+  size_t ws_bytes = 0;
+  uint8_t* ws = nullptr;
+  bool packed = false;
+  // ---- GEMM ops ----
+  std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b;
+  GemmOp op_post, op_out, op_in;
+  // sampler
+  int T = 0;
+  bool sampler_ready = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_n = -1;
+  const float* graph_params = nullptr;
+  float* graph_x = nullptr;
+  const float* graph_infill_x = nullptr;
+  const float* graph_infill_mask = nullptr;
+  float* graph_collection = nullptr;
+  float* graph_metrics = nullptr;
+  long long graph_nodes = 0;
+  smd::TrainState train;
+
+  template <typename Tp>
+  Tp* buf(const std::string& n) const { return reinterpret_cast<Tp*>(ws + ws_off.at(n)); }
+  const float* P(const float* params, const std::string& n) const { return params + off.at(n); }
+};
+
+namespace smd {
+
+static void add_tensor(smd_plan* p, const std::string& name, std::initializer_list<int> shape) {
+  TensorInfo t;
+  t.name = name;
+  t.ndim = static_cast<int>(shape.size());
+  int i = 0;
+  for (int s : shape) t.shape[i++] = s;
+  for (; i < 4; ++i) t.shape[i] = 1;
+  t.offset = p->arena;
+  p->off[name] = t.offset;
+  p->arena += (t.size() + 3) / 4 * 4;  // keep every tensor 16-byte aligned
+  p->tensors.push_back(t);
+}
+
+static void add_film_resblock(smd_plan* p, const std::string& pre, int Mdim) {
+  add_tensor(p, pre + "film.d1.kernel", {kFilmEmb, kFilmHid});
+  add_tensor(p, pre + "film.d1.bias", {kFilmHid});
+  add_tensor(p, pre + "film.d2.kernel", {kFilmHid, kFilmHid});
+  add_tensor(p, pre + "film.d2.bias", {kFilmHid});
+  add_tensor(p, pre + "film.ss.kernel", {kFilmHid, 2 * Mdim});
+  add_tensor(p, pre + "film.ss.bias", {2 * Mdim});
+  add_tensor(p, pre + "res.ln_a.scale", {Mdim});
+  add_tensor(p, pre + "res.ln_a.bias", {Mdim});
+  add_tensor(p, pre + "res.a.kernel", {Mdim, Mdim});
+  add_tensor(p, pre + "res.a.bias", {Mdim});
+  add_tensor(p, pre + "res.ln_b.scale", {Mdim});
+  add_tensor(p, pre + "res.ln_b.bias", {Mdim});
+  add_tensor(p, pre + "res.b.kernel", {Mdim, Mdim});
+  add_tensor(p, pre + "res.b.bias", {Mdim});
+}
+
+static void build_layout(smd_plan* p) {
+  const smd_config& c = p->cfg;
+  const int C = c.channels, Md = c.mlp_dims;
+  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
+    add_tensor(p, "in.kernel", {C, kE});
+    add_tensor(p, "in.bias", {kE});
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string pre = "l" + std::to_string(l) + ".";
+      add_tensor(p, pre + "ln1.scale", {kE});
+      add_tensor(p, pre + "ln1.bias", {kE});
+      add_tensor(p, pre + "attn.qkv.kernel", {kE, 3 * kE});
+      add_tensor(p, pre + "attn.qkv.bias", {3 * kE});
+      add_tensor(p, pre + "attn.out.kernel", {kE, kE});
+      add_tensor(p, pre + "attn.out.bias", {kE});
+      add_tensor(p, pre + "ln2.scale", {kE});
+      add_tensor(p, pre + "ln2.bias", {kE});
+      add_tensor(p, pre + "ffn1.kernel", {kE, Md});
+      add_tensor(p, pre + "ffn1.bias", {Md});
+      add_tensor(p, pre + "ffn2.kernel", {Md, kE});
+      add_tensor(p, pre + "ffn2.bias", {kE});
+    }
+    add_tensor(p, "post_ln.scale", {kE});
+    add_tensor(p, "post_ln.bias", {kE});
+    add_tensor(p, "post.kernel", {kE, Md});
+    add_tensor(p, "post.bias", {Md});
+    p->K = c.num_mlp_layers;
+  } else {
+    add_tensor(p, "in.kernel", {C, Md});
+    add_tensor(p, "in.bias", {Md});
+    p->K = c.num_layers;
+  }
+  for (int k = 0; k < p->K; ++k) add_film_resblock(p, "k" + std::to_string(k) + ".", Md);
+  add_tensor(p, "out_ln.scale", {Md});
+  add_tensor(p, "out_ln.bias", {Md});
+  add_tensor(p, "out.kernel", {Md, C});
+  add_tensor(p, "out.bias", {C});
+}
+
+static size_t ws_add(smd_plan* p, const std::string& name, size_t bytes) {
+  const size_t off = p->ws_bytes;
+  p->ws_off[name] = off;
+  p->ws_bytes += (bytes + 1023) / 1024 * 1024;
+  return off;
+}
+
+static void build_workspace(smd_plan* p) {
+  const smd_config& c = p->cfg;
+  const size_t Mp = p->Mp, Md = c.mlp_dims, C = c.channels, B = c.max_batch, K = p->K;
+  const bool tr = c.arch == SMD_ARCH_TRANSFORMER_DDPM;
+  // packed bf16 weights ([out][in], K-major tensor-core operands)
+  if (tr) {
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string pre = "w.l" + std::to_string(l) + ".";
+      ws_add(p, pre + "qkv", 3 * kE * kE * 2);
+      ws_add(p, pre + "o", kE * kE * 2);
+      ws_add(p, pre + "ffn1", Md * kE * 2);
+      ws_add(p, pre + "ffn2", kE * Md * 2);
+    }
+    ws_add(p, "w.post", Md * kE * 2);
+  } else {
+    ws_add(p, "w.in", Md * ((C + 63) / 64 * 64) * 2);
+  }
+  for (size_t k = 0; k < K; ++k) {
+    ws_add(p, "w.k" + std::to_string(k) + ".a", Md * Md * 2);
+    ws_add(p, "w.k" + std::to_string(k) + ".b", Md * Md * 2);
+  }
+  ws_add(p, "w.out", ((C + 15) / 16 * 16) * Md * 2);
+  // activations
+  if (tr) {
+    ws_add(p, "h", Mp * kE * 4);
+    ws_add(p, "a", Mp * kE * 2);
+    ws_add(p, "qkv", Mp * 3 * kE * 4);
+    ws_add(p, "o", Mp * kE * 2);
+    ws_add(p, "hidden", Mp * Md * 2);
+  } else {
+    ws_add(p, "xb", Mp * ((C + 63) / 64 * 64) * 2);
+  }
+  ws_add(p, "u", Mp * Md * 4);
+  ws_add(p, "r1", Mp * Md * 4);
+  ws_add(p, "act", Mp * Md * 2);
+  ws_add(p, "stats", (2 * K + 1) * Mp * 2 * 4);
+  // FiLM generator
+  ws_add(p, "tvec", B * 4);
+  ws_add(p, "enc", B * kFilmEmb * 4);
+  ws_add(p, "e1", B * kFilmHid * 4);
+  ws_add(p, "e2", B * kFilmHid * 4);
+  ws_add(p, "ss", K * B * 2 * Md * 4);
+  ws_add(p, "posenc", static_cast<size_t>(c.seq_len) * kE * 4);
+  ws_add(p, "freqs", 64 * 4);
+  // objective / sampler scratch
+  ws_add(p, "xt", B * c.seq_len * C * 4);
+  ws_add(p, "eps_hat", B * c.seq_len * C * 4);
+  ws_add(p, "coef", kMaxT * 8 * 4);
+  ws_add(p, "keys", kMaxT * 4 * 4);
+  ws_add(p, "slots", kMaxT * 4);
+  ws_add(p, "t_ptr", 64);
+  if (c.training) train_workspace(p->train, c, p->Mp, p->K, [&](const std::string& n, size_t b) { return ws_add(p, n, b); });
+}
+
+// sinusoid frequency table, float32 like jnp (models/ncsn.py:33-35, models/shared.py:41-43)
+static void host_freqs(float* f) {
+  const float emb = logf(10000.0f) / 63.0f;
+  for (int j = 0; j < 64; ++j) f[j] = expf(static_cast<float>(j) * -emb);
+}
+
+static int build_ops(smd_plan* p) {
+  const smd_config& c = p->cfg;
+  const int Md = c.mlp_dims, C = c.channels, cg = c.cta_group;
+  const uint64_t Mp = p->Mp;
+  auto W = [&](const std::string& n) { return p->buf<void>(n); };
+  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
+    p->op_qkv.resize(c.num_layers); p->op_o.resize(c.num_layers);
+    p->op_ffn1.resize(c.num_layers); p->op_ffn2.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string pre = "w.l" + std::to_string(l) + ".";
+      if (!make_gemm_op(&p->op_qkv[l], W("a"), Mp, W(pre + "qkv"), 3 * kE, 3 * kE, kE, 128, cg, 0, 0)) return SMD_ERR_CUDA;
+      if (!make_gemm_op(&p->op_o[l], W("o"), Mp, W(pre + "o"), kE, kE, kE, 128, cg, 0, 0)) return SMD_ERR_CUDA;
+      if (!make_gemm_op(&p->op_ffn1[l], W("a"), Mp, W(pre + "ffn1"), Md, Md, kE, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+      if (!make_gemm_op(&p->op_ffn2[l], W("hidden"), Mp, W(pre + "ffn2"), kE, kE, Md, 128, cg, 0, 0)) return SMD_ERR_CUDA;
+    }
+    if (!make_gemm_op(&p->op_post, W("a"), Mp, W("w.post"), Md, Md, kE, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+  } else {
+    const int Cp = (C + 63) / 64 * 64;
+    if (!make_gemm_op(&p->op_in, W("xb"), Mp, W("w.in"), Md, Md, Cp, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+  }
+  p->op_a.resize(p->K); p->op_b.resize(p->K);
+  for (int k = 0; k < p->K; ++k) {
+    const std::string pre = "w.k" + std::to_string(k) + ".";
+    if (!make_gemm_op(&p->op_a[k], W("act"), Mp, W(pre + "a"), Md, Md, Md, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+    if (!make_gemm_op(&p->op_b[k], W("act"), Mp, W(pre + "b"), Md, Md, Md, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+  }
+  if (!make_gemm_op(&p->op_out, W("act"), Mp, W("w.out"), C, C, Md, choose_bn(C, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+  return SMD_OK;
+}
+
+static GemmEpilogue epi() {
+  GemmEpilogue e;
+  memset(&e, 0, sizeof(e));
+  return e;
+}
+
+// FiLM generator for all K blocks: t (R values) -> ss[k][R][2*Md]   (models/ncsn.py:47-61)
+static int run_film(smd_plan* p, const float* params, const float* t, int R, cudaStream_t st) {
+  const int Md = p->cfg.mlp_dims;
+  float* enc = p->buf<float>("enc");
+  float* e1 = p->buf<float>("e1");
+  float* e2 = p->buf<float>("e2");
+  float* ss = p->buf<float>("ss");
+  launch_noise_encoding(t, p->buf<float>("freqs"), enc, R, st); CNT();
+  for (int k = 0; k < p->K; ++k) {
+    const std::string pre = "k" + std::to_string(k) + ".film.";
+    launch_small_linear(enc, p->P(params, pre + "d1.kernel"), p->P(params, pre + "d1.bias"), e1, R, kFilmEmb, kFilmHid, 2, st); CNT();
+    launch_small_linear(e1, p->P(params, pre + "d2.kernel"), p->P(params, pre + "d2.bias"), e2, R, kFilmHid, kFilmHid, 0, st); CNT();
+    launch_small_linear(e2, p->P(params, pre + "ss.kernel"), p->P(params, pre + "ss.bias"),
+                        ss + static_cast<size_t>(k) * p->cfg.max_batch * 2 * Md, R, kFilmHid, 2 * Md, 0, st); CNT();
+  }
+  SMD_LAUNCH_CHECK("film");
+  return SMD_OK;
+}
+
+// The FiLM'd residual tail shared by both architectures (models/ncsn.py:173-178, models/shared.py:61-75).
+// On entry u (fp32 [M][Md]) and stats[0] hold the block input and its row statistics.
+static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadcast, float* y, cudaStream_t st,
+                    smd::TrainState* save) {
+  const int Md = p->cfg.mlp_dims, C = p->cfg.channels;
+  float* u = p->buf<float>("u");
+  float* r1 = p->buf<float>("r1");
+  __nv_bfloat16* act = p->buf<__nv_bfloat16>("act");
+  float* stats = p->buf<float>("stats");
+  const size_t sstride = static_cast<size_t>(p->Mp) * 2;
+  float* ss = p->buf<float>("ss");
+  for (int k = 0; k < p->K; ++k) {
+    const std::string pre = "k" + std::to_string(k) + ".res.";
+    const float* scale = ss + static_cast<size_t>(k) * p->cfg.max_batch * 2 * Md;
+    const float* shift = scale + Md;
+    float* u_in = u;
+    float* r1_out = r1;
+    __nv_bfloat16* act_a = act;
+    __nv_bfloat16* act_b = act;
+    float* u_out = u;
+    if (save) {  // training keeps every block's tensors
+      u_in = save->u(p->ws, k); r1_out = save->r1(p->ws, k); act_a = save->act_a(p->ws, k);
+      act_b = save->act_b(p->ws, k); u_out = save->u(p->ws, k + 1);
+    }
+    launch_ln_film_act(u_in, stats + (2 * k) * sstride, p->P(params, pre + "ln_a.scale"), p->P(params, pre + "ln_a.bias"),
+                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st); CNT();
+    GemmEpilogue e = epi();
+    e.bias = p->P(params, pre + "a.bias");
+    e.out_f32 = r1_out; e.ld_f32 = Md;
+    e.row_stats = stats + (2 * k + 1) * sstride;
+    GemmOp opa = p->op_a[k];
+    GemmOp opb = p->op_b[k];
+    if (save) { if (!retarget_a(&opa, act_a, p->Mp) || !retarget_a(&opb, act_b, p->Mp)) return SMD_ERR_CUDA; }
+    SMD_CUDA(launch_gemm(opa, M, e, st));
+    launch_ln_film_act(r1_out, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
+                       p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st); CNT();
+    e = epi();
+    e.bias = p->P(params, pre + "b.bias");
+    e.residual = u_in; e.ld_res = Md;
+    e.out_f32 = u_out; e.ld_f32 = Md;
+    e.row_stats = stats + (2 * k + 2) * sstride;
+    SMD_CUDA(launch_gemm(opb, M, e, st));
+  }
+  float* u_last = save ? save->u(p->ws, p->K) : u;
+  __nv_bfloat16* act_o = save ? save->act_out(p->ws) : act;
+  launch_ln_film_act(u_last, stats + (2 * p->K) * sstride, p->P(params, "out_ln.scale"), p->P(params, "out_ln.bias"),
+                     nullptr, nullptr, 0, 0, 0, act_o, M, Md, S, st); CNT();
+  GemmEpilogue e = epi();
+  e.bias = p->P(params, "out.bias");
+  e.out_f32 = y; e.ld_f32 = C;
+  GemmOp opo = p->op_out;
+  if (save) { if (!retarget_a(&opo, act_o, p->Mp)) return SMD_ERR_CUDA; }
+  SMD_CUDA(launch_gemm(opo, M, e, st));
+  SMD_LAUNCH_CHECK("tail");
+  return SMD_OK;
+}
+
+int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
+                float* y, cudaStream_t st, smd::TrainState* save) {
+  const smd_config& c = p->cfg;
+  if (!p->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (!p->packed) { set_error("smd_pack_weights has not been called"); return SMD_ERR_STATE; }
+  if (batch < 1 || batch > c.max_batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  const int S = c.seq_len, C = c.channels, Md = c.mlp_dims;
+  const int M = batch * S;
+  float* stats = p->buf<float>("stats");
+  SMD_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * p->K + 1) * p->Mp * 2 * 4, st));
+  int rc = run_film(p, params, t, t_broadcast ? 1 : batch, st);
+  if (rc) return rc;
+  float* u0 = save ? save->u(p->ws, 0) : p->buf<float>("u");
+  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
+    float* h = p->buf<float>("h");
+    __nv_bfloat16* a = p->buf<__nv_bfloat16>("a");
+    float* qkv = p->buf<float>("qkv");
+    __nv_bfloat16* o = p->buf<__nv_bfloat16>("o");
+    __nv_bfloat16* hidden = p->buf<__nv_bfloat16>("hidden");
+    if (save) { h = save->h(p->ws, 0); a = save->a1(p->ws, 0); }
+    launch_embed(x, p->P(params, "in.kernel"), p->P(params, "in.bias"), p->buf<float>("posenc"),
+                 p->P(params, "l0.ln1.scale"), p->P(params, "l0.ln1.bias"), h, a, M, C, S, st); CNT();
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string pre = "l" + std::to_string(l) + ".";
+      GemmOp oq = p->op_qkv[l], oo = p->op_o[l], o1 = p->op_ffn1[l], o2 = p->op_ffn2[l];
+      float* h_in = h; float* h_mid = h; float* h_out = h;
+      __nv_bfloat16* a1 = a; __nv_bfloat16* a2 = a; __nv_bfloat16* a_next = a;
+      float* probs = nullptr;
+      __nv_bfloat16* hid_pre = nullptr;
+      if (save) {
+        h_in = save->h(p->ws, 2 * l); h_mid = save->h(p->ws, 2 * l + 1); h_out = save->h(p->ws, 2 * l + 2);
+        a1 = save->a1(p->ws, l); a2 = save->a2(p->ws, l);
+        a_next = (l + 1 < c.num_layers) ? save->a1(p->ws, l + 1) : save->a_post(p->ws);
+        qkv = save->qkv(p->ws, l); o = save->o(p->ws, l); hidden = save->hidden(p->ws, l);
+        hid_pre = save->hidden_pre(p->ws, l); probs = save->probs(p->ws, l);
+        if (!retarget_a(&oq, a1, p->Mp) || !retarget_a(&oo, o, p->Mp) || !retarget_a(&o1, a2, p->Mp) ||
+            !retarget_a(&o2, hidden, p->Mp)) return SMD_ERR_CUDA;
+      }
+      GemmEpilogue e = epi();
+      e.bias = p->P(params, pre + "attn.qkv.bias");
+      e.out_f32 = qkv; e.ld_f32 = 3 * kE;
+      SMD_CUDA(launch_gemm(oq, M, e, st));
+      launch_attention(qkv, o, probs, batch, c.num_heads, st); CNT();
+      e = epi();
+      e.bias = p->P(params, pre + "attn.out.bias");
+      e.residual = h_in; e.ld_res = kE;
+      e.out_f32 = h_mid; e.ld_f32 = kE;
+      e.out_bf16 = a2; e.ld_bf16 = kE;
+      e.ln_gamma = p->P(params, pre + "ln2.scale"); e.ln_beta = p->P(params, pre + "ln2.bias");
+      SMD_CUDA(launch_gemm(oo, M, e, st));
+      e = epi();
+      e.bias = p->P(params, pre + "ffn1.bias");
+      e.out_bf16 = hidden; e.ld_bf16 = Md; e.act = ACT_GELU_TANH;
+      e.out_bf16_pre = hid_pre;
+      SMD_CUDA(launch_gemm(o1, M, e, st));
+      e = epi();
+      e.bias = p->P(params, pre + "ffn2.bias");
+      e.residual = h_mid; e.ld_res = kE;
+      e.out_f32 = h_out; e.ld_f32 = kE;
+      e.out_bf16 = a_next; e.ld_bf16 = kE;
+      const std::string nl = (l + 1 < c.num_layers) ? ("l" + std::to_string(l + 1) + ".ln1.") : std::string("post_ln.");
+      e.ln_gamma = p->P(params, nl + "scale"); e.ln_beta = p->P(params, nl + "bias");
+      SMD_CUDA(launch_gemm(o2, M, e, st));
+    }
+    GemmEpilogue e = epi();
+    e.bias = p->P(params, "post.bias");
+    e.out_f32 = u0; e.ld_f32 = Md;
+    e.row_stats = stats;
+    GemmOp op = p->op_post;
+    if (save) { if (!retarget_a(&op, save->a_post(p->ws), p->Mp)) return SMD_ERR_CUDA; }
+    SMD_CUDA(launch_gemm(op, M, e, st));
+  } else {
+    __nv_bfloat16* xb = p->buf<__nv_bfloat16>("xb");
+    const int Cp = (C + 63) / 64 * 64;
+    if (Cp != C) { set_error("DenseDDPM on the CUDA path needs channels % 64 == 0"); return SMD_ERR_INVALID; }
+    launch_cast_bf16(x, xb, static_cast<size_t>(M) * C, st); CNT();
+    GemmEpilogue e = epi();
+    e.bias = p->P(params, "in.bias");
+    e.out_f32 = u0; e.ld_f32 = Md;
+    e.row_stats = stats;
+    SMD_CUDA(launch_gemm(p->op_in, M, e, st));
+  }
+  SMD_LAUNCH_CHECK("trunk");
+  return run_tail(p, params, M, S, t_broadcast, y, st, save);
+}
+
+// host threefry (same block function as the device one)
+static inline uint32_t h_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static void h_threefry(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  static const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0]; x1 += ks[1];
+  for (int i = 0; i < 5; ++i) {
+    for (int j = 0; j < 4; ++j) { x0 += x1; x1 = h_rotl(x1, R[i & 1][j]); x1 ^= x0; }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + static_cast<uint32_t>(i + 1);
+  }
+}
+static void h_split(const uint32_t key[2], int num, uint32_t* out) {
+  // jax.random.split: threefry_2x32(key, iota(2*num)).reshape(num, 2); counters split in halves
+  std::vector<uint32_t> flat(2 * num);
+  for (int i = 0; i < num; ++i) {
+    uint32_t a = static_cast<uint32_t>(i), b = static_cast<uint32_t>(num + i);
+    h_threefry(key[0], key[1], a, b);
+    flat[i] = a; flat[num + i] = b;
+  }
+  memcpy(out, flat.data(), sizeof(uint32_t) * 2 * num);
+}
+
+__global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, i, n));
+}
+
+}  // namespace smd
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* smd_last_error(void) { return g_err.c_str(); }
+int smd_version(void) { return 100; }
+long long smd_launch_count(void) { return g_launches.load(); }
+
+int smd_plan_create(const smd_config* cfg, smd_plan** out) {
+  if (!cfg || !out) { set_error("null argument"); return SMD_ERR_INVALID; }
+  smd_config c = *cfg;
+  if (c.arch != SMD_ARCH_TRANSFORMER_DDPM && c.arch != SMD_ARCH_DENSE_DDPM) { set_error("unknown arch"); return SMD_ERR_INVALID; }
+  if (c.cta_group == 0) c.cta_group = 1;
+  if (c.cta_group != 1 && c.cta_group != 2) { set_error("cta_group must be 1 or 2"); return SMD_ERR_INVALID; }
+  if (c.mlp_dims < 256 || c.mlp_dims % 256 != 0 || c.mlp_dims > 4096) { set_error("mlp_dims must be a multiple of 256 in [256, 4096]"); return SMD_ERR_INVALID; }
+  if (c.channels < 1 || c.max_batch < 1 || c.num_layers < 1) { set_error("bad sizes"); return SMD_ERR_INVALID; }
+  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
+    if (c.seq_len != 32) { set_error("TransformerDDPM CUDA path supports seq_len == 32 only (all reference configs)"); return SMD_ERR_INVALID; }
+    if (c.num_heads != 4 && c.num_heads != 8 && c.num_heads != 16 && c.num_heads != 32) { set_error("num_heads must be 4, 8, 16 or 32"); return SMD_ERR_INVALID; }
+    if (c.num_mlp_layers < 1) { set_error("num_mlp_layers must be >= 1"); return SMD_ERR_INVALID; }
+  } else {
+    c.seq_len = 1;
+  }
+  smd_plan* p = new smd_plan();
+  p->cfg = c;
+  p->Mp = (c.max_batch * c.seq_len + 255) / 256 * 256;
+  build_layout(p);
+  build_workspace(p);
+  *out = p;
+  return SMD_OK;
+}
+
+void smd_plan_destroy(smd_plan* plan) {
+  if (!plan) return;
+  if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+  delete plan;
+}
+
+int smd_num_tensors(const smd_plan* plan) { return static_cast<int>(plan->tensors.size()); }
+long long smd_arena_floats(const smd_plan* plan) { return plan->arena; }
+int smd_tensor_info(const smd_plan* plan, int index, char* name, int name_cap, long long* offset, int* shape4,
+                    int* ndim) {
+  if (index < 0 || index >= static_cast<int>(plan->tensors.size())) { set_error("tensor index out of range"); return SMD_ERR_INVALID; }
+  const TensorInfo& t = plan->tensors[index];
+  if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (offset) *offset = t.offset;
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = t.shape[i];
+  if (ndim) *ndim = t.ndim;
+  return SMD_OK;
+}
+size_t smd_workspace_bytes(const smd_plan* plan) { return plan->ws_bytes; }
+
+int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
+  if (!workspace || bytes < plan->ws_bytes) { set_error("workspace too small"); return SMD_ERR_INVALID; }
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024 != 0) { set_error("workspace must be 1024-byte aligned"); return SMD_ERR_INVALID; }
+  plan->ws = static_cast<uint8_t*>(workspace);
+  SMD_CUDA(cudaMemset(workspace, 0, plan->ws_bytes));  // padded rows / columns of every operand start finite
+  plan->packed = false;
+  plan->sampler_ready = false;
+  int rc = build_ops(plan);
+  if (rc) return rc;
+  float f[64];
+  host_freqs(f);
+  SMD_CUDA(cudaMemcpy(plan->buf<float>("freqs"), f, sizeof(f), cudaMemcpyHostToDevice));
+  // positional table (models/shared.py:33-48), float32 like jnp
+  std::vector<float> pe(static_cast<size_t>(plan->cfg.seq_len) * kE);
+  for (int s = 0; s < plan->cfg.seq_len; ++s)
+    for (int j = 0; j < 64; ++j) {
+      const float arg = static_cast<float>(s) * f[j];
+      pe[s * kE + j] = sinf(arg);
+      pe[s * kE + 64 + j] = cosf(arg);
+    }
+  SMD_CUDA(cudaMemcpy(plan->buf<float>("posenc"), pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
+  return SMD_OK;
+}
+
+int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const smd_config& c = plan->cfg;
+  const int Md = c.mlp_dims, C = c.channels;
+  auto pack = [&](const std::string& src, const std::string& dst, int K, int N) {
+    launch_pack_transpose_bf16(plan->P(params, src), plan->buf<__nv_bfloat16>(dst), K, N, st); CNT();
+  };
+  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string s = "l" + std::to_string(l) + ".", d = "w.l" + std::to_string(l) + ".";
+      pack(s + "attn.qkv.kernel", d + "qkv", kE, 3 * kE);
+      pack(s + "attn.out.kernel", d + "o", kE, kE);
+      pack(s + "ffn1.kernel", d + "ffn1", kE, Md);
+      pack(s + "ffn2.kernel", d + "ffn2", Md, kE);
+    }
+    pack("post.kernel", "w.post", kE, Md);
+  } else {
+    pack("in.kernel", "w.in", C, Md);
+  }
+  for (int k = 0; k < plan->K; ++k) {
+    const std::string s = "k" + std::to_string(k) + ".res.", d = "w.k" + std::to_string(k) + ".";
+    pack(s + "a.kernel", d + "a", Md, Md);
+    pack(s + "b.kernel", d + "b", Md, Md);
+  }
+  pack("out.kernel", "w.out", Md, C);
+  SMD_LAUNCH_CHECK("pack_weights");
+  plan->packed = true;
+  return SMD_OK;
+}
+
+int smd_forward(smd_plan* plan, const float* params, const float* x, const float* t, int t_broadcast, int batch,
+                float* y, smd_stream_t stream) {
+  return run_forward(plan, params, x, t, t_broadcast, batch, y, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int smd_ddpm_loss(smd_plan* plan, const float* params, const float* x0, const float* used_alpha, const float* eps,
+                  int batch, float* loss_per_example, float* pred_or_null, smd_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (batch < 1 || batch > plan->cfg.max_batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  const int per = plan->cfg.seq_len * plan->cfg.channels;
+  float* xt = plan->buf<float>("xt");
+  float* cond = plan->buf<float>("tvec");
+  float* pred = pred_or_null ? pred_or_null : plan->buf<float>("eps_hat");
+  launch_q_sample(x0, eps, used_alpha, xt, cond, batch, per, st); CNT();
+  int rc = run_forward(plan, params, xt, cond, 0, batch, pred, st, nullptr);
+  if (rc) return rc;
+  launch_ddpm_loss(eps, pred, loss_per_example, nullptr, 0.f, batch, per, st); CNT();
+  SMD_LAUNCH_CHECK("ddpm_loss");
+  return SMD_OK;
+}
+
+int smd_sampler_setup(smd_plan* plan, const float* host_betas, int T, const uint32_t host_key[2],
+                      smd_stream_t stream) {
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (T < 1 || T > kMaxT) { set_error("T out of range"); return SMD_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // utils/ebm_utils.py:315-318, 332-357, 363-364 -- float32, same operation order
+  std::vector<float> coef(static_cast<size_t>(T) * 8);
+  std::vector<float> ap(T), app(T), al(T);
+  float run = 1.0f;
+  for (int i = 0; i < T; ++i) {
+    al[i] = 1.0f - host_betas[i];
+    run = (i == 0) ? al[0] : run * al[i];
+    ap[i] = run;
+    app[i] = (i == 0) ? 1.0f : ap[i - 1];
+  }
+  for (int i = 0; i < T; ++i) {
+    const float beta = host_betas[i];
+    const float sqrt_recip = sqrtf(1.0f / ap[i]);
+    const float sqrt_m1 = sqrtf(1.0f - ap[i]) * sqrt_recip;
+    const float mu1 = beta * sqrtf(app[i]) / (1.0f - ap[i]);
+    const float mu2 = (1.0f - app[i]) * sqrtf(al[i]) / (1.0f - ap[i]);
+    const float var = beta * (1.0f - app[i]) / (1.0f - ap[i]);
+    const float logv = logf(fmaxf(var, 1e-20f));
+    const float sigma = expf(0.5f * logv);
+    float* c = &coef[static_cast<size_t>(i) * 8];
+    c[0] = sqrt_recip; c[1] = sqrt_m1; c[2] = mu1; c[3] = mu2; c[4] = sigma;
+    c[5] = sqrtf(ap[i]); c[6] = sqrtf(1.0f - ap[i]); c[7] = ap[i];
+  }
+  // keys: per scan step (t = T-1 .. 0): rng,key = split(rng); rng,infill = split(rng); rng,noise = split(rng)
+  std::vector<uint32_t> keys(static_cast<size_t>(T) * 4);
+  uint32_t rng[2] = {host_key[0], host_key[1]};
+  for (int t = T - 1; t >= 0; --t) {
+    uint32_t o[4];
+    h_split(rng, 2, o); rng[0] = o[0]; rng[1] = o[1];
+    h_split(rng, 2, o); rng[0] = o[0]; rng[1] = o[1];
+    keys[4 * t + 2] = o[2]; keys[4 * t + 3] = o[3];
+    h_split(rng, 2, o); rng[0] = o[0]; rng[1] = o[1];
+    keys[4 * t + 0] = o[2]; keys[4 * t + 1] = o[3];
+  }
+  // collection slots (utils/ebm_utils.py:320-325, 387-394): collection_idx = linspace(1, T, 40).astype(int32)
+  std::vector<int> slots(T, -1);
+  int idx_tab[40];
+  for (int j = 0; j < 40; ++j) {
+    const float v = (40 > 1) ? (1.0f + static_cast<float>(j) * (static_cast<float>(T - 1) / 39.0f)) : 1.0f;
+    idx_tab[j] = (j == 39) ? T : static_cast<int>(v);
+  }
+  for (int t = 0; t < T; ++t) {
+    const int image_idx = T - t + 1;
+    int sum = 0; bool any = false;
+    for (int j = 0; j < 40; ++j) if (idx_tab[j] == image_idx) { sum += j; any = true; }
+    if (any) slots[t] = sum + 1;
+  }
+  SMD_CUDA(cudaMemcpyAsync(plan->buf<float>("coef"), coef.data(), coef.size() * 4, cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaMemcpyAsync(plan->buf<uint32_t>("keys"), keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaMemcpyAsync(plan->buf<int>("slots"), slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+  plan->T = T;
+  plan->sampler_ready = true;
+  if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }
+  return SMD_OK;
+}
+
+// one reverse step; t < 0 means "read t from the device scalar t_ptr" (graph replay)
+static int reverse_step_impl(smd_plan* plan, const float* params, const float* x, int n, int t, const float* z,
+                             const float* infill_x, const float* infill_mask, const float* infill_z, float* x_next,
+                             float* eps_hat, float* collection, float* metrics, cudaStream_t st) {
+  float* tvec = plan->buf<float>("tvec");
+  int* t_ptr = plan->buf<int>("t_ptr");
+  const float* coef = plan->buf<float>("coef");
+  if (t >= 0) {
+    // conditioning value sqrt(alpha_prod_t), shared by every sample (utils/ebm_utils.py:367-369)
+    SMD_CUDA(cudaMemcpyAsync(tvec, coef + 8 * t + 5, 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    launch_fill_cond(coef, t_ptr, tvec, 1, st); CNT();
+  }
+  float* eh = eps_hat ? eps_hat : plan->buf<float>("eps_hat");
+  int rc = run_forward(plan, params, x, tvec, 1, n, eh, st, nullptr);
+  if (rc) return rc;
+  ReverseStepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.eps_hat = eh; a.z = z;
+  a.key_tab = plan->buf<uint32_t>("keys");
+  a.coef = coef;
+  a.slot_tab = plan->buf<int>("slots");
+  a.t_ptr = (t >= 0) ? nullptr : t_ptr;
+  a.t = t;
+  a.infill_x = infill_x; a.infill_mask = infill_mask; a.infill_z = infill_z;
+  a.x_next = x_next; a.collection = collection; a.metrics = metrics;
+  a.N = n; a.S = plan->cfg.seq_len; a.C = plan->cfg.channels; a.T = plan->T;
+  launch_reverse_step(a, st); CNT();
+  SMD_LAUNCH_CHECK("reverse_step");
+  return SMD_OK;
+}
+
+int smd_ddpm_reverse_step(smd_plan* plan, const float* params, const float* x, int n, int t, const float* z,
+                          const float* infill_x, const float* infill_mask, const float* infill_z, float* x_next,
+                          float* eps_hat_or_null, float* collection, float* metrics, smd_stream_t stream) {
+  if (!plan->sampler_ready) { set_error("smd_sampler_setup has not been called"); return SMD_ERR_STATE; }
+  if (t < 0 || t >= plan->T) { set_error("t out of range"); return SMD_ERR_INVALID; }
+  if (n < 1 || n > plan->cfg.max_batch) { set_error("n out of range"); return SMD_ERR_INVALID; }
+  return reverse_step_impl(plan, params, x, n, t, z, infill_x, infill_mask, infill_z, x_next, eps_hat_or_null,
+                           collection, metrics, static_cast<cudaStream_t>(stream));
+}
+
+int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int steps, const float* infill_x,
+                    const float* infill_mask, float* collection, float* metrics, int use_graph,
+                    smd_stream_t stream) {
+  if (!plan->sampler_ready) { set_error("smd_sampler_setup has not been called"); return SMD_ERR_STATE; }
+  if (n < 1 || n > plan->cfg.max_batch) { set_error("n out of range"); return SMD_ERR_INVALID; }
+  if (steps < 1 || steps > plan->T) { set_error("steps out of range"); return SMD_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = plan->T;
+  if (metrics) SMD_CUDA(cudaMemsetAsync(metrics, 0, sizeof(float) * 4 * T, st));
+  if (!use_graph) {
+    for (int i = 0; i < steps; ++i) {
+      int rc = reverse_step_impl(plan, params, x, n, T - 1 - i, nullptr, infill_x, infill_mask, nullptr, x, nullptr,
+                                 collection, metrics, st);
+      if (rc) return rc;
+    }
+    return SMD_OK;
+  }
+  int* t_ptr = plan->buf<int>("t_ptr");
+  const int t0 = T - 1;
+  SMD_CUDA(cudaMemcpyAsync(t_ptr, &t0, sizeof(int), cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaStreamSynchronize(st));  // t0 is a stack variable
+  const bool same = plan->graph_exec && plan->graph_n == n && plan->graph_params == params && plan->graph_x == x &&
+                    plan->graph_infill_x == infill_x && plan->graph_infill_mask == infill_mask &&
+                    plan->graph_collection == collection && plan->graph_metrics == metrics;
+  if (!same) {
+    if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches.load();
+    SMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = reverse_step_impl(plan, params, x, n, -1, nullptr, infill_x, infill_mask, nullptr, x, nullptr,
+                               collection, metrics, st);
+    if (rc == SMD_OK) { launch_step_advance(t_ptr, st); CNT(); }
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return SMD_ERR_CUDA; }
+    plan->graph_nodes = g_launches.load() - before;
+    g_launches.store(before);  // captured launches are counted per replay below
+    SMD_CUDA(cudaGraphInstantiate(&plan->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    plan->graph_n = n; plan->graph_params = params; plan->graph_x = x; plan->graph_infill_x = infill_x;
+    plan->graph_infill_mask = infill_mask; plan->graph_collection = collection; plan->graph_metrics = metrics;
+  }
+  for (int i = 0; i < steps; ++i) {
+    SMD_CUDA(cudaGraphLaunch(plan->graph_exec, st));
+    g_launches.fetch_add(plan->graph_nodes, std::memory_order_relaxed);
+  }
+  return SMD_OK;
+}
+
+int smd_threefry_normal(const uint32_t host_key[2], float* out, long long n, smd_stream_t stream) {
+  if (n < 0 || n > 0xFFFFFFFFll) { set_error("n out of range"); return SMD_ERR_INVALID; }
+  if (n == 0) return SMD_OK;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  threefry_normal_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(host_key[0], host_key[1], out,
+                                                                                static_cast<uint32_t>(n));
+  CNT();
+  SMD_LAUNCH_CHECK("threefry_normal");
+  return SMD_OK;
+}
+int smd_threefry_split(const uint32_t host_key[2], int num, uint32_t* host_out_keys) {
+  if (num < 1) { set_error("num must be >= 1"); return SMD_ERR_INVALID; }
+  h_split(host_key, num, host_out_keys);
+  return SMD_OK;
+}
+
+int smd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, int b_mn, int BN, int cta_group,
+                  const float* bias, const float* residual, int act, float* out_f32, void* out_bf16,
+                  float* row_stats, const float* ln_gamma, const float* ln_beta, smd_stream_t stream) {
+  GemmOp op;
+  if (BN <= 0) BN = choose_bn(N, cta_group);
+  if (!make_gemm_op(&op, A, static_cast<uint64_t>(M), B, static_cast<uint64_t>(N), N, K, BN, cta_group, a_mn, b_mn))
+    return SMD_ERR_CUDA;
+  GemmEpilogue e = epi();
+  e.bias = bias; e.residual = residual; e.ld_res = N; e.act = act;
+  e.out_f32 = out_f32; e.ld_f32 = N;
+  e.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); e.ld_bf16 = N;
+  e.row_stats = row_stats; e.ln_gamma = ln_gamma; e.ln_beta = ln_beta;
+  SMD_CUDA(launch_gemm(op, M, e, static_cast<cudaStream_t>(stream)));
+  SMD_LAUNCH_CHECK("gemm");
+  return SMD_OK;
+}
+
+}  // extern "C"

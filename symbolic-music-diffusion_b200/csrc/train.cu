@@ -1,0 +1,155 @@
+// Training-side pieces of libsmd: saved-activation workspace, fused clip + Adam (+EMA), EMA update.
+// (The backward pass itself lives in backward.cu.)
+#include "train.cuh"
+#include "kernels.cuh"
+
+namespace smd {
+
+void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
+                     const std::function<size_t(const std::string&, size_t)>& add) {
+  ts.enabled = true;
+  ts.L = (c.arch == SMD_ARCH_TRANSFORMER_DDPM) ? c.num_layers : 0;
+  ts.K = K; ts.H = c.num_heads; ts.Md = c.mlp_dims; ts.C = c.channels; ts.S = c.seq_len; ts.B = c.max_batch;
+  ts.Mp = static_cast<size_t>(Mp);
+  const size_t M = ts.Mp, Md = c.mlp_dims, B = c.max_batch;
+  const size_t Cp = (static_cast<size_t>(c.channels) + 63) / 64 * 64;
+  auto nm = [](const char* base, int i) { return std::string("t.") + base + std::to_string(i); };
+  for (int i = 0; i < 2 * ts.L + 1; ++i) ts.off_h.push_back(add(nm("h", i), M * kEt * 4));
+  for (int l = 0; l < ts.L; ++l) {
+    ts.off_a1.push_back(add(nm("a1_", l), M * kEt * 2));
+    ts.off_a2.push_back(add(nm("a2_", l), M * kEt * 2));
+    ts.off_qkv.push_back(add(nm("qkv", l), M * 3 * kEt * 4));
+    ts.off_probs.push_back(add(nm("probs", l), B * c.num_heads * 32 * 32 * 4));
+    ts.off_o.push_back(add(nm("o", l), M * kEt * 2));
+    ts.off_hidden_pre.push_back(add(nm("hpre", l), M * Md * 2));
+    ts.off_hidden.push_back(add(nm("hid", l), M * Md * 2));
+  }
+  if (ts.L) ts.off_a_post = add("t.a_post", M * kEt * 2);
+  for (int k = 0; k < K + 1; ++k) ts.off_u.push_back(add(nm("u", k), M * Md * 4));
+  for (int k = 0; k < K; ++k) {
+    ts.off_r1.push_back(add(nm("r1_", k), M * Md * 4));
+    ts.off_act_a.push_back(add(nm("acta", k), M * Md * 2));
+    ts.off_act_b.push_back(add(nm("actb", k), M * Md * 2));
+    ts.off_e1pre.push_back(add(nm("e1pre", k), B * 512 * 4));
+    ts.off_e1.push_back(add(nm("e1_", k), B * 512 * 4));
+    ts.off_e2.push_back(add(nm("e2_", k), B * 512 * 4));
+  }
+  ts.off_act_out = add("t.act_out", M * Md * 2);
+  ts.off_g32a = add("t.g32a", M * Md * 4);
+  ts.off_g32b = add("t.g32b", M * Md * 4);
+  ts.off_g16a = add("t.g16a", M * Md * 2);
+  ts.off_g16b = add("t.g16b", M * Md * 2);
+  ts.off_dh = add("t.dh", M * kEt * 4);
+  ts.off_dh2 = add("t.dh2", M * kEt * 4);
+  ts.off_dh16 = add("t.dh16", M * kEt * 2);
+  ts.off_dqkv16 = add("t.dqkv16", M * 3 * kEt * 2);
+  ts.off_dqkv32 = add("t.dqkv32", M * 3 * kEt * 4);
+  ts.off_dpred16 = add("t.dpred16", M * Cp * 2);
+  ts.off_dpred32 = add("t.dpred32", M * c.channels * 4);
+  ts.off_dss = add("t.dss", B * 2 * Md * 4);
+  ts.off_de = add("t.de", B * 512 * 4);
+  ts.off_de2 = add("t.de2", B * 512 * 4);
+  ts.off_loss = add("t.loss", B * 4);
+  // plain (in,out) bf16 weight copies: the K-major B operand of every dX GEMM
+  for (int l = 0; l < ts.L; ++l) {
+    ts.off_w_qkv.push_back(add(nm("wqkv", l), kEt * 3 * kEt * 2));
+    ts.off_w_o.push_back(add(nm("wo", l), kEt * kEt * 2));
+    ts.off_w_ffn1.push_back(add(nm("wffn1_", l), kEt * Md * 2));
+    ts.off_w_ffn2.push_back(add(nm("wffn2_", l), Md * kEt * 2));
+  }
+  if (ts.L) ts.off_w_post = add("t.wpost", kEt * Md * 2);
+  else ts.off_w_in = add("t.win", Cp * Md * 2);
+  for (int k = 0; k < K; ++k) {
+    ts.off_w_a.push_back(add(nm("wa", k), Md * Md * 2));
+    ts.off_w_b.push_back(add(nm("wb", k), Md * Md * 2));
+  }
+  ts.off_w_out = add("t.wout", Md * Cp * 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused global-norm clip + Adam (+ EMA)        (train_ncsn.py:284-287, flax.optim.Adam, train_utils.py:73-78)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float s = 0.f;
+  const long long n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) s += g[i] * g[i];
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int j = 0; j < 8; ++j) v += red[j];
+    atomicAdd(out, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 float* __restrict__ ema, long long n, float lr, float max_norm, float b1, float b2, float eps,
+                 float bc1, float bc2, float mu, const float* __restrict__ sumsq, float* __restrict__ gnorm_out) {
+  const float norm = sqrtf(*sumsq);
+  // jax.experimental.optimizers.clip_grads: g if norm < max else g * (max / norm)
+  const float factor = (norm < max_norm) ? 1.0f : (max_norm / norm);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && gnorm_out) *gnorm_out = norm * factor;  // post-clip norm (train_ncsn.py:285)
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * factor;
+    const float mi = (1.0f - b1) * gi + b1 * m[i];
+    const float vi = (1.0f - b2) * gi * gi + b2 * v[i];
+    m[i] = mi; v[i] = vi;
+    const float mh = mi / bc1, vh = vi / bc2;
+    const float pi = p[i] - lr * mh / (sqrtf(vh) + eps);
+    p[i] = pi;
+    if (ema) ema[i] = ema[i] * mu + pi * (1.0f - mu);
+  }
+}
+
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, long long n, float mu) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    ema[i] = ema[i] * mu + p[i] * (1.0f - mu);
+}
+
+}  // namespace smd
+
+using namespace smd;
+
+extern "C" {
+
+int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, float* ema_or_null, long long n,
+                  float lr, int step, float max_norm, float beta1, float beta2, float eps, float ema_mu,
+                  float* scratch, float* grad_norm_out, smd_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n <= 0 || !scratch) { set_error("bad arguments"); return SMD_ERR_INVALID; }
+  if (cudaMemsetAsync(scratch, 0, sizeof(float), st) != cudaSuccess) { set_error("memset failed"); return SMD_ERR_CUDA; }
+  const int blocks = 148 * 8;
+  sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, scratch);
+  g_launches.fetch_add(1);
+  const double t = static_cast<double>(step) + 1.0;
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), t));
+  clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, adam_m, adam_v, ema_or_null, n, lr, max_norm, beta1, beta2,
+                                           eps, bc1, bc2, ema_mu, scratch, grad_norm_out);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("clip_adam: ") + cudaGetErrorString(e)); return SMD_ERR_CUDA; }
+  return SMD_OK;
+}
+
+int smd_ema_update(float* ema, const float* params, long long n, float mu, smd_stream_t stream) {
+  ema_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(ema, params, n, mu);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("ema: ") + cudaGetErrorString(e)); return SMD_ERR_CUDA; }
+  return SMD_OK;
+}
+
+}  // extern "C"

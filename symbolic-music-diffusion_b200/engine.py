@@ -1,0 +1,238 @@
+"""Host-side driver of libsmd: owns the plan, the device workspace and the flat fp32 parameter arena.
+
+PyTorch is used only as the device-memory / stream provider; all compute goes through the C ABI
+(include/smd.h).  Everything here raises if CUDA or libsmd.so is unavailable -- no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, asdict
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+ARCHS = {"TransformerDDPM": 0, "TransformerDDPM4": 0, "DenseDDPM": 1}
+
+
+@dataclass
+class ModelConfig:
+    """Keyword surface of the reference score networks (models/ncsn.py:125,141-147; train_ncsn.py:321-326)."""
+    arch: str = "TransformerDDPM"
+    num_layers: int = 6
+    num_heads: int = 8
+    num_mlp_layers: int = 2
+    mlp_dims: int = 2048
+    seq_len: int = 32
+    channels: int = 42
+
+    def flops_fwd_per_sample(self) -> float:
+        """Algorithmic forward FLOPs per sample."""
+        E, S, C, M = 128, self.seq_len, self.channels, self.mlp_dims
+        if ARCHS[self.arch] == 0:
+            L, K = self.num_layers, self.num_mlp_layers
+            mac_tok = C * E + L * (4 * E * E + 2 * S * E + 2 * E * M) + E * M + K * 2 * M * M + M * C
+        else:
+            K = self.num_layers
+            mac_tok = C * M + K * 2 * M * M + M * C
+        mac_film = K * (128 * 512 + 512 * 512 + 2 * 512 * M)
+        return 2.0 * (S * mac_tok + mac_film)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous float32 CUDA tensor")
+    return t
+
+
+class Engine:
+    def __init__(self, cfg: ModelConfig, max_batch: int, cta_group: int = 2, training: bool = False,
+                 device: Optional[str] = None):
+        if cfg.arch not in ARCHS:
+            raise ValueError(f"unknown architecture {cfg.arch!r}")
+        self.cfg = cfg
+        self.max_batch = int(max_batch)
+        self.lib = _lib.load_library()
+        c = _lib.SmdConfig(ARCHS[cfg.arch], cfg.num_layers, cfg.num_heads, cfg.num_mlp_layers, cfg.mlp_dims,
+                           cfg.seq_len if ARCHS[cfg.arch] == 0 else 1, cfg.channels, self.max_batch,
+                           int(cta_group), int(training))
+        h = C.c_void_p()
+        _lib.check(self.lib.smd_plan_create(C.byref(c), C.byref(h)))
+        self._plan = h
+        self.seq_len = cfg.seq_len if ARCHS[cfg.arch] == 0 else 1
+        self.training = bool(training)
+        self.layout: List[Tuple[str, int, Tuple[int, ...]]] = []
+        name = C.create_string_buffer(128)
+        off = C.c_longlong()
+        shape = (C.c_int * 4)()
+        nd = C.c_int()
+        for i in range(self.lib.smd_num_tensors(h)):
+            _lib.check(self.lib.smd_tensor_info(h, i, name, 128, C.byref(off), shape, C.byref(nd)))
+            self.layout.append((name.value.decode(), int(off.value), tuple(shape[j] for j in range(nd.value))))
+        self.arena_floats = int(self.lib.smd_arena_floats(h))
+        self.workspace_bytes = int(self.lib.smd_workspace_bytes(h))
+        self.device = device
+        self._ws: Optional[torch.Tensor] = None
+        self.params: Optional[torch.Tensor] = None
+        self._sampler_T = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self.lib.smd_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameter arena (host side)
+    @property
+    def num_params(self) -> int:
+        return int(sum(int(np.prod(s)) for _, _, s in self.layout))
+
+    def init_params(self, seed: int = 0, perturb: float = 0.0) -> np.ndarray:
+        """flax.nn 0.3.0 default initialisers (Dense: lecun_normal kernel / zero bias; LayerNorm: ones / zeros).
+
+        Same distributions as the reference, own RNG stream (seed-level init parity with flax is unpinned).
+        ``perturb`` adds N(0, perturb) to every bias and LayerNorm parameter so tests exercise those paths.
+        """
+        rng = np.random.default_rng(seed)
+        flat = np.zeros((self.arena_floats,), np.float32)
+        for name, off, shape in self.layout:
+            n = int(np.prod(shape))
+            if name.endswith(".kernel"):
+                fan_in = shape[0]
+                std = np.sqrt(1.0 / fan_in) / 0.87962566103423978
+                v = rng.standard_normal(n * 2)
+                v = v[np.abs(v) <= 2.0][:n]
+                while v.size < n:  # pragma: no cover
+                    extra = rng.standard_normal(n)
+                    v = np.concatenate([v, extra[np.abs(extra) <= 2.0]])[:n]
+                val = (v * std).astype(np.float32)
+            elif name.endswith(".scale"):
+                val = np.ones((n,), np.float32)
+            else:
+                val = np.zeros((n,), np.float32)
+            if perturb and not name.endswith(".kernel"):
+                val = val + rng.normal(0.0, perturb, n).astype(np.float32)
+            flat[off:off + n] = val
+        return flat
+
+    def flat_to_dict(self, flat) -> Dict[str, np.ndarray]:
+        flat = flat.detach().cpu().numpy() if isinstance(flat, torch.Tensor) else np.asarray(flat)
+        return {name: flat[off:off + int(np.prod(shape))].reshape(shape).copy() for name, off, shape in self.layout}
+
+    def dict_to_flat(self, d: Dict[str, np.ndarray]) -> np.ndarray:
+        flat = np.zeros((self.arena_floats,), np.float32)
+        for name, off, shape in self.layout:
+            flat[off:off + int(np.prod(shape))] = np.asarray(d[name], np.float32).reshape(-1)
+        return flat
+
+    # ------------------------------------------------------------------ device side
+    def _stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def _ensure_ws(self) -> None:
+        if self._ws is not None:
+            return
+        if not torch.cuda.is_available():
+            raise _lib.SmdError("CUDA device required (libsmd has no CPU fallback)")
+        dev = self.device or f"cuda:{torch.cuda.current_device()}"
+        self._ws = torch.empty(self.workspace_bytes + 1024, dtype=torch.uint8, device=dev)
+        base = self._ws.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        _lib.check(self.lib.smd_bind_workspace(self._plan, aligned, self.workspace_bytes))
+
+    def set_params(self, flat) -> torch.Tensor:
+        """Upload (or adopt) the fp32 arena and refresh the bf16 tensor-core operand copies."""
+        self._ensure_ws()
+        if isinstance(flat, np.ndarray):
+            flat = torch.from_numpy(np.ascontiguousarray(flat, np.float32))
+        if flat.numel() != self.arena_floats:
+            raise ValueError("parameter arena has the wrong size")
+        if not flat.is_cuda:
+            flat = flat.to(self._ws.device)
+        self.params = _f32c(flat, "params")
+        self.repack()
+        return self.params
+
+    def repack(self) -> None:
+        _lib.check(self.lib.smd_pack_weights(self._plan, self.params.data_ptr(), self._stream()))
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """eps_hat = model(x, t); t has one value per example, or a single value (broadcast)."""
+        x = _f32c(x, "x")
+        batch = x.shape[0]
+        t = _f32c(t.reshape(-1), "t")
+        bcast = 1 if (t.numel() == 1 and batch > 1) else 0
+        if not bcast and t.numel() != batch:
+            raise ValueError("t must hold one value per example")
+        y = torch.empty_like(x) if out is None else _f32c(out, "out")
+        _lib.check(self.lib.smd_forward(self._plan, self.params.data_ptr(), x.data_ptr(), t.data_ptr(), bcast, batch,
+                                        y.data_ptr(), self._stream()))
+        return y
+
+    def ddpm_loss(self, x0: torch.Tensor, used_alpha: torch.Tensor, eps: torch.Tensor, want_pred: bool = False):
+        x0 = _f32c(x0, "x0"); eps = _f32c(eps, "eps"); ua = _f32c(used_alpha.reshape(-1), "used_alpha")
+        batch = x0.shape[0]
+        loss = torch.empty((batch,), dtype=torch.float32, device=x0.device)
+        pred = torch.empty_like(x0) if want_pred else None
+        _lib.check(self.lib.smd_ddpm_loss(self._plan, self.params.data_ptr(), x0.data_ptr(), ua.data_ptr(),
+                                          eps.data_ptr(), batch, loss.data_ptr(), _ptr(pred), self._stream()))
+        return (loss, pred) if want_pred else loss
+
+    def ddpm_grads(self, x0, used_alpha, eps, grads: torch.Tensor, loss_sum: torch.Tensor, global_batch=None):
+        x0 = _f32c(x0, "x0"); eps = _f32c(eps, "eps"); ua = _f32c(used_alpha.reshape(-1), "used_alpha")
+        batch = x0.shape[0]
+        _lib.check(self.lib.smd_ddpm_grads(self._plan, self.params.data_ptr(), x0.data_ptr(), ua.data_ptr(),
+                                           eps.data_ptr(), batch, int(global_batch or batch), grads.data_ptr(),
+                                           loss_sum.data_ptr(), self._stream()))
+
+    def clip_adam(self, grads, m, v, lr: float, step: int, max_norm: float, scratch, gnorm, ema=None,
+                  beta1=0.9, beta2=0.999, eps=1e-8, mu=0.999):
+        _lib.check(self.lib.smd_clip_adam(self.params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                          _ptr(ema), self.arena_floats, float(lr), int(step), float(max_norm),
+                                          float(beta1), float(beta2), float(eps), float(mu), scratch.data_ptr(),
+                                          gnorm.data_ptr(), self._stream()))
+
+    # ------------------------------------------------------------------ sampler
+    def sampler_setup(self, betas: np.ndarray, key=(0, 0)) -> None:
+        self._ensure_ws()
+        b = np.ascontiguousarray(betas, np.float32)
+        k = (C.c_uint32 * 2)(int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF)
+        _lib.check(self.lib.smd_sampler_setup(self._plan, b.ctypes.data_as(C.POINTER(C.c_float)), len(b), k,
+                                              self._stream()))
+        self._sampler_T = len(b)
+
+    def reverse_step(self, x, t: int, z=None, infill_x=None, infill_mask=None, infill_z=None, x_next=None,
+                     eps_hat=None, collection=None, metrics=None):
+        x = _f32c(x, "x")
+        x_next = torch.empty_like(x) if x_next is None else x_next
+        _lib.check(self.lib.smd_ddpm_reverse_step(self._plan, self.params.data_ptr(), x.data_ptr(), x.shape[0],
+                                                  int(t), _ptr(z), _ptr(infill_x), _ptr(infill_mask), _ptr(infill_z),
+                                                  x_next.data_ptr(), _ptr(eps_hat), _ptr(collection), _ptr(metrics),
+                                                  self._stream()))
+        return x_next
+
+    def sample(self, x, steps: Optional[int] = None, infill_x=None, infill_mask=None, collection=None,
+               metrics=None, use_graph: bool = True):
+        """Runs `steps` reverse steps in place on x (n, S, C)."""
+        x = _f32c(x, "x")
+        steps = self._sampler_T if steps is None else int(steps)
+        _lib.check(self.lib.smd_ddpm_sample(self._plan, self.params.data_ptr(), x.data_ptr(), x.shape[0], steps,
+                                            _ptr(infill_x), _ptr(infill_mask), _ptr(collection), _ptr(metrics),
+                                            1 if use_graph else 0, self._stream()))
+        return x
+
+    def launch_count(self) -> int:
+        return int(self.lib.smd_launch_count())
+
+    def describe(self) -> dict:
+        d = asdict(self.cfg)
+        d.update(params=self.num_params, arena_floats=self.arena_floats, workspace_mb=self.workspace_bytes / 2 ** 20)
+        return d
