@@ -124,6 +124,11 @@ int smd_threefry_split(const uint32_t host_key[2], int num, uint32_t* host_out_k
 int smd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, int b_mn, int BN, int cta_group,
                   const float* bias, const float* residual, int act, float* out_f32, void* out_bf16,
                   float* row_stats, const float* ln_gamma, const float* ln_beta, smd_stream_t stream);
+/* forward pass that keeps every intermediate in the training save buffers (plan must have training = 1) */
+int smd_debug_forward_save(smd_plan* plan, const float* params, const float* x, const float* t, int batch, float* y,
+                           smd_stream_t stream);
+/* device pointer / size of a named workspace region (names: DESIGN.md "Workspace"), for stage-by-stage parity */
+int smd_debug_buffer(smd_plan* plan, const char* name, void** dev_ptr, size_t* bytes);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long smd_launch_count(void);
 

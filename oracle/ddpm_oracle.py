@@ -144,8 +144,13 @@ def dense_res_block(x: Tensor, scale: Tensor, shift: Tensor, p: Dict[str, Tensor
 
 def transformer_ddpm(p: Dict[str, Tensor], inputs: Tensor, t: Tensor, num_layers: int = 6,
                      num_heads: int = 8, num_mlp_layers: int = 2, mlp_dims: int = 2048,
-                     emulate_bf16: bool = False) -> Tensor:
-    """models/ncsn.py:138-179 (TransformerDDPM.apply). inputs (B,S,C), t (B,1,1) or (B,)."""
+                     emulate_bf16: bool = False, trace: Optional[dict] = None) -> Tensor:
+    """models/ncsn.py:138-179 (TransformerDDPM.apply). inputs (B,S,C), t (B,1,1) or (B,).
+
+    ``trace`` (tests only) collects the intermediate tensors under the CUDA workspace names."""
+    def rec(name, val):
+        if trace is not None:
+            trace[name] = val.detach().clone()
     B, S, C = inputs.shape
     E = 128
     dt = inputs.dtype
@@ -153,26 +158,38 @@ def transformer_ddpm(p: Dict[str, Tensor], inputs: Tensor, t: Tensor, num_layers
     # NB: the C->128 input projection is SIMT fp32 on the CUDA path (never bf16).
     x = dense(inputs, p["in.kernel"], p["in.bias"])
     x = x + temb
+    rec("t.h0", x)
     for l in range(num_layers):
         pre = f"l{l}."
         sc = x
         a = layer_norm(x, p[pre + "ln1.scale"], p[pre + "ln1.bias"])
+        rec(f"t.a1_{l}", a)
         a = self_attention(a, p, pre + "attn.", num_heads, emulate_bf16)
         x = a + sc
+        rec(f"t.h{2 * l + 1}", x)
         sc2 = x
         m = layer_norm(x, p[pre + "ln2.scale"], p[pre + "ln2.bias"])
+        rec(f"t.a2_{l}", m)
         m = dense(m, p[pre + "ffn1.kernel"], p[pre + "ffn1.bias"], emulate_bf16)
+        rec(f"t.hpre{l}", m)
         m = gelu_tanh(m)
+        rec(f"t.hid{l}", m)
         m = dense(m, p[pre + "ffn2.kernel"], p[pre + "ffn2.bias"], emulate_bf16)
         x = m + sc2
+        rec(f"t.h{2 * l + 2}", x)
     x = layer_norm(x, p["post_ln.scale"], p["post_ln.bias"])
+    rec("t.a_post", x)
     x = dense(x, p["post.kernel"], p["post.bias"], emulate_bf16)
+    rec("t.u0", x)
     tt = t.reshape(B)
     for k in range(num_mlp_layers):
         pre = f"k{k}."
         scale, shift = dense_film(tt, p, pre + "film.")
+        rec(f"ss{k}", torch.cat([scale, shift], dim=-1))
         x = dense_res_block(x, scale[:, None, :], shift[:, None, :], p, pre + "res.", emulate_bf16)
+        rec(f"t.u{k + 1}", x)
     x = layer_norm(x, p["out_ln.scale"], p["out_ln.bias"])
+    rec("t.act_out", x)
     x = dense(x, p["out.kernel"], p["out.bias"], emulate_bf16)
     return x
 

@@ -1,0 +1,543 @@
+// SIMT kernels of the hand-written backward pass (what jax.value_and_grad derives for train_ncsn.py:282-283;
+// contract per op in SURVEY Appendix E).
+#pragma once
+#include "kernels.cuh"
+
+namespace smd {
+
+// ---------------------------------------------------------------------------------------------------
+// wide LayerNorm + FiLM + swish backward (models/shared.py:62-64 / 66-68), one CTA per 32 rows
+// ---------------------------------------------------------------------------------------------------
+struct LnFilmBwdArgs {
+  const float* g;        // [M][N] gradient wrt the bf16 activation that fed the GEMM
+  const float* u;        // [M][N] LayerNorm input
+  const float* stats;    // [M][2] (sum, sumsq) of u rows
+  const float* gamma;    // [N]
+  const float* beta;     // [N]
+  const float* ss;       // FiLM [nsamples][2N] = [scale | shift], or null (plain LayerNorm)
+  int act;               // 2: swish, 0: none
+  const float* dres;     // [M][N] residual-path gradient added to dx, or null (may alias dx32)
+  float* dx32;           // [M][N]
+  __nv_bfloat16* dx16;   // [M][N] or null
+  float* dgamma;         // [N] (atomics)
+  float* dbeta;          // [N]
+  float* dbias;          // [N] += column sums of the dx32 written here, or null
+  float* dss;            // [nsamples][2N] gradient of [scale | shift], or null
+  int dss_accum;         // 0: overwrite, 1: add (second use of the same FiLM pair)
+  int M, N, S;           // S in {1, 32}: rows per sample
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
+  __shared__ float red[2][8][2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * 32;
+  const int N = a.N;
+  const float inv_n = 1.0f / static_cast<float>(N);
+  const bool film = a.ss != nullptr;
+  float gam[NCH][4], bet[NCH][4], sc[NCH][4], sh[NCH][4];
+  float acc_dg[NCH][4], acc_db[NCH][4], acc_bias[NCH][4], acc_dsc[NCH][4], acc_dsh[NCH][4];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c = tid * 4 + 1024 * j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc_dg[j][i] = acc_db[j][i] = acc_bias[j][i] = acc_dsc[j][i] = acc_dsh[j][i] = 0.f;
+      gam[j][i] = (c < N) ? a.gamma[c + i] : 0.f;
+      bet[j][i] = (c < N) ? a.beta[c + i] : 0.f;
+      sc[j][i] = 1.f; sh[j][i] = 0.f;
+    }
+  }
+  const bool per_block_sample = (a.S == 32);
+  if (film && per_block_sample) {
+    const float* sp = a.ss + static_cast<size_t>(r0 / 32) * 2 * N;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c = tid * 4 + 1024 * j;
+      if (c < N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sc[j][i] = sp[c + i]; sh[j][i] = sp[N + c + i]; }
+      }
+    }
+  }
+  for (int r = 0; r < 32; ++r) {
+    const int row = r0 + r;
+    const bool ok = row < a.M;   // block-uniform
+    float dxh[NCH][4], xh[NCH][4];
+    float p1 = 0.f, p2 = 0.f, rstd = 0.f;
+    if (ok) {
+      const float s1 = a.stats[2 * static_cast<size_t>(row)], s2 = a.stats[2 * static_cast<size_t>(row) + 1];
+      const float mean = s1 * inv_n;
+      rstd = rsqrtf(s2 * inv_n - mean * mean + 1e-6f);
+      if (film && !per_block_sample) {
+        const float* sp = a.ss + static_cast<size_t>(row / a.S) * 2 * N;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int c = tid * 4 + 1024 * j;
+          if (c < N) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sc[j][i] = sp[c + i]; sh[j][i] = sp[N + c + i]; }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int c = tid * 4 + 1024 * j;
+        if (c < N) {
+          const float4 g4 = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
+          const float4 u4 = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+          const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+          float dsc_row[4], dsh_row[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x = (uu[i] - mean) * rstd;
+            const float yln = x * gam[j][i] + bet[j][i];
+            const float f = film ? (sc[j][i] * yln + sh[j][i]) : yln;
+            const float dact = (a.act == 2) ? gg[i] * swish_grad(f) : gg[i];
+            const float dyln = film ? dact * sc[j][i] : dact;
+            dsh_row[i] = dact; dsc_row[i] = dact * yln;
+            acc_db[j][i] += dyln;
+            acc_dg[j][i] += dyln * x;
+            const float d = dyln * gam[j][i];
+            dxh[j][i] = d; xh[j][i] = x;
+            p1 += d; p2 += d * x;
+          }
+          if (film) {
+            if (per_block_sample) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { acc_dsc[j][i] += dsc_row[i]; acc_dsh[j][i] += dsh_row[i]; }
+            } else if (a.dss) {
+              float* dp = a.dss + static_cast<size_t>(row / a.S) * 2 * N;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (a.dss_accum) { dp[c + i] += dsc_row[i]; dp[N + c + i] += dsh_row[i]; }
+                else { dp[c + i] = dsc_row[i]; dp[N + c + i] = dsh_row[i]; }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { dxh[j][i] = 0.f; xh[j][i] = 0.f; }
+        }
+      }
+    }
+    p1 = warp_sum(p1); p2 = warp_sum(p2);
+    if (lane == 0) { red[r & 1][warp][0] = p1; red[r & 1][warp][1] = p2; }
+    __syncthreads();
+    if (ok) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { t1 += red[r & 1][w][0]; t2 += red[r & 1][w][1]; }
+      const float m1 = t1 * inv_n, m2 = t2 * inv_n;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int c = tid * 4 + 1024 * j;
+        if (c < N) {
+          float dx[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dx[i] = rstd * (dxh[j][i] - m1 - xh[j][i] * m2);
+          if (a.dres) {
+            const float4 d4 = *reinterpret_cast<const float4*>(a.dres + static_cast<size_t>(row) * N + c);
+            dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc_bias[j][i] += dx[i];
+          *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * N + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+          if (a.dx16) {
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(dx[0], dx[1]);
+            __nv_bfloat162 q1 = __floats2bfloat162_rn(dx[2], dx[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&q0);
+            pk.y = *reinterpret_cast<uint32_t*>(&q1);
+            *reinterpret_cast<uint2*>(a.dx16 + static_cast<size_t>(row) * N + c) = pk;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c = tid * 4 + 1024 * j;
+    if (c < N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(a.dgamma + c + i, acc_dg[j][i]);
+        atomicAdd(a.dbeta + c + i, acc_db[j][i]);
+        if (a.dbias) atomicAdd(a.dbias + c + i, acc_bias[j][i]);
+      }
+      if (film && per_block_sample && a.dss && r0 < a.M) {
+        float* dp = a.dss + static_cast<size_t>(r0 / 32) * 2 * N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (a.dss_accum) { dp[c + i] += acc_dsc[j][i]; dp[N + c + i] += acc_dsh[j][i]; }
+          else { dp[c + i] = acc_dsc[j][i]; dp[N + c + i] = acc_dsh[j][i]; }
+        }
+      }
+    }
+  }
+}
+
+inline void launch_ln_film_act_bwd(const LnFilmBwdArgs& a, cudaStream_t st) {
+  const int blocks = (a.M + 31) / 32;
+  const int nch = (a.N + 1023) / 1024;
+  if (nch == 1) ln_film_act_bwd_kernel<1><<<blocks, 256, 0, st>>>(a);
+  else if (nch == 2) ln_film_act_bwd_kernel<2><<<blocks, 256, 0, st>>>(a);
+  else if (nch == 3) ln_film_act_bwd_kernel<3><<<blocks, 256, 0, st>>>(a);
+  else ln_film_act_bwd_kernel<4><<<blocks, 256, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// narrow (128-wide) LayerNorm backward, one warp per row; statistics recomputed from the saved input
+// ---------------------------------------------------------------------------------------------------
+struct Ln128BwdArgs {
+  const float* g;       // [M][128] gradient wrt the LayerNorm output
+  const float* h;       // [M][128] LayerNorm input
+  const float* gamma;   // [128]
+  const float* dres;    // [M][128] or null (may alias dx32)
+  float* dx32;          // [M][128]
+  __nv_bfloat16* dx16;  // [M][128] or null
+  float* dgamma; float* dbeta;   // [128] atomics
+  float* dbias;         // [128] += column sums of dx32, or null
+  int M;
+};
+
+__global__ void __launch_bounds__(256) ln128_bwd_kernel(const Ln128BwdArgs a) {
+  __shared__ float red[3][8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+  const int c = lane * 4;
+  const float4 gm = *reinterpret_cast<const float4*>(a.gamma + c);
+  const float gam[4] = {gm.x, gm.y, gm.z, gm.w};
+  float adg[4] = {0, 0, 0, 0}, adb[4] = {0, 0, 0, 0}, abias[4] = {0, 0, 0, 0};
+  for (int row = gw; row < a.M; row += nw) {
+    const float4 h4 = *reinterpret_cast<const float4*>(a.h + static_cast<size_t>(row) * 128 + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * 128 + c);
+    const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float s1 = hh[0] + hh[1] + hh[2] + hh[3];
+    float s2 = hh[0] * hh[0] + hh[1] * hh[1] + hh[2] * hh[2] + hh[3] * hh[3];
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const float mean = s1 * (1.0f / 128.0f);
+    const float rstd = rsqrtf(s2 * (1.0f / 128.0f) - mean * mean + 1e-6f);
+    float xh[4], dxh[4], p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      xh[i] = (hh[i] - mean) * rstd;
+      adb[i] += gg[i];
+      adg[i] += gg[i] * xh[i];
+      dxh[i] = gg[i] * gam[i];
+      p1 += dxh[i]; p2 += dxh[i] * xh[i];
+    }
+    p1 = warp_sum(p1) * (1.0f / 128.0f); p2 = warp_sum(p2) * (1.0f / 128.0f);
+    float dx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dx[i] = rstd * (dxh[i] - p1 - xh[i] * p2);
+    if (a.dres) {
+      const float4 d4 = *reinterpret_cast<const float4*>(a.dres + static_cast<size_t>(row) * 128 + c);
+      dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) abias[i] += dx[i];
+    *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * 128 + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+    if (a.dx16) {
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(dx[0], dx[1]);
+      __nv_bfloat162 q1 = __floats2bfloat162_rn(dx[2], dx[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&q0);
+      pk.y = *reinterpret_cast<uint32_t*>(&q1);
+      *reinterpret_cast<uint2*>(a.dx16 + static_cast<size_t>(row) * 128 + c) = pk;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { red[0][warp][c + i] = adg[i]; red[1][warp][c + i] = adb[i]; red[2][warp][c + i] = abias[i]; }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 3 * 128; idx += blockDim.x) {
+    const int k = idx / 128, col = idx % 128;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[k][w][col];
+    if (k == 0) atomicAdd(a.dgamma + col, v);
+    else if (k == 1) atomicAdd(a.dbeta + col, v);
+    else if (a.dbias) atomicAdd(a.dbias + col, v);
+  }
+}
+inline void launch_ln128_bwd(const Ln128BwdArgs& a, cudaStream_t st) {
+  int blocks = (a.M + 7) / 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  ln128_bwd_kernel<<<blocks, 256, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] += sum_m in[m][n]
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int M, int N) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int m0 = blockIdx.y * 256, m1 = min(M, m0 + 256);
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) {
+    if constexpr (sizeof(T) == 2) s += __bfloat162float(in[static_cast<size_t>(m) * ld + n]);
+    else s += in[static_cast<size_t>(m) * ld + n];
+  }
+  atomicAdd(out + n, s);
+}
+template <typename T>
+inline void launch_colsum(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
+  dim3 grid((N + 127) / 128, (M + 255) / 256);
+  colsum_kernel<T><<<grid, 128, 0, st>>>(in, ld, out, M, N);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention backward: one CTA per sample, one warp per head, lane = query / key index
+// ---------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+                                     const float* __restrict__ dO, __nv_bfloat16* __restrict__ dqkv16,
+                                     float* __restrict__ dbias, int H) {
+  extern __shared__ float sm[];
+  float* sQ = sm;                  // [32][128] scaled q
+  float* sK = sQ + 32 * 128;
+  float* sV = sK + 32 * 128;
+  float* sD = sV + 32 * 128;       // dO
+  float* scr = sD + 32 * 128;      // [H][32][33]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float qs = rsqrtf(static_cast<float>(DH));
+  const float* base = qkv + static_cast<size_t>(b) * 32 * 384;
+  const float* dob = dO + static_cast<size_t>(b) * 32 * 128;
+  for (int i = tid; i < 32 * 32; i += blockDim.x) {
+    const int row = i / 32, c4 = (i % 32) * 4;
+    float4 q4 = *reinterpret_cast<const float4*>(base + row * 384 + c4);
+    q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
+    *reinterpret_cast<float4*>(&sQ[row * 128 + c4]) = q4;
+    *reinterpret_cast<float4*>(&sK[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 128 + c4);
+    *reinterpret_cast<float4*>(&sV[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 256 + c4);
+    *reinterpret_cast<float4*>(&sD[row * 128 + c4]) = *reinterpret_cast<const float4*>(dob + row * 128 + c4);
+  }
+  __syncthreads();
+  const int h = tid >> 5, lane = tid & 31;
+  if (h >= H) return;
+  float* my = scr + h * 32 * 33;
+  const int hc = h * DH;
+  float P[32];
+  const float* pr = probs + ((static_cast<size_t>(b) * H + h) * 32 + lane) * 32;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(pr + j);
+    P[j] = t.x; P[j + 1] = t.y; P[j + 2] = t.z; P[j + 3] = t.w;
+  }
+  float dO_i[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) dO_i[d] = sD[lane * 128 + hc + d];
+  float dS[32];
+  float rs = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(dO_i[d], sV[j * 128 + hc + d], s);
+    dS[j] = s;
+    rs = fmaf(s, P[j], rs);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { my[lane * 33 + j] = P[j]; dS[j] = P[j] * (dS[j] - rs); }
+  __syncwarp();
+  // dv_j = sum_i P[i][j] dO_i    (lane = j)
+  float dv[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) dv[d] = 0.f;
+  for (int i = 0; i < 32; ++i) {
+    const float p = my[i * 33 + lane];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) dv[d] = fmaf(p, sD[i * 128 + hc + d], dv[d]);
+  }
+  __syncwarp();
+  // dq_i = (sum_j dS[i][j] k_j) / sqrt(dh)   (lane = i)
+  float dq[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) dq[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    my[lane * 33 + j] = dS[j];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) dq[d] = fmaf(dS[j], sK[j * 128 + hc + d], dq[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < DH; ++d) dq[d] *= qs;
+  __syncwarp();
+  // dk_j = sum_i dS[i][j] q~_i   (lane = j)
+  float dk[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) dk[d] = 0.f;
+  for (int i = 0; i < 32; ++i) {
+    const float s = my[i * 33 + lane];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) dk[d] = fmaf(s, sQ[i * 128 + hc + d], dk[d]);
+  }
+  __nv_bfloat16* orow = dqkv16 + (static_cast<size_t>(b) * 32 + lane) * 384;
+#pragma unroll
+  for (int d = 0; d < DH; d += 2) {
+    *reinterpret_cast<__nv_bfloat162*>(orow + hc + d) = __floats2bfloat162_rn(dq[d], dq[d + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(orow + 128 + hc + d) = __floats2bfloat162_rn(dk[d], dk[d + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(orow + 256 + hc + d) = __floats2bfloat162_rn(dv[d], dv[d + 1]);
+  }
+#pragma unroll
+  for (int d = 0; d < DH; ++d) {
+    const float a = warp_sum(dq[d]), bsum = warp_sum(dk[d]), c = warp_sum(dv[d]);
+    if (lane == 0) {
+      atomicAdd(dbias + hc + d, a);
+      atomicAdd(dbias + 128 + hc + d, bsum);
+      atomicAdd(dbias + 256 + hc + d, c);
+    }
+  }
+}
+inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, const float* dO, __nv_bfloat16* dqkv16,
+                                        float* dbias, int B, int H, cudaStream_t st) {
+  const int dh = 128 / H;
+  const size_t smem = (4 * 32 * 128 + static_cast<size_t>(H) * 32 * 33) * sizeof(float);
+#define SMD_ATT_BWD(DHV)                                                                                       \
+  {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(smem));                                              \
+    if (e != cudaSuccess) return e;                                                                            \
+    attention_bwd_kernel<DHV><<<B, H * 32, smem, st>>>(qkv, probs, dO, dqkv16, dbias, H);                       \
+  }
+  if (dh == 16) SMD_ATT_BWD(16)
+  else if (dh == 8) SMD_ATT_BWD(8)
+  else if (dh == 32) SMD_ATT_BWD(32)
+  else if (dh == 4) SMD_ATT_BWD(4)
+#undef SMD_ATT_BWD
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// input projection backward: dW_in[c][o] += sum_m x[m][c] dh[m][o]
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dh, float* __restrict__ dW, int M, int C) {
+  const int c = blockIdx.x, o = threadIdx.x;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m) acc = fmaf(__ldg(x + static_cast<size_t>(m) * C + c), dh[static_cast<size_t>(m) * 128 + o], acc);
+  atomicAdd(dW + static_cast<size_t>(c) * 128 + o, acc);
+}
+inline void launch_embed_bwd(const float* x, const float* dh, float* dW, int M, int C, cudaStream_t st) {
+  dim3 grid(C, 16);
+  embed_bwd_kernel<<<grid, 128, 0, st>>>(x, dh, dW, M, C);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small fp32 linear layers of the FiLM generator: weight gradient and input gradient
+// ---------------------------------------------------------------------------------------------------
+// dW[k][n] (+)= sum_r x[r][k] g[r][n]; block = 128 columns x 8 k-rows
+__global__ void __launch_bounds__(128)
+small_linear_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dW, int R,
+                          int K, int N) {
+  __shared__ float sx[64][8];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int rb = 0; rb < R; rb += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+      const int rr = i / 8, kk = i % 8;
+      sx[rr][kk] = (rb + rr < R && k0 + kk < K) ? x[static_cast<size_t>(rb + rr) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+    const int lim = min(64, R - rb);
+    if (n < N) {
+      for (int rr = 0; rr < lim; ++rr) {
+        const float gv = g[static_cast<size_t>(rb + rr) * N + n];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(sx[rr][i], gv, acc[i]);
+      }
+    }
+  }
+  if (n < N)
+    for (int i = 0; i < 8 && k0 + i < K; ++i) atomicAdd(dW + static_cast<size_t>(k0 + i) * N + n, acc[i]);
+}
+inline void launch_small_linear_bwd_w(const float* x, const float* g, float* dW, int R, int K, int N, cudaStream_t st) {
+  dim3 grid((N + 127) / 128, (K + 7) / 8);
+  small_linear_bwd_w_kernel<<<grid, 128, 0, st>>>(x, g, dW, R, K, N);
+}
+// dx[r][k] = (sum_n g[r][n] W[k][n]) * (pre ? swish'(pre[r][k]) : 1); one CTA per row r, one warp per k (looped)
+__global__ void __launch_bounds__(256)
+small_linear_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ W, const float* __restrict__ pre,
+                          float* __restrict__ dx, int K, int N) {
+  extern __shared__ float sg[];  // [N]
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sg[i] = g[static_cast<size_t>(r) * N + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < K; k += 8) {
+    const float* wr = W + static_cast<size_t>(k) * N;
+    float s = 0.f;
+    for (int n = lane; n < N; n += 32) s = fmaf(sg[n], __ldg(wr + n), s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (pre) s *= swish_grad(pre[static_cast<size_t>(r) * K + k]);
+      dx[static_cast<size_t>(r) * K + k] = s;
+    }
+  }
+}
+inline void launch_small_linear_bwd_x(const float* g, const float* W, const float* pre, float* dx, int R, int K, int N,
+                                      cudaStream_t st) {
+  small_linear_bwd_x_kernel<<<R, 256, N * sizeof(float), st>>>(g, W, pre, dx, K, N);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// objective: per-example loss, d loss / d pred (fp32 + zero-padded bf16 operand), running loss sum
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
+                     float* __restrict__ loss_sum, float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16,
+                     float gscale, int S, int C, int Cp) {
+  const int b = blockIdx.x;
+  const int per = S * C;
+  const size_t base = static_cast<size_t>(b) * per;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    const float d = eps[base + i] - pred[base + i];
+    s += d * d;
+    const float gval = -2.0f * d * gscale;
+    dpred32[base + i] = gval;
+    const int row = i / C, c = i % C;
+    dpred16[(static_cast<size_t>(b) * S + row) * Cp + c] = __float2bfloat16_rn(gval);
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int j = 0; j < 8; ++j) v += red[j];
+    v /= static_cast<float>(per);
+    loss[b] = v;
+    if (loss_sum) atomicAdd(loss_sum, v);
+  }
+}
+
+// bf16 dst[r][0..cols) = src[r][0..cols), dst row pitch ld (padding columns untouched)
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
+                                     int ld) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / cols, c = i % cols;
+    dst[r * ld + c] = __float2bfloat16_rn(src[i]);
+  }
+}
+inline void launch_cast_pad_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int ld, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  cast_pad_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, rows, cols, ld);
+}
+
+}  // namespace smd

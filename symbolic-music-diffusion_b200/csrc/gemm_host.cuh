@@ -45,7 +45,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, ui
 
 struct GemmOp {
   CUtensorMap tmA, tmB;
-  int N = 0, K = 0, BN = 0, cg = 1, a_mn = 0, b_mn = 0;
+  int N = 0, K = 0, BN = 0, cg = 1, a_mn = 0, b_mn = 0, k_splits = 1;
 };
 
 inline int choose_bn(int N, int cg) {
@@ -59,7 +59,7 @@ inline int choose_bn(int N, int cg) {
 // A: K-major [a_rows][K] (a_mn=0) or MN-major [K][a_rows] (a_mn=1); same for B with N rows.
 inline bool make_gemm_op(GemmOp* op, const void* A, uint64_t a_rows, const void* B, uint64_t b_rows_total, int N,
                          int K, int BN, int cg, int a_mn, int b_mn, uint64_t k_rows_a = 0, uint64_t k_rows_b = 0) {
-  op->N = N; op->K = K; op->BN = BN; op->cg = cg; op->a_mn = a_mn; op->b_mn = b_mn;
+  op->N = N; op->K = K; op->BN = BN; op->cg = cg; op->a_mn = a_mn; op->b_mn = b_mn; op->k_splits = 1;
   if (K % 64 != 0) { set_error("GEMM K must be a multiple of 64"); return false; }
   if (BN % (16 * cg) != 0 || BN > 256 || BN < 16 * cg) { set_error("bad BN " + std::to_string(BN)); return false; }
   if (b_mn && (BN / cg) % 64 != 0) { set_error("MN-major B needs BN/cta_group % 64 == 0"); return false; }
@@ -95,8 +95,15 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
   }
   GemmShape sh;
   sh.M = M; sh.N = op.N; sh.K = op.K; sh.BN = op.BN; sh.a_mn = op.a_mn; sh.b_mn = op.b_mn;
+  // normalise the split count so that every split owns at least one 64-wide k block
+  const int num_kb = op.K / kBK;
+  int splits = op.k_splits < 1 ? 1 : op.k_splits;
+  if (splits > num_kb) splits = num_kb;
+  const int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;
+  sh.k_splits = splits;
   const int rows_per_tile = kBM * kCG;
-  const int tiles = ((M + rows_per_tile - 1) / rows_per_tile) * ((op.N + op.BN - 1) / op.BN);
+  const int tiles = ((M + rows_per_tile - 1) / rows_per_tile) * ((op.N + op.BN - 1) / op.BN) * splits;
   int groups = device_sm_count() / kCG;
   if (tiles < groups) groups = tiles;
   if (groups < 1) groups = 1;

@@ -31,12 +31,16 @@ struct GemmEpilogue {
   const float* ln_beta;
   __nv_bfloat16* out_bf16_pre;  // bf16 [M][ld_bf16] <- v before the activation (training saves), or null
   float out_scale;              // v is multiplied by out_scale before everything else if != 0 (0 means 1)
+  int atomic_out;               // out_f32 += v with atomics (split-K weight-gradient GEMMs; buffer pre-zeroed)
+  const __nv_bfloat16* gelu_grad_of;  // v *= gelu_tanh'(gelu_grad_of[row][col]) (FFN backward), or null
+  int ld_gg;
 };
 
 struct GemmShape {
   int M, N, K;     // logical problem; K % 64 == 0
   int BN;          // n-tile width: multiple of 16 (kCG=1) / 32 (kCG=2), <= 256
   int a_mn, b_mn;  // 0: operand is K-major ([rows][K], K contiguous); 1: MN-major ([K][rows], rows contiguous)
+  int k_splits;    // >= 1: the K loop is cut into this many independent tiles (needs atomic_out when > 1)
 };
 
 static constexpr int kBM = 128;
@@ -54,6 +58,13 @@ struct GemmSmem {
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
 };
+
+__device__ __forceinline__ float gelu_tanh_grad_f(float x) {
+  const float c = 0.7978845608028654f;
+  const float u = c * (x + 0.044715f * x * x * x);
+  const float th = tanhf(u);
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * c * (1.0f + 3.0f * 0.044715f * x * x);
+}
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_GELU_TANH) {
@@ -89,8 +100,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int rows_per_tile = kBM * kCG;
   const int num_m = (sh.M + rows_per_tile - 1) / rows_per_tile;
   const int num_n = (sh.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = sh.K / kBK;
+  const int splits = sh.k_splits > 0 ? sh.k_splits : 1;
+  const int num_tiles = num_m * num_n * splits;
+  const int num_kb_total = sh.K / kBK;
+  const int kb_per = (num_kb_total + splits - 1) / splits;
   const int group = blockIdx.x / kCG;
   const int num_groups = gridDim.x / kCG;
   const int b_rows = BN / kCG;  // B rows staged by this CTA
@@ -125,9 +138,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0; uint32_t phase = 0;
       const uint32_t stage_tx = static_cast<uint32_t>((kBM + b_rows) * kBK * 2);
       for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int m_row0 = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM;
-        const int n_row0 = (tile % num_n) * BN + static_cast<int>(rank) * b_rows;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int mn = tile / splits, split = tile % splits;
+        const int m_row0 = (mn / num_n) * rows_per_tile + static_cast<int>(rank) * kBM;
+        const int n_row0 = (mn % num_n) * BN + static_cast<int>(rank) * b_rows;
+        const int kb0 = split * kb_per, kb1 = min(num_kb_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sA = smem + stage * SM::kStageBytes;
           uint8_t* sB = sA + SM::kABytes;
@@ -170,7 +185,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         else mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile % splits;
+        const int kb0 = split * kb_per, kb1 = min(num_kb_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sA = smem_u32(smem + stage * SM::kStageBytes);
@@ -179,7 +196,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sA + k * a_kadv, a_lbo, 1024u);
             const uint64_t bdesc = make_smem_desc_sw128(sB + k * b_kadv, b_lbo, 1024u);
-            umma_bf16<kCG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16<kCG>(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit<kCG>(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
           if (++stage == SM::kStages) { stage = 0; phase ^= 1u; }
@@ -194,8 +211,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int acc = 0; uint32_t acc_phase = 0;
     const float oscale = (ep.out_scale != 0.0f) ? ep.out_scale : 1.0f;
     for (int tile = group; tile < num_tiles; tile += num_groups) {
-      const int row = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u + lane);
-      const int n0 = (tile % num_n) * BN;
+      const int mn = tile / splits;
+      const bool first_split = (tile % splits) == 0;
+      const int row = (mn / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u + lane);
+      const int n0 = (mn % num_n) * BN;
       const bool row_ok = row < sh.M;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -225,12 +244,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
           const bool full_chunk = (col0 + ncols <= sh.N);
-          if (ep.bias != nullptr) {
+          // LayerNorm pass 1 with an fp32 output: take v back from what this thread stored in pass 0 (the
+          // residual may alias the output buffer, so it must not be re-added)
+          const bool reload = (pass == 1) && (ep.out_f32 != nullptr);
+          if (reload) {
+            const float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols && col0 + i < sh.N) v[i] = op[i];
+          }
+          if (ep.bias != nullptr && first_split && !reload) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i < ncols && col0 + i < sh.N) v[i] += __ldg(ep.bias + col0 + i);
           }
-          if (ep.residual != nullptr) {
+          if (ep.residual != nullptr && first_split && !reload) {
             const float* rp = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
             if (full_chunk && (ep.ld_res & 3) == 0) {
 #pragma unroll
@@ -246,6 +274,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (i < ncols && col0 + i < sh.N) v[i] += rp[i];
             }
           }
+          if (ep.gelu_grad_of != nullptr && !reload) {
+            const __nv_bfloat16* gp = ep.gelu_grad_of + static_cast<size_t>(row) * ep.ld_gg + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols && col0 + i < sh.N) v[i] *= gelu_tanh_grad_f(__bfloat162float(gp[i]));
+          }
           if (pass == 0) {
             if (ep.row_stats != nullptr || do_ln) {
 #pragma unroll
@@ -254,7 +288,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (ep.out_f32 != nullptr) {
               float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
-              if (full_chunk && (ep.ld_f32 & 3) == 0) {
+              if (ep.atomic_out) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) atomicAdd(op + i, v[i]);
+              } else if (full_chunk && (ep.ld_f32 & 3) == 0) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                   if (i < ncols) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);

@@ -224,7 +224,7 @@ void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R
 // y[r, n] = act(sum_k x[r,k] W[k,n] + b[n]);  block: 128 columns x 8 rows
 __global__ void __launch_bounds__(128)
 small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
-                    float* __restrict__ y, int R, int K, int N, int act) {
+                    float* __restrict__ y, float* __restrict__ pre, int R, int K, int N, int act) {
   extern __shared__ float sx[];  // [8][K]
   const int r0 = blockIdx.y * 8;
   const int nr = min(8, R - r0);
@@ -246,14 +246,15 @@ small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, co
   const float bb = b ? b[n] : 0.f;
   for (int i = 0; i < nr; ++i) {
     float v = acc[i] + bb;
+    if (pre) pre[static_cast<size_t>(r0 + i) * N + n] = v;
     if (act == 2) v = v / (1.0f + expf(-v));
     y[static_cast<size_t>(r0 + i) * N + n] = v;
   }
 }
 void launch_small_linear(const float* x, const float* W, const float* b, float* y, int R, int K, int N, int act,
-                         cudaStream_t st) {
+                         cudaStream_t st, float* pre) {
   dim3 grid((N + 127) / 128, (R + 7) / 8);
-  small_linear_kernel<<<grid, 128, 8 * K * sizeof(float), st>>>(x, W, b, y, R, K, N, act);
+  small_linear_kernel<<<grid, 128, 8 * K * sizeof(float), st>>>(x, W, b, y, pre, R, K, N, act);
 }
 
 // ---------------------------------------------------------------------------------------------------

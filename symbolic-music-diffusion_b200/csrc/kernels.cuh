@@ -130,7 +130,7 @@ void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R
 
 // y[r, n] = act(sum_k x[r,k] W[k,n] + b[n]), all fp32, small R (FiLM generator, models/ncsn.py:47-61)
 void launch_small_linear(const float* x, const float* W, const float* b, float* y, int R, int K, int N, int act,
-                         cudaStream_t st);
+                         cudaStream_t st, float* pre_act_out = nullptr);
 
 // bf16 dst[n][k] = src[k][n]  (fp32 (in,out) Dense kernel -> K-major tensor-core operand)
 void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int N, cudaStream_t st);

@@ -1,0 +1,101 @@
+// Shared internals of libsmd: the plan object, error helpers and launch-count macros.
+#pragma once
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/smd.h"
+#include "gemm_host.cuh"
+#include "kernels.cuh"
+#include "train.cuh"
+
+#define SMD_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+      return SMD_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+#define SMD_LAUNCH_CHECK(what)                                                                      \
+  do {                                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) {                                                                        \
+      set_error(std::string(what) + ": " + cudaGetErrorString(_e));                                \
+      return SMD_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+#define CNT() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+namespace smd {
+extern std::atomic<long long> g_launches;
+void set_error(const std::string& msg);
+const char* get_error();
+
+struct TensorInfo {
+  std::string name;
+  long long offset;
+  int shape[4];
+  int ndim;
+  long long size() const {
+    long long n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    return n;
+  }
+};
+
+static constexpr int kE = 128;       // embed_channels (models/ncsn.py:151)
+static constexpr int kFilmEmb = 128; // DenseFiLM embedding_channels (models/ncsn.py:174)
+static constexpr int kFilmHid = 512; // embedding_channels * 4
+static constexpr int kMaxT = 8192;
+
+}  // namespace smd
+
+using namespace smd;
+
+struct smd_plan {
+  smd_config cfg;
+  std::vector<TensorInfo> tensors;
+  std::map<std::string, long long> off;
+  long long arena = 0;
+  int Mp = 0;  // padded token rows
+  int K = 0;   // number of FiLM res-blocks (num_mlp_layers, or num_layers for DenseDDPM)
+  // ---- workspace carve (byte offsets) ----
+  std::map<std::string, size_t> ws_off;
+  size_t ws_bytes = 0;
+  uint8_t* ws = nullptr;
+  bool packed = false;
+  // ---- GEMM ops ----
+  std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b;
+  GemmOp op_post, op_out, op_in;
+  // sampler
+  int T = 0;
+  bool sampler_ready = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_n = -1;
+  const float* graph_params = nullptr;
+  float* graph_x = nullptr;
+  const float* graph_infill_x = nullptr;
+  const float* graph_infill_mask = nullptr;
+  float* graph_collection = nullptr;
+  float* graph_metrics = nullptr;
+  long long graph_nodes = 0;
+  smd::TrainState train;
+
+  template <typename Tp>
+  Tp* buf(const std::string& n) const { return reinterpret_cast<Tp*>(ws + ws_off.at(n)); }
+  const float* P(const float* params, const std::string& n) const { return params + off.at(n); }
+};
+
+
+namespace smd {
+inline GemmEpilogue epi() {
+  GemmEpilogue e;
+  memset(&e, 0, sizeof(e));
+  return e;
+}
+int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
+                float* y, cudaStream_t st, TrainState* save);
+int train_bind(smd_plan* p);
+}  // namespace smd

@@ -9,90 +9,14 @@
 #include <string>
 #include <vector>
 
-#include "gemm_host.cuh"
-#include "kernels.cuh"
-#include "train.cuh"
+#include "plan.cuh"
 
 namespace smd {
 
 std::atomic<long long> g_launches{0};
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
-
-#define SMD_CUDA(expr)                                                                              \
-  do {                                                                                              \
-    cudaError_t _e = (expr);                                                                        \
-    if (_e != cudaSuccess) {                                                                        \
-      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
-      return SMD_ERR_CUDA;                                                                          \
-    }                                                                                               \
-  } while (0)
-#define SMD_LAUNCH_CHECK(what)                                                                      \
-  do {                                                                                              \
-    cudaError_t _e = cudaGetLastError();                                                            \
-    if (_e != cudaSuccess) {                                                                        \
-      set_error(std::string(what) + ": " + cudaGetErrorString(_e));                                \
-      return SMD_ERR_CUDA;                                                                          \
-    }                                                                                               \
-  } while (0)
-#define CNT() g_launches.fetch_add(1, std::memory_order_relaxed)
-
-struct TensorInfo {
-  std::string name;
-  long long offset;
-  int shape[4];
-  int ndim;
-  long long size() const {
-    long long n = 1;
-    for (int i = 0; i < ndim; ++i) n *= shape[i];
-    return n;
-  }
-};
-
-static constexpr int kE = 128;       // embed_channels (models/ncsn.py:151)
-static constexpr int kFilmEmb = 128; // DenseFiLM embedding_channels (models/ncsn.py:174)
-static constexpr int kFilmHid = 512; // embedding_channels * 4
-static constexpr int kMaxT = 8192;
-
-}  // namespace smd
-
-using namespace smd;
-
-struct smd_plan {
-  smd_config cfg;
-  std::vector<TensorInfo> tensors;
-  std::map<std::string, long long> off;
-  long long arena = 0;
-  int Mp = 0;  // padded token rows
-  int K = 0;   // number of FiLM res-blocks (num_mlp_layers, or num_layers for DenseDDPM)
-  // ---- workspace carve (byte offsets) ----
-  std::map<std::string, size_t> ws_off;
-  size_t ws_bytes = 0;
-  uint8_t* ws = nullptr;
-  bool packed = false;
-  // ---- GEMM ops ----
-  std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b;
-  GemmOp op_post, op_out, op_in;
-  // sampler
-  int T = 0;
-  bool sampler_ready = false;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_n = -1;
-  const float* graph_params = nullptr;
-  float* graph_x = nullptr;
-  const float* graph_infill_x = nullptr;
-  const float* graph_infill_mask = nullptr;
-  float* graph_collection = nullptr;
-  float* graph_metrics = nullptr;
-  long long graph_nodes = 0;
-  smd::TrainState train;
-
-  template <typename Tp>
-  Tp* buf(const std::string& n) const { return reinterpret_cast<Tp*>(ws + ws_off.at(n)); }
-  const float* P(const float* params, const std::string& n) const { return params + off.at(n); }
-};
-
-namespace smd {
+const char* get_error() { return g_err.c_str(); }
 
 static void add_tensor(smd_plan* p, const std::string& name, std::initializer_list<int> shape) {
   TensorInfo t;
@@ -259,23 +183,18 @@ static int build_ops(smd_plan* p) {
   return SMD_OK;
 }
 
-static GemmEpilogue epi() {
-  GemmEpilogue e;
-  memset(&e, 0, sizeof(e));
-  return e;
-}
-
 // FiLM generator for all K blocks: t (R values) -> ss[k][R][2*Md]   (models/ncsn.py:47-61)
-static int run_film(smd_plan* p, const float* params, const float* t, int R, cudaStream_t st) {
+static int run_film(smd_plan* p, const float* params, const float* t, int R, cudaStream_t st, TrainState* save) {
   const int Md = p->cfg.mlp_dims;
   float* enc = p->buf<float>("enc");
-  float* e1 = p->buf<float>("e1");
-  float* e2 = p->buf<float>("e2");
   float* ss = p->buf<float>("ss");
   launch_noise_encoding(t, p->buf<float>("freqs"), enc, R, st); CNT();
   for (int k = 0; k < p->K; ++k) {
     const std::string pre = "k" + std::to_string(k) + ".film.";
-    launch_small_linear(enc, p->P(params, pre + "d1.kernel"), p->P(params, pre + "d1.bias"), e1, R, kFilmEmb, kFilmHid, 2, st); CNT();
+    float* e1 = save ? save->at<float>(p->ws, save->off_e1[k]) : p->buf<float>("e1");
+    float* e2 = save ? save->at<float>(p->ws, save->off_e2[k]) : p->buf<float>("e2");
+    float* e1pre = save ? save->at<float>(p->ws, save->off_e1pre[k]) : nullptr;
+    launch_small_linear(enc, p->P(params, pre + "d1.kernel"), p->P(params, pre + "d1.bias"), e1, R, kFilmEmb, kFilmHid, 2, st, e1pre); CNT();
     launch_small_linear(e1, p->P(params, pre + "d2.kernel"), p->P(params, pre + "d2.bias"), e2, R, kFilmHid, kFilmHid, 0, st); CNT();
     launch_small_linear(e2, p->P(params, pre + "ss.kernel"), p->P(params, pre + "ss.bias"),
                         ss + static_cast<size_t>(k) * p->cfg.max_batch * 2 * Md, R, kFilmHid, 2 * Md, 0, st); CNT();
@@ -351,7 +270,7 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
   const int M = batch * S;
   float* stats = p->buf<float>("stats");
   SMD_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * p->K + 1) * p->Mp * 2 * 4, st));
-  int rc = run_film(p, params, t, t_broadcast ? 1 : batch, st);
+  int rc = run_film(p, params, t, t_broadcast ? 1 : batch, st, save);
   if (rc) return rc;
   float* u0 = save ? save->u(p->ws, 0) : p->buf<float>("u");
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
@@ -462,7 +381,7 @@ __global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uin
 // =====================================================================================================
 extern "C" {
 
-const char* smd_last_error(void) { return g_err.c_str(); }
+const char* smd_last_error(void) { return get_error(); }
 int smd_version(void) { return 100; }
 long long smd_launch_count(void) { return g_launches.load(); }
 
@@ -754,6 +673,23 @@ int smd_threefry_normal(const uint32_t host_key[2], float* out, long long n, smd
 int smd_threefry_split(const uint32_t host_key[2], int num, uint32_t* host_out_keys) {
   if (num < 1) { set_error("num must be >= 1"); return SMD_ERR_INVALID; }
   h_split(host_key, num, host_out_keys);
+  return SMD_OK;
+}
+
+int smd_debug_forward_save(smd_plan* plan, const float* params, const float* x, const float* t, int batch, float* y,
+                           smd_stream_t stream) {
+  if (!plan->cfg.training) { set_error("plan was not created with training = 1"); return SMD_ERR_STATE; }
+  return run_forward(plan, params, x, t, 0, batch, y, static_cast<cudaStream_t>(stream), &plan->train);
+}
+
+int smd_debug_buffer(smd_plan* plan, const char* name, void** dev_ptr, size_t* bytes) {
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  auto it = plan->ws_off.find(name);
+  if (it == plan->ws_off.end()) { set_error(std::string("no workspace region named ") + name); return SMD_ERR_INVALID; }
+  size_t end = plan->ws_bytes;
+  for (const auto& kv : plan->ws_off) if (kv.second > it->second && kv.second < end) end = kv.second;
+  if (dev_ptr) *dev_ptr = plan->ws + it->second;
+  if (bytes) *bytes = end - it->second;
   return SMD_OK;
 }
 
