@@ -1,13 +1,357 @@
-// Backward pass of the DDPM objective (placeholder until the hand-written backward lands in this file).
-#include "train.cuh"
+// Hand-written backward pass of the DDPM objective: what jax.value_and_grad(loss_fn) produces at
+// train_ncsn.py:282-283 for diffusion_loss (utils/losses.py:250-308) over TransformerDDPM / DenseDDPM.
+// Every matmul runs on the tcgen05 GEMM (dX: K-major operands, dW: MN-major operands reducing over tokens,
+// split-K + atomics for the skinny ones); everything else is SIMT (backward_kernels.cuh).
+#include "plan.cuh"
+#include "backward_kernels.cuh"
+
+namespace smd {
+
+static int pick_splits(int m_rows, int n_cols, int BN, int cg, int num_kb) {
+  const int tiles = ((m_rows + 128 * cg - 1) / (128 * cg)) * ((n_cols + BN - 1) / BN);
+  if (tiles >= 64) return 1;
+  int s = 148 / (tiles * cg);
+  if (s < 1) s = 1;
+  if (s > num_kb) s = num_kb;
+  return s;
+}
+
+// dW GEMM: A = X (MN-major [tokens][in]), B = G (MN-major [tokens][out]) -> out_f32 [in][out]
+static bool make_dw(GemmOp* op, const void* X, int in_f, const void* G, int g_cols, int out_f, uint64_t rows, int cg) {
+  int BN = (out_f >= 256) ? 256 : ((out_f + 63) / 64 * 64);
+  if (BN / cg < 64) cg = 1;
+  if (in_f <= 128) cg = 1;
+  return make_gemm_op(op, X, static_cast<uint64_t>(in_f), G, static_cast<uint64_t>(g_cols), out_f,
+                      static_cast<int>(rows), BN, cg, 1, 1);
+}
+// dX GEMM: A = G (K-major [tokens][out]), B = W plain (in,out) = [N=in][K=out] -> [tokens][in]
+static bool make_dx(GemmOp* op, const void* G, int out_f, const void* W, int in_f, uint64_t rows, int cg) {
+  return make_gemm_op(op, G, rows, W, static_cast<uint64_t>(in_f), in_f, out_f, choose_bn(in_f, cg), cg, 0, 0);
+}
+
+int train_bind(smd_plan* p) {
+  TrainState& ts = p->train;
+  uint8_t* ws = p->ws;
+  const smd_config& c = p->cfg;
+  const int Md = c.mlp_dims, C = c.channels, cg = c.cta_group;
+  const int Cp = (C + 63) / 64 * 64;
+  const uint64_t Mp = p->Mp;
+  auto B16 = [&](size_t off) { return ts.at<__nv_bfloat16>(ws, off); };
+  ts.dWb.resize(ts.K); ts.dXb.resize(ts.K); ts.dWa.resize(ts.K); ts.dXa.resize(ts.K);
+  ts.dWss.resize(ts.K); ts.dXss.resize(ts.K);
+  const uint64_t Bp = (static_cast<uint64_t>(c.max_batch) + 127) / 128 * 128;
+  for (int k = 0; k < ts.K; ++k) {
+    if (!make_dw(&ts.dWb[k], ts.act_b(ws, k), Md, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXb[k], B16(ts.off_g16a), Md, B16(ts.off_w_b[k]), Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dw(&ts.dWa[k], ts.act_a(ws, k), Md, B16(ts.off_g16b), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXa[k], B16(ts.off_g16b), Md, B16(ts.off_w_a[k]), Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dw(&ts.dWss[k], B16(ts.off_e2_16), 512, B16(ts.off_dss16), 2 * Md, 2 * Md, Bp, 1)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXss[k], B16(ts.off_dss16), 2 * Md, B16(ts.off_w_ss[k]), 512, Bp, 1)) return SMD_ERR_CUDA;
+  }
+  // output projection: dpred16 is zero-padded to Cp columns; the plain weight copy is [Md][Cp]
+  if (!make_gemm_op(&ts.dWout, ts.act_out(ws), static_cast<uint64_t>(Md), B16(ts.off_dpred16), static_cast<uint64_t>(Cp),
+                    C, static_cast<int>(Mp), (Cp >= 256) ? 256 : Cp, (Cp / cg >= 64 && Cp % (64 * cg) == 0) ? cg : 1, 1, 1))
+    return SMD_ERR_CUDA;
+  if (!make_gemm_op(&ts.dXout, B16(ts.off_dpred16), Mp, B16(ts.off_w_out), static_cast<uint64_t>(Md), Md, Cp,
+                    choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+  if (ts.L > 0) {
+    if (!make_dw(&ts.dWpost, ts.a_post(ws), 128, B16(ts.off_g16a), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXpost, B16(ts.off_g16a), Md, B16(ts.off_w_post), 128, Mp, cg)) return SMD_ERR_CUDA;
+    ts.dW2.resize(ts.L); ts.dX2.resize(ts.L); ts.dW1.resize(ts.L); ts.dX1.resize(ts.L);
+    ts.dWo.resize(ts.L); ts.dXo.resize(ts.L); ts.dWqkv.resize(ts.L); ts.dXqkv.resize(ts.L);
+    for (int l = 0; l < ts.L; ++l) {
+      if (!make_dw(&ts.dW2[l], ts.hidden(ws, l), Md, B16(ts.off_dh16), 128, 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dX2[l], B16(ts.off_dh16), 128, B16(ts.off_w_ffn2[l]), Md, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dW1[l], ts.a2(ws, l), 128, B16(ts.off_g16b), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dX1[l], B16(ts.off_g16b), Md, B16(ts.off_w_ffn1[l]), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dWo[l], ts.o(ws, l), 128, B16(ts.off_dh16), 128, 128, Mp, 1)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dXo[l], B16(ts.off_dh16), 128, B16(ts.off_w_o[l]), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dWqkv[l], ts.a1(ws, l), 128, B16(ts.off_dqkv16), 384, 384, Mp, 1)) return SMD_ERR_CUDA;
+      ts.dWqkv[l].BN = 128;
+      if (!make_dx(&ts.dXqkv[l], B16(ts.off_dqkv16), 384, B16(ts.off_w_qkv[l]), 128, Mp, cg)) return SMD_ERR_CUDA;
+    }
+  } else {
+    if (!make_dw(&ts.dWin, p->buf<__nv_bfloat16>("xb"), C, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
+  }
+  return SMD_OK;
+}
+
+// plain (in,out) bf16 copies of the GEMM weights: B operands of the dX GEMMs
+int train_pack(smd_plan* p, const float* params, cudaStream_t st) {
+  TrainState& ts = p->train;
+  uint8_t* ws = p->ws;
+  const int Md = p->cfg.mlp_dims, C = p->cfg.channels;
+  const int Cp = (C + 63) / 64 * 64;
+  auto cast = [&](const std::string& name, size_t off, size_t n) {
+    launch_cast_bf16(p->P(params, name), ts.at<__nv_bfloat16>(ws, off), n, st); CNT();
+  };
+  for (int l = 0; l < ts.L; ++l) {
+    const std::string s = "l" + std::to_string(l) + ".";
+    cast(s + "attn.qkv.kernel", ts.off_w_qkv[l], 128 * 384);
+    cast(s + "attn.out.kernel", ts.off_w_o[l], 128 * 128);
+    cast(s + "ffn1.kernel", ts.off_w_ffn1[l], static_cast<size_t>(128) * Md);
+    cast(s + "ffn2.kernel", ts.off_w_ffn2[l], static_cast<size_t>(Md) * 128);
+  }
+  if (ts.L) cast("post.kernel", ts.off_w_post, static_cast<size_t>(128) * Md);
+  for (int k = 0; k < ts.K; ++k) {
+    const std::string s = "k" + std::to_string(k) + ".";
+    cast(s + "res.a.kernel", ts.off_w_a[k], static_cast<size_t>(Md) * Md);
+    cast(s + "res.b.kernel", ts.off_w_b[k], static_cast<size_t>(Md) * Md);
+    cast(s + "film.ss.kernel", ts.off_w_ss[k], static_cast<size_t>(512) * 2 * Md);
+  }
+  launch_cast_pad_bf16(p->P(params, "out.kernel"), ts.at<__nv_bfloat16>(ws, ts.off_w_out), Md, C, Cp, st); CNT();
+  SMD_LAUNCH_CHECK("train_pack");
+  return SMD_OK;
+}
+
+static cudaError_t gemm_k(const GemmOp& op0, int rows, int K, int splits, const GemmEpilogue& e, cudaStream_t st) {
+  GemmOp op = op0;
+  op.K = K;
+  op.k_splits = splits;
+  return launch_gemm(op, rows, e, st);
+}
+
+}  // namespace smd
 
 using namespace smd;
 
-extern "C" int smd_ddpm_grads(smd_plan* plan, const float* params, const float* x0, const float* used_alpha,
+extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0, const float* used_alpha,
                               const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
                               smd_stream_t stream) {
-  (void)plan; (void)params; (void)x0; (void)used_alpha; (void)eps; (void)batch; (void)global_batch; (void)grads;
-  (void)loss_sum; (void)stream;
-  set_error("smd_ddpm_grads: backward pass not built yet");
-  return SMD_ERR_STATE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!p->cfg.training) { set_error("plan was not created with training = 1"); return SMD_ERR_STATE; }
+  if (!p->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (batch < 1 || batch > p->cfg.max_batch || global_batch < batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  TrainState& ts = p->train;
+  uint8_t* ws = p->ws;
+  const smd_config& c = p->cfg;
+  const int S = c.seq_len, C = c.channels, Md = c.mlp_dims;
+  const int Cp = (C + 63) / 64 * 64;
+  const int M = batch * S;
+  const int Mk = (M + 63) / 64 * 64;           // reduction length of the dW GEMMs
+  const int Bk = (batch + 63) / 64 * 64;
+  const int per = S * C;
+  auto G = [&](const std::string& n) { return grads + p->off.at(n); };
+  auto B16 = [&](size_t off) { return ts.at<__nv_bfloat16>(ws, off); };
+  auto F32 = [&](size_t off) { return ts.at<float>(ws, off); };
+
+  SMD_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * p->arena, st));
+  if (Mk != M) {  // zero the reduction-tail rows of every MN-major gradient operand
+    const size_t tail = static_cast<size_t>(Mk - M);
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_g16a) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_g16b) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_dh16) + static_cast<size_t>(M) * 128, 0, tail * 128 * 2, st));
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_dqkv16) + static_cast<size_t>(M) * 384, 0, tail * 384 * 2, st));
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_dpred16) + static_cast<size_t>(M) * Cp, 0, tail * Cp * 2, st));
+  }
+  if (Bk != batch) {
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_dss16) + static_cast<size_t>(batch) * 2 * Md, 0,
+                             static_cast<size_t>(Bk - batch) * 2 * Md * 2, st));
+    SMD_CUDA(cudaMemsetAsync(B16(ts.off_e2_16) + static_cast<size_t>(batch) * 512, 0,
+                             static_cast<size_t>(Bk - batch) * 512 * 2, st));
+  }
+
+  // ---------------- forward (keeps every activation) ----------------
+  float* xt = p->buf<float>("xt");
+  float* cond = p->buf<float>("tvec");
+  float* pred = p->buf<float>("eps_hat");
+  launch_q_sample(x0, eps, used_alpha, xt, cond, batch, per, st); CNT();
+  int rc = run_forward(p, params, xt, cond, 0, batch, pred, st, &ts);
+  if (rc) return rc;
+
+  // ---------------- objective ----------------
+  const float gscale = 1.0f / (static_cast<float>(global_batch) * static_cast<float>(per));
+  float* dpred32 = F32(ts.off_dpred32);
+  __nv_bfloat16* dpred16 = B16(ts.off_dpred16);
+  ddpm_loss_bwd_kernel<<<batch, 256, 0, st>>>(eps, pred, F32(ts.off_loss), loss_sum, dpred32, dpred16, gscale, S, C, Cp);
+  CNT();
+  launch_colsum<float>(dpred32, C, G("out.bias"), M, C, st); CNT();
+
+  float* g32 = F32(ts.off_g32a);    // dX GEMM outputs (gradient wrt a bf16 activation)
+  float* du32 = F32(ts.off_g32b);   // gradient of the fp32 residual stream u
+  __nv_bfloat16* du16 = B16(ts.off_g16a);
+  __nv_bfloat16* dr16 = B16(ts.off_g16b);
+  float* stats = p->buf<float>("stats");
+  const size_t sstride = static_cast<size_t>(p->Mp) * 2;
+  const int nkb = Mk / 64;
+
+  // ---------------- output projection + final LayerNorm ----------------
+  {
+    GemmEpilogue e = epi();
+    e.out_f32 = G("out.kernel"); e.ld_f32 = C;
+    const int sp = pick_splits(Md, C, ts.dWout.BN, ts.dWout.cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dWout, Md, Mk, sp, e, st));
+    e = epi();
+    e.out_f32 = g32; e.ld_f32 = Md;
+    SMD_CUDA(launch_gemm(ts.dXout, M, e, st));
+    LnFilmBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g32; a.u = ts.u(ws, ts.K); a.stats = stats + (2 * ts.K) * sstride;
+    a.gamma = p->P(params, "out_ln.scale"); a.beta = p->P(params, "out_ln.bias");
+    a.dx32 = du32; a.dx16 = du16;
+    a.dgamma = G("out_ln.scale"); a.dbeta = G("out_ln.bias");
+    a.dbias = G("k" + std::to_string(ts.K - 1) + ".res.b.bias");
+    a.M = M; a.N = Md; a.S = S;
+    launch_ln_film_act_bwd(a, st); CNT();
+  }
+
+  // ---------------- FiLM'd residual blocks ----------------
+  float* ssbuf = p->buf<float>("ss");
+  float* dss = F32(ts.off_dss);
+  for (int k = ts.K - 1; k >= 0; --k) {
+    const std::string pre = "k" + std::to_string(k) + ".";
+    const float* ss_k = ssbuf + static_cast<size_t>(k) * c.max_batch * 2 * Md;
+    GemmEpilogue e = epi();
+    e.out_f32 = G(pre + "res.b.kernel"); e.ld_f32 = Md;
+    SMD_CUDA(gemm_k(ts.dWb[k], Md, Mk, 1, e, st));
+    e = epi();
+    e.out_f32 = g32; e.ld_f32 = Md;
+    SMD_CUDA(launch_gemm(ts.dXb[k], M, e, st));
+    LnFilmBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g32; a.u = ts.r1(ws, k); a.stats = stats + (2 * k + 1) * sstride;
+    a.gamma = p->P(params, pre + "res.ln_b.scale"); a.beta = p->P(params, pre + "res.ln_b.bias");
+    a.ss = ss_k; a.act = 2;
+    a.dx32 = g32; a.dx16 = dr16;
+    a.dgamma = G(pre + "res.ln_b.scale"); a.dbeta = G(pre + "res.ln_b.bias");
+    a.dbias = G(pre + "res.a.bias");
+    a.dss = dss; a.dss_accum = 0;
+    a.M = M; a.N = Md; a.S = S;
+    launch_ln_film_act_bwd(a, st); CNT();
+    e = epi();
+    e.out_f32 = G(pre + "res.a.kernel"); e.ld_f32 = Md;
+    SMD_CUDA(gemm_k(ts.dWa[k], Md, Mk, 1, e, st));
+    e = epi();
+    e.out_f32 = g32; e.ld_f32 = Md;
+    SMD_CUDA(launch_gemm(ts.dXa[k], M, e, st));
+    memset(&a, 0, sizeof(a));
+    a.g = g32; a.u = ts.u(ws, k); a.stats = stats + (2 * k) * sstride;
+    a.gamma = p->P(params, pre + "res.ln_a.scale"); a.beta = p->P(params, pre + "res.ln_a.bias");
+    a.ss = ss_k; a.act = 2;
+    a.dres = du32; a.dx32 = du32; a.dx16 = du16;
+    a.dgamma = G(pre + "res.ln_a.scale"); a.dbeta = G(pre + "res.ln_a.bias");
+    a.dbias = (k > 0) ? G("k" + std::to_string(k - 1) + ".res.b.bias") : G(ts.L ? "post.bias" : "in.bias");
+    a.dss = dss; a.dss_accum = 1;
+    a.M = M; a.N = Md; a.S = S;
+    launch_ln_film_act_bwd(a, st); CNT();
+
+    // ---- FiLM generator backward (models/ncsn.py:47-61); no gradient flows into t ----
+    float* enc = p->buf<float>("enc");
+    float* e1pre = F32(ts.off_e1pre[k]);
+    float* e1 = F32(ts.off_e1[k]);
+    float* e2 = F32(ts.off_e2[k]);
+    float* de2 = F32(ts.off_de2);
+    float* de1 = F32(ts.off_de);
+    launch_colsum<float>(dss, 2 * Md, G(pre + "film.ss.bias"), batch, 2 * Md, st); CNT();
+    launch_cast_bf16(dss, B16(ts.off_dss16), static_cast<size_t>(batch) * 2 * Md, st); CNT();
+    launch_cast_bf16(e2, B16(ts.off_e2_16), static_cast<size_t>(batch) * 512, st); CNT();
+    e = epi();
+    e.out_f32 = G(pre + "film.ss.kernel"); e.ld_f32 = 2 * Md;
+    SMD_CUDA(gemm_k(ts.dWss[k], 512, Bk, 1, e, st));
+    e = epi();
+    e.out_f32 = de2; e.ld_f32 = 512;
+    SMD_CUDA(launch_gemm(ts.dXss[k], batch, e, st));
+    launch_colsum<float>(de2, 512, G(pre + "film.d2.bias"), batch, 512, st); CNT();
+    launch_small_linear_bwd_w(e1, de2, G(pre + "film.d2.kernel"), batch, 512, 512, st); CNT();
+    launch_small_linear_bwd_x(de2, p->P(params, pre + "film.d2.kernel"), e1pre, de1, batch, 512, 512, st); CNT();
+    launch_colsum<float>(de1, 512, G(pre + "film.d1.bias"), batch, 512, st); CNT();
+    launch_small_linear_bwd_w(enc, de1, G(pre + "film.d1.kernel"), batch, 128, 512, st); CNT();
+  }
+  SMD_LAUNCH_CHECK("backward tail");
+
+  if (ts.L == 0) {
+    // DenseDDPM: input projection weight gradient (models/ncsn.py:129)
+    GemmEpilogue e = epi();
+    e.out_f32 = G("in.kernel"); e.ld_f32 = Md;
+    SMD_CUDA(gemm_k(ts.dWin, C, Mk, 1, e, st));
+    SMD_LAUNCH_CHECK("backward dense");
+    return SMD_OK;
+  }
+
+  // ---------------- post dense + post LayerNorm ----------------
+  float* da32 = F32(ts.off_dh2);
+  float* dh32 = F32(ts.off_dh);
+  __nv_bfloat16* dh16 = B16(ts.off_dh16);
+  {
+    GemmEpilogue e = epi();
+    e.out_f32 = G("post.kernel"); e.ld_f32 = Md;
+    const int sp = pick_splits(128, Md, ts.dWpost.BN, ts.dWpost.cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dWpost, 128, Mk, sp, e, st));
+    e = epi();
+    e.out_f32 = da32; e.ld_f32 = 128;
+    SMD_CUDA(launch_gemm(ts.dXpost, M, e, st));
+    Ln128BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = da32; a.h = ts.h(ws, 2 * ts.L); a.gamma = p->P(params, "post_ln.scale");
+    a.dx32 = dh32; a.dx16 = dh16;
+    a.dgamma = G("post_ln.scale"); a.dbeta = G("post_ln.bias");
+    a.dbias = G("l" + std::to_string(ts.L - 1) + ".ffn2.bias");
+    a.M = M;
+    launch_ln128_bwd(a, st); CNT();
+  }
+
+  // ---------------- transformer trunk ----------------
+  for (int l = ts.L - 1; l >= 0; --l) {
+    const std::string pre = "l" + std::to_string(l) + ".";
+    // FFN: h_out = gelu(a2 W1 + b1) W2 + b2 + h_mid
+    GemmEpilogue e = epi();
+    e.out_f32 = G(pre + "ffn2.kernel"); e.ld_f32 = 128;
+    int sp = pick_splits(Md, 128, ts.dW2[l].BN, ts.dW2[l].cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dW2[l], Md, Mk, sp, e, st));
+    e = epi();
+    e.out_bf16 = dr16; e.ld_bf16 = Md;
+    e.gelu_grad_of = ts.hidden_pre(ws, l); e.ld_gg = Md;
+    SMD_CUDA(launch_gemm(ts.dX2[l], M, e, st));
+    launch_colsum<__nv_bfloat16>(dr16, Md, G(pre + "ffn1.bias"), M, Md, st); CNT();
+    e = epi();
+    e.out_f32 = G(pre + "ffn1.kernel"); e.ld_f32 = Md;
+    sp = pick_splits(128, Md, ts.dW1[l].BN, ts.dW1[l].cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dW1[l], 128, Mk, sp, e, st));
+    e = epi();
+    e.out_f32 = da32; e.ld_f32 = 128;
+    SMD_CUDA(launch_gemm(ts.dX1[l], M, e, st));
+    Ln128BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = da32; a.h = ts.h(ws, 2 * l + 1); a.gamma = p->P(params, pre + "ln2.scale");
+    a.dres = dh32; a.dx32 = dh32; a.dx16 = dh16;
+    a.dgamma = G(pre + "ln2.scale"); a.dbeta = G(pre + "ln2.bias");
+    a.dbias = G(pre + "attn.out.bias");
+    a.M = M;
+    launch_ln128_bwd(a, st); CNT();
+    // attention: h_mid = attn(a1) Wo + bo + h_in
+    e = epi();
+    e.out_f32 = G(pre + "attn.out.kernel"); e.ld_f32 = 128;
+    sp = pick_splits(128, 128, ts.dWo[l].BN, ts.dWo[l].cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dWo[l], 128, Mk, sp, e, st));
+    e = epi();
+    e.out_f32 = da32; e.ld_f32 = 128;
+    SMD_CUDA(launch_gemm(ts.dXo[l], M, e, st));
+    SMD_CUDA(launch_attention_bwd(ts.qkv(ws, l), ts.probs(ws, l), da32, B16(ts.off_dqkv16), G(pre + "attn.qkv.bias"),
+                                  batch, c.num_heads, st));
+    CNT();
+    e = epi();
+    e.out_f32 = G(pre + "attn.qkv.kernel"); e.ld_f32 = 384;
+    sp = pick_splits(128, 384, ts.dWqkv[l].BN, ts.dWqkv[l].cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dWqkv[l], 128, Mk, sp, e, st));
+    e = epi();
+    e.out_f32 = da32; e.ld_f32 = 128;
+    SMD_CUDA(launch_gemm(ts.dXqkv[l], M, e, st));
+    memset(&a, 0, sizeof(a));
+    a.g = da32; a.h = ts.h(ws, 2 * l); a.gamma = p->P(params, pre + "ln1.scale");
+    a.dres = dh32; a.dx32 = dh32; a.dx16 = dh16;
+    a.dgamma = G(pre + "ln1.scale"); a.dbeta = G(pre + "ln1.bias");
+    a.dbias = (l > 0) ? G("l" + std::to_string(l - 1) + ".ffn2.bias") : G("in.bias");
+    a.M = M;
+    launch_ln128_bwd(a, st); CNT();
+  }
+  // ---------------- input projection ----------------
+  launch_embed_bwd(xt, dh32, G("in.kernel"), M, C, st); CNT();
+  SMD_LAUNCH_CHECK("backward trunk");
+  return SMD_OK;
 }

@@ -81,6 +81,8 @@ struct smd_plan {
   float* graph_collection = nullptr;
   float* graph_metrics = nullptr;
   long long graph_nodes = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t own_event = nullptr;
   smd::TrainState train;
 
   template <typename Tp>
@@ -98,4 +100,5 @@ inline GemmEpilogue epi() {
 int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
                 float* y, cudaStream_t st, TrainState* save);
 int train_bind(smd_plan* p);
+int train_pack(smd_plan* p, const float* params, cudaStream_t st);
 }  // namespace smd

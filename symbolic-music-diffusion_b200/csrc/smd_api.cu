@@ -412,6 +412,8 @@ int smd_plan_create(const smd_config* cfg, smd_plan** out) {
 void smd_plan_destroy(smd_plan* plan) {
   if (!plan) return;
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+  if (plan->own_event) cudaEventDestroy(plan->own_event);
+  if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
   delete plan;
 }
 
@@ -450,6 +452,7 @@ int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
       pe[s * kE + 64 + j] = cosf(arg);
     }
   SMD_CUDA(cudaMemcpy(plan->buf<float>("posenc"), pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
+  if (plan->cfg.training) { rc = train_bind(plan); if (rc) return rc; }
   return SMD_OK;
 }
 
@@ -480,6 +483,7 @@ int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
   }
   pack("out.kernel", "w.out", Md, C);
   SMD_LAUNCH_CHECK("pack_weights");
+  if (c.training) { int rc = train_pack(plan, params, st); if (rc) return rc; }
   plan->packed = true;
   return SMD_OK;
 }
@@ -627,10 +631,21 @@ int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int st
     }
     return SMD_OK;
   }
+  // the legacy default stream cannot be captured: run the replay loop on a private stream ordered after `st`
+  cudaStream_t cs = st;
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+    if (!plan->own_stream) {
+      SMD_CUDA(cudaStreamCreateWithFlags(&plan->own_stream, cudaStreamNonBlocking));
+      SMD_CUDA(cudaEventCreateWithFlags(&plan->own_event, cudaEventDisableTiming));
+    }
+    SMD_CUDA(cudaEventRecord(plan->own_event, st));
+    SMD_CUDA(cudaStreamWaitEvent(plan->own_stream, plan->own_event, 0));
+    cs = plan->own_stream;
+  }
   int* t_ptr = plan->buf<int>("t_ptr");
   const int t0 = T - 1;
-  SMD_CUDA(cudaMemcpyAsync(t_ptr, &t0, sizeof(int), cudaMemcpyHostToDevice, st));
-  SMD_CUDA(cudaStreamSynchronize(st));  // t0 is a stack variable
+  SMD_CUDA(cudaMemcpyAsync(t_ptr, &t0, sizeof(int), cudaMemcpyHostToDevice, cs));
+  SMD_CUDA(cudaStreamSynchronize(cs));  // t0 is a stack variable
   const bool same = plan->graph_exec && plan->graph_n == n && plan->graph_params == params && plan->graph_x == x &&
                     plan->graph_infill_x == infill_x && plan->graph_infill_mask == infill_mask &&
                     plan->graph_collection == collection && plan->graph_metrics == metrics;
@@ -638,11 +653,11 @@ int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int st
     if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
-    SMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    SMD_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     int rc = reverse_step_impl(plan, params, x, n, -1, nullptr, infill_x, infill_mask, nullptr, x, nullptr,
-                               collection, metrics, st);
-    if (rc == SMD_OK) { launch_step_advance(t_ptr, st); CNT(); }
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                               collection, metrics, cs);
+    if (rc == SMD_OK) { launch_step_advance(t_ptr, cs); CNT(); }
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return SMD_ERR_CUDA; }
     plan->graph_nodes = g_launches.load() - before;
@@ -653,8 +668,12 @@ int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int st
     plan->graph_infill_mask = infill_mask; plan->graph_collection = collection; plan->graph_metrics = metrics;
   }
   for (int i = 0; i < steps; ++i) {
-    SMD_CUDA(cudaGraphLaunch(plan->graph_exec, st));
+    SMD_CUDA(cudaGraphLaunch(plan->graph_exec, cs));
     g_launches.fetch_add(plan->graph_nodes, std::memory_order_relaxed);
+  }
+  if (cs != st) {
+    SMD_CUDA(cudaEventRecord(plan->own_event, cs));
+    SMD_CUDA(cudaStreamWaitEvent(st, plan->own_event, 0));
   }
   return SMD_OK;
 }

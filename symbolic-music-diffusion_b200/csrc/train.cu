@@ -64,6 +64,10 @@ void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
     ts.off_w_b.push_back(add(nm("wb", k), Md * Md * 2));
   }
   ts.off_w_out = add("t.wout", Md * Cp * 2);
+  const size_t Bp = (B + 127) / 128 * 128;
+  for (int k = 0; k < K; ++k) ts.off_w_ss.push_back(add(nm("wss", k), 512 * 2 * Md * 2));
+  ts.off_e2_16 = add("t.e2_16", Bp * 512 * 2);
+  ts.off_dss16 = add("t.dss16", Bp * 2 * Md * 2);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -46,6 +46,12 @@ struct TrainState {
   size_t off_wplain = 0;               // bf16 plain (in,out) copies of every GEMM weight (dX operands)
   std::vector<size_t> off_w_qkv, off_w_o, off_w_ffn1, off_w_ffn2, off_w_a, off_w_b;
   size_t off_w_post = 0, off_w_out = 0, off_w_in = 0;
+  std::vector<size_t> off_w_ss;        // bf16 [512][2Md] per block
+  size_t off_e2_16 = 0, off_dss16 = 0; // bf16 [Bp][512], [Bp][2Md]
+  // backward GEMM descriptors (built by train_bind)
+  std::vector<GemmOp> dWb, dXb, dWa, dXa, dWss, dXss;
+  std::vector<GemmOp> dW2, dX2, dW1, dX1, dWo, dXo, dWqkv, dXqkv;
+  GemmOp dWout, dXout, dWpost, dXpost, dWin;
 
   float* h(uint8_t* ws, int i) const { return reinterpret_cast<float*>(ws + off_h[i]); }
   __nv_bfloat16* a1(uint8_t* ws, int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + off_a1[l]); }

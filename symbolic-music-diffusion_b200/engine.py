@@ -200,6 +200,49 @@ class Engine:
                                           float(beta1), float(beta2), float(eps), float(mu), scratch.data_ptr(),
                                           gnorm.data_ptr(), self._stream()))
 
+    # ------------------------------------------------------------------ optimizer step (train_ncsn.py:260-288)
+    def init_train_state(self, ema: bool = False) -> None:
+        """Allocates gradient / Adam moment (/ EMA) arenas next to the parameter arena (flax.optim.Adam state)."""
+        if not self.training:
+            raise _lib.SmdError("Engine was created with training=False")
+        if self.params is None:
+            raise _lib.SmdError("set_params() first")
+        dev = self.params.device
+        n = self.arena_floats
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.ema_params = self.params.clone() if ema else None
+        self._scratch = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.opt_step = 0
+
+    def compute_grads(self, x0, used_alpha, eps, global_batch: Optional[int] = None) -> None:
+        """grads <- d(mean over the GLOBAL batch of the loss)/d params for this shard; loss_sum <- sum of losses."""
+        self.loss_sum.zero_()
+        self.ddpm_grads(x0, used_alpha, eps, self.grads, self.loss_sum, global_batch)
+
+    def apply_grads(self, lr: float, grad_clip: float = 1.0, mu: float = 0.999) -> None:
+        self.clip_adam(self.grads, self.adam_m, self.adam_v, lr, self.opt_step, grad_clip, self._scratch,
+                       self.grad_norm, ema=self.ema_params, mu=mu)
+        self.opt_step += 1
+        self.repack()
+
+    def train_step(self, x0, used_alpha, eps, lr: float, grad_clip: float = 1.0, process_group=None,
+                   world_size: int = 1):
+        """One data-parallel optimizer step: local grads -> NCCL all-reduce(sum) -> clip -> Adam.
+
+        Returns (mean loss over the global batch, post-clip grad norm) as device tensors (no host sync)."""
+        batch = x0.shape[0]
+        self.compute_grads(x0, used_alpha, eps, global_batch=batch * world_size)
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=process_group)
+            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=process_group)
+        self.apply_grads(lr, grad_clip)
+        return self.loss_sum / float(batch * world_size), self.grad_norm
+
     # ------------------------------------------------------------------ sampler
     def sampler_setup(self, betas: np.ndarray, key=(0, 0)) -> None:
         self._ensure_ws()
