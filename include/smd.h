@@ -95,6 +95,14 @@ int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, flo
                   float* scratch, float* grad_norm_out, smd_stream_t stream);
 int smd_ema_update(float* ema, const float* params, long long n, float mu, smd_stream_t stream);
 
+/* Random draws of diffusion_loss (utils/losses.py:270-294) on device with jax 0.2.8 threefry semantics:
+ * rng,label_rng,sample_rng = split(key,3); labels = randint(label_rng, 1, T+1); rng,noise_rng = split(rng);
+ * used_alpha = uniform(noise_rng, minval=abar[labels-1], maxval=abar[labels]); eps = normal(sample_rng).
+ * smd_objective_setup uploads abar = concat([1], cumprod(1-betas)) (host_betas: HOST pointer, T floats). */
+int smd_objective_setup(smd_plan* plan, const float* host_betas, int T, smd_stream_t stream);
+int smd_ddpm_draws(smd_plan* plan, const uint32_t host_key[2], int batch, float* used_alpha, float* eps,
+                   int* labels_or_null, smd_stream_t stream);
+
 /* ---- sampler ---------------------------------------------------------------------------------------------- */
 /* host_betas: HOST pointer, T floats.  Builds the per-step coefficient / key / slot tables in the workspace.
  * key = jax PRNG key (2 x uint32) that diffusion_dynamics receives as `rng`. */

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for f in tests/test_gpu_gemm.py tests/test_gpu_forward.py tests/test_gpu_sampler.py "$@"; do
   n=$(basename $f .py)
   echo "=== $f"
-  timeout 600 python -m pytest $f -m gpu -q -x --timeout=300 -p no:cacheprovider > gpurun_out/$n.log 2>&1
+  timeout 420 python -m pytest $f -m gpu -q -x --timeout=240 -p no:cacheprovider > gpurun_out/$n.log 2>&1
   echo "exit=$?" >> gpurun_out/$n.log
   tail -n 25 gpurun_out/$n.log
 done

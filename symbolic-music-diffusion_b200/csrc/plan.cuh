@@ -71,6 +71,7 @@ struct smd_plan {
   GemmOp op_post, op_out, op_in;
   // sampler
   int T = 0;
+  int T_obj = 0;  // schedule length of the training objective
   bool sampler_ready = false;
   cudaGraphExec_t graph_exec = nullptr;
   int graph_n = -1;

@@ -7,9 +7,16 @@
 
 namespace smd {
 
-#ifndef SMD_SPIN_LIMIT
-#define SMD_SPIN_LIMIT (1u << 26)   // bounded spins: a protocol bug traps instead of hanging the GPU
+// Bounded waits: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The limit is
+// wall-clock (globaltimer, ns): no legitimate wait inside one of these kernels comes near two seconds.
+#ifndef SMD_WAIT_LIMIT_NS
+#define SMD_WAIT_LIMIT_NS 2000000000ull
 #endif
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -74,14 +81,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SMD_SPIN_LIMIT) __trap();
+    if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
   }
 }
 // cluster-scope acquire variant (used when the arrivals come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  const unsigned long long t0 = global_timer_ns();
   for (;;) {
     uint32_t ok;
     asm volatile(
@@ -92,7 +102,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (ok) break;
-    if (++spins > SMD_SPIN_LIMIT) __trap();
+    if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
   }
 }
 

@@ -144,6 +144,7 @@ static void build_workspace(smd_plan* p) {
   ws_add(p, "keys", kMaxT * 4 * 4);
   ws_add(p, "slots", kMaxT * 4);
   ws_add(p, "t_ptr", 64);
+  ws_add(p, "abar", (kMaxT + 1) * 4);
   if (c.training) train_workspace(p->train, c, p->Mp, p->K, [&](const std::string& n, size_t b) { return ws_add(p, n, b); });
 }
 
@@ -369,6 +370,30 @@ static void h_split(const uint32_t key[2], int num, uint32_t* out) {
   memcpy(out, flat.data(), sizeof(uint32_t) * 2 * num);
 }
 
+// labels = jax.random.randint(label_key, (B,), 1, T+1); used = max(lo, u*(hi-lo)+lo) with lo=abar[l-1], hi=abar[l]
+__global__ void ddpm_draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint32_t nk1, const float* __restrict__ abar,
+                                  int T, int B, float* __restrict__ used, int* __restrict__ labels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  // randint: k1,k2 = split(key); hi,lo bits; span = T; mult = (2^16 % span)^2 % span
+  uint32_t a0 = 0, b0 = 2, a1 = 1, b1 = 3;
+  threefry2x32(lk0, lk1, a0, b0);
+  threefry2x32(lk0, lk1, a1, b1);
+  const uint32_t k1_0 = a0, k1_1 = a1, k2_0 = b0, k2_1 = b1;
+  const uint32_t hi = jax_random_bits(k1_0, k1_1, i, B);
+  const uint32_t lo = jax_random_bits(k2_0, k2_1, i, B);
+  const uint32_t span = static_cast<uint32_t>(T);
+  uint32_t mult = 65536u % span;
+  mult = static_cast<uint32_t>((static_cast<uint64_t>(mult) * mult) % span);
+  const uint32_t off = static_cast<uint32_t>((static_cast<uint64_t>(hi % span) * mult + (lo % span)) % span);
+  const int label = 1 + static_cast<int>(off);
+  if (labels) labels[i] = label;
+  const float minv = abar[label - 1], maxv = abar[label];
+  const uint32_t bits = jax_random_bits(nk0, nk1, i, B);
+  const float u01 = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  used[i] = fmaxf(minv, __fadd_rn(__fmul_rn(u01, __fsub_rn(maxv, minv)), minv));
+}
+
 __global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, i, n));
@@ -507,6 +532,41 @@ int smd_ddpm_loss(smd_plan* plan, const float* params, const float* x0, const fl
   if (rc) return rc;
   launch_ddpm_loss(eps, pred, loss_per_example, nullptr, 0.f, batch, per, st); CNT();
   SMD_LAUNCH_CHECK("ddpm_loss");
+  return SMD_OK;
+}
+
+int smd_objective_setup(smd_plan* plan, const float* host_betas, int T, smd_stream_t stream) {
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (T < 1 || T > kMaxT) { set_error("T out of range"); return SMD_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<float> ap(T + 1);
+  ap[0] = 1.0f;
+  float run = 1.0f;
+  for (int i = 0; i < T; ++i) { const float a = 1.0f - host_betas[i]; run = (i == 0) ? a : run * a; ap[i + 1] = run; }
+  SMD_CUDA(cudaMemcpyAsync(plan->buf<float>("abar"), ap.data(), ap.size() * 4, cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaStreamSynchronize(st));
+  plan->T_obj = T;
+  return SMD_OK;
+}
+
+int smd_ddpm_draws(smd_plan* plan, const uint32_t host_key[2], int batch, float* used_alpha, float* eps,
+                   int* labels_or_null, smd_stream_t stream) {
+  if (plan->T_obj <= 0) { set_error("smd_objective_setup has not been called"); return SMD_ERR_STATE; }
+  if (batch < 1) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t k3[6], k2[4];
+  h_split(host_key, 3, k3);               // rng, label_rng, sample_rng
+  const uint32_t rng[2] = {k3[0], k3[1]};
+  h_split(rng, 2, k2);                    // rng, noise_rng
+  ddpm_draws_kernel<<<(batch + 127) / 128, 128, 0, st>>>(k3[2], k3[3], k2[2], k2[3], plan->buf<float>("abar"),
+                                                         plan->T_obj, batch, used_alpha, labels_or_null);
+  CNT();
+  const long long n = static_cast<long long>(batch) * plan->cfg.seq_len * plan->cfg.channels;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  threefry_normal_kernel<<<blocks, 256, 0, st>>>(k3[4], k3[5], eps, static_cast<uint32_t>(n));
+  CNT();
+  SMD_LAUNCH_CHECK("ddpm_draws");
   return SMD_OK;
 }
 

@@ -200,6 +200,25 @@ class Engine:
                                           float(beta1), float(beta2), float(eps), float(mu), scratch.data_ptr(),
                                           gnorm.data_ptr(), self._stream()))
 
+    # ------------------------------------------------------------------ objective draws (utils/losses.py:270-294)
+    def objective_setup(self, betas: np.ndarray) -> None:
+        self._ensure_ws()
+        b = np.ascontiguousarray(betas, np.float32)
+        _lib.check(self.lib.smd_objective_setup(self._plan, b.ctypes.data_as(C.POINTER(C.c_float)), len(b),
+                                                self._stream()))
+
+    def draws(self, key, batch: int, want_labels: bool = False):
+        """(used_alpha (B,), eps (B,S,C)[, labels]) from a jax PRNG key, generated on device."""
+        dev = self._ws.device
+        shape = (batch, self.seq_len, self.cfg.channels) if ARCHS[self.cfg.arch] == 0 else (batch, self.cfg.channels)
+        used = torch.empty((batch,), dtype=torch.float32, device=dev)
+        eps = torch.empty(shape, dtype=torch.float32, device=dev)
+        labels = torch.empty((batch,), dtype=torch.int32, device=dev) if want_labels else None
+        k = (C.c_uint32 * 2)(int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF)
+        _lib.check(self.lib.smd_ddpm_draws(self._plan, k, batch, used.data_ptr(), eps.data_ptr(), _ptr(labels),
+                                           self._stream()))
+        return (used, eps, labels) if want_labels else (used, eps)
+
     # ------------------------------------------------------------------ optimizer step (train_ncsn.py:260-288)
     def init_train_state(self, ema: bool = False) -> None:
         """Allocates gradient / Adam moment (/ EMA) arenas next to the parameter arena (flax.optim.Adam state)."""

@@ -1,0 +1,34 @@
+"""jax.random (0.2.8, threefry2x32) subset used by the hot path, host side backed by libsmd.
+
+Keys are numpy uint32[2] arrays exactly like ``jax.random.PRNGKey``; ``split`` runs the C++ host threefry in
+libsmd (smd_threefry_split); ``normal`` generates on the GPU (smd_threefry_normal)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+
+def PRNGKey(seed: int) -> np.ndarray:
+    seed = int(seed)
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=np.uint32)
+
+
+def split(key, num: int = 2) -> np.ndarray:
+    lib = _lib.load_library()
+    k = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
+    out = (C.c_uint32 * (2 * num))()
+    _lib.check(lib.smd_threefry_split(k, int(num), out))
+    return np.array(list(out), dtype=np.uint32).reshape(num, 2)
+
+
+def normal(key, shape, device=None) -> torch.Tensor:
+    lib = _lib.load_library()
+    n = int(np.prod(shape))
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=device or "cuda")
+    k = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
+    _lib.check(lib.smd_threefry_normal(k, out.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    return out

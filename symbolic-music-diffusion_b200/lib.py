@@ -39,6 +39,8 @@ _SIGNATURES = {
     "smd_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.c_longlong, C.c_float, C.c_int, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     "smd_ema_update": (C.c_int, [_P, _P, C.c_longlong, C.c_float, _P]),
+    "smd_objective_setup": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, _P]),
+    "smd_ddpm_draws": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int, _P, _P, _P, _P]),
     "smd_sampler_setup": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint32), _P]),
     "smd_ddpm_reverse_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "smd_ddpm_sample": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P]),

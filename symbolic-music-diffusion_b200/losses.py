@@ -1,0 +1,35 @@
+"""Objectives with the reference signatures (utils/losses.py).  Only the DDPM objective is on the hot path."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def reduce_fn(x, mode):
+    """utils/losses.py:22-30."""
+    if mode == "none" or mode is None:
+        return x
+    if mode == "sum":
+        return x.sum()
+    if mode == "mean":
+        return x.mean()
+    raise ValueError("Unsupported reduction option.")
+
+
+def diffusion_loss(batch, model, betas, rng, continuous_noise=False, reduction="mean"):
+    """utils/losses.py:250-308: draws (labels, alpha-bar, eps) from `rng` on device with jax threefry semantics,
+    forms x_t, evaluates the network and reduces the per-example mean-squared error.  `model` is an nn.Model."""
+    from .nn import _as_device_f32
+    x0 = _as_device_f32(batch)
+    eng = model.engine(x0.shape[0])
+    betas = np.asarray(betas, np.float32)
+    if getattr(eng, "_obj_betas", None) is None or not np.array_equal(eng._obj_betas, betas):
+        eng.objective_setup(betas)
+        eng._obj_betas = betas.copy()
+    if not continuous_noise:
+        # the reference's discrete branch is commented out upstream (losses.py:287-288,301-302): only the
+        # label range changes (minval 0), which would index alphas_prod[-1]; not supported here.
+        raise ValueError("diffusion_loss: only continuous_noise=True is implemented (all ddpm-*.cfg use it)")
+    used, eps = eng.draws((int(rng[0]), int(rng[1])), x0.shape[0])
+    loss = eng.ddpm_loss(x0, used, eps)
+    return reduce_fn(loss, reduction)
