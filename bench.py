@@ -40,9 +40,9 @@ def synthetic_batch(batch: int, seed: int):
     rng = np.random.default_rng(seed)
     raw = rng.standard_normal((batch, 32, 512)).astype(np.float32)
     idx = np.sort(np.random.default_rng(1234).choice(512, 42, replace=False))
-    x = raw[..., idx]
+    x = np.ascontiguousarray(raw[..., idx])
     lo, hi = x.min(), x.max()
-    return (2.0 * (x - lo) / (hi - lo) - 1.0).astype(np.float32)
+    return np.ascontiguousarray((2.0 * (x - lo) / (hi - lo) - 1.0).astype(np.float32))
 
 
 class ClockSampler(threading.Thread):

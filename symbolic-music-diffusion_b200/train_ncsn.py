@@ -1,0 +1,244 @@
+"""Training entry point with the reference's flag surface (train_ncsn.py:48-128), so configs/ddpm-*.cfg run
+unchanged:  python -m smd_b200.train_ncsn --flagfile=configs/ddpm-mel-32seq-512.cfg [--synthetic]
+
+Only the DDPM family is on the B200 hot path: --loss=ddpm, --sampling=ddpm, --architecture in
+{TransformerDDPM, TransformerDDPM4, DenseDDPM}.  Other values raise ValueError exactly where the reference would
+dispatch on them.  Data-parallel: launch with torchrun (one process per GPU); the batch is sharded across ranks
+and gradients are summed with one NCCL all-reduce over the flat arena.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+from absl import app, flags, logging
+
+from smd_b200 import checkpoints, ebm_utils, input_pipeline, jrandom as random, ncsn, nn, optim, parallel, train_utils
+from smd_b200.losses import diffusion_loss
+
+FLAGS = flags.FLAGS
+_D = flags.DEFINE_integer, flags.DEFINE_float, flags.DEFINE_bool, flags.DEFINE_string, flags.DEFINE_enum
+
+# --- optimisation ------------------------------------------------------------------------------------------
+flags.DEFINE_integer("seed", 0, "PRNG seed (jax.random.PRNGKey).")
+flags.DEFINE_enum("loss", "dsm", ["dsm", "ssm", "ddpm"], "Training objective.")
+flags.DEFINE_bool("continuous_noise", True, "Condition on the continuous noise level sqrt(alpha_bar).")
+flags.DEFINE_float("learning_rate", 3e-4, "Base learning rate.")
+flags.DEFINE_integer("batch_size", 128, "GLOBAL batch size (sharded over ranks when launched with torchrun).")
+flags.DEFINE_integer("epochs", 10, "Number of epochs.")
+flags.DEFINE_integer("max_steps", None, "Stop after this many optimizer steps.")
+flags.DEFINE_bool("early_stopping", False, "Stop on a non-improving evaluation loss.")
+flags.DEFINE_float("grad_clip", 1.0, "Global-norm gradient clipping threshold.")
+flags.DEFINE_float("lr_gamma", 0.98, "Multiplicative LR decay per interval.")
+flags.DEFINE_integer("lr_schedule_interval", 10000, "Steps per LR decay interval.")
+# --- model -------------------------------------------------------------------------------------------------
+flags.DEFINE_string("architecture", "TransformerDDPM", "Score-network class name in models/ncsn.py.")
+flags.DEFINE_integer("num_layers", 6, "Transformer layers (or DenseDDPM res-blocks).")
+flags.DEFINE_integer("num_heads", 8, "Attention heads.")
+flags.DEFINE_integer("num_mlp_layers", 2, "FiLM residual MLP blocks after the trunk.")
+flags.DEFINE_integer("mlp_dims", 2048, "Width of the residual MLP blocks.")
+# --- noise schedule / sampling -----------------------------------------------------------------------------
+flags.DEFINE_float("sigma_begin", 1.0, "First value of the noise schedule.")
+flags.DEFINE_float("sigma_end", 1e-2, "Last value of the noise schedule.")
+flags.DEFINE_enum("schedule_type", "geometric", ["geometric", "linear", "fibonacci"], "Noise schedule.")
+flags.DEFINE_integer("num_sigmas", 15, "Length of the noise schedule.")
+flags.DEFINE_integer("ld_steps", 100, "Langevin steps per noise level (null for ddpm).")
+flags.DEFINE_float("ld_epsilon", 2e-6, "Langevin step size (null for ddpm).")
+flags.DEFINE_enum("sampling", "ald", ["ald", "cas", "ddpm"], "Sampling algorithm.")
+flags.DEFINE_bool("ema", True, "Track an exponential moving average of the parameters.")
+flags.DEFINE_float("mu", 0.999, "EMA momentum.")
+flags.DEFINE_bool("denoise", True, "Expected-denoised-sample step (null for ddpm).")
+# --- data --------------------------------------------------------------------------------------------------
+flags.DEFINE_list("data_shape", [2], "Shape of one example, e.g. 32,512.")
+flags.DEFINE_enum("problem", "toy", ["toy", "mnist", "vae"], "Problem family.")
+flags.DEFINE_string("dataset", "./output/mix2d", "Dataset directory ({train,eval}-*.tfrecord).")
+flags.DEFINE_string("pca_ckpt", "", "PCA transform pickle.")
+flags.DEFINE_string("slice_ckpt", "", "Pickle of latent dimensions to keep.")
+flags.DEFINE_string("dim_weights_ckpt", "", "Pickle of per-dimension weights.")
+flags.DEFINE_bool("normalize", True, "Min/max normalise to [-1, 1].")
+# --- logging / checkpoints ---------------------------------------------------------------------------------
+flags.DEFINE_integer("logging_freq", 100, "Steps between log lines.")
+flags.DEFINE_integer("snapshot_freq", 5000, "Steps between evaluation + checkpoint.")
+flags.DEFINE_bool("snapshot_sampling", True, "Sample at every snapshot.")
+flags.DEFINE_integer("eval_samples", 3000, "Samples drawn at a snapshot.")
+flags.DEFINE_integer("checkpoints_to_keep", 50, "Checkpoints retained.")
+flags.DEFINE_bool("save_ckpt", True, "Write checkpoints.")
+flags.DEFINE_string("model_dir", "./save/ncsn", "Output directory.")
+flags.DEFINE_bool("verbose", True, "Verbose logging.")
+# --- additions of this implementation (not in the reference) ------------------------------------------------
+flags.DEFINE_bool("synthetic", False, "Use synthetic N(0,1) latents of --data_shape instead of reading --dataset.")
+flags.DEFINE_integer("synthetic_examples", 4096, "Examples per split with --synthetic.")
+
+
+def model_kwargs():
+    return dict(num_layers=FLAGS.num_layers, num_heads=FLAGS.num_heads, num_mlp_layers=FLAGS.num_mlp_layers,
+                mlp_dims=FLAGS.mlp_dims)
+
+
+def create_optimizer(model, learning_rate):
+    """train_ncsn.py:187-190."""
+    return optim.Adam(learning_rate=learning_rate).create(model)
+
+
+def create_model(rng, input_shape, model_kwargs, batch_size=32, verbose=False):
+    """train_ncsn.py:193-203: getattr(ncsn, FLAGS.architecture).partial(**kw).init_by_shape(...) -> nn.Model."""
+    clazz = getattr(ncsn, FLAGS.architecture, None)
+    if clazz is None:
+        raise ValueError(f"Unknown architecture {FLAGS.architecture!r} (models/ncsn.py has no such class)")
+    module = clazz.partial(**model_kwargs)
+    _, params = module.init_by_shape(rng, [((batch_size, *input_shape), np.float32),
+                                           ((batch_size, *([1] * len(input_shape))), np.float32)])
+    model = nn.Model(module, params)
+    if verbose:
+        train_utils.report_model(model)
+    return model
+
+
+def _objective():
+    if FLAGS.loss == "ddpm":
+        return diffusion_loss
+    if FLAGS.loss in ("dsm", "ssm"):
+        raise ValueError(f"--loss={FLAGS.loss}: the NCSN objectives are outside the B200 hot path (use --loss=ddpm)")
+    raise ValueError(f"Unsupported objective {FLAGS.loss}")
+
+
+def eval_step(objective, batch, model, sigmas, rng):
+    """train_ncsn.py:206-221: summed loss of one batch."""
+    return objective(batch, model, sigmas, rng, FLAGS.continuous_noise, "sum")
+
+
+def evaluate(dataset, model, sigmas, rng):
+    """train_ncsn.py:224-257."""
+    objective = _objective()
+    count, total = 0, 0.0
+    for inputs in dataset:
+        count += inputs.shape[0]
+        rng, eval_rng = random.split(rng)
+        total += float(eval_step(objective, inputs, model, sigmas, eval_rng))
+    return {"loss": total / max(count, 1)}
+
+
+def lr_at(step: int) -> float:
+    """flax create_stepped_learning_rate_schedule as called at train_ncsn.py:340-342."""
+    n = 0 if step <= 0 else (step - 1) // FLAGS.lr_schedule_interval
+    return FLAGS.learning_rate * (FLAGS.lr_gamma ** n)
+
+
+def train_step(objective, batch, optimizer, sigmas, rng, learning_rate, ema=None):
+    """train_ncsn.py:260-288 on this rank's shard: grads -> all-reduce -> clip -> Adam (one fused pass)."""
+    if objective is not diffusion_loss:
+        raise ValueError("only the DDPM objective has a hand-written backward")
+    model = optimizer.target
+    world, rank = parallel.world_size(), parallel.rank()
+    x0 = nn._as_device_f32(batch)
+    local = x0.shape[0]
+    eng = model.engine(local, training=True)
+    betas = np.asarray(sigmas, np.float32)
+    if getattr(eng, "_obj_betas", None) is None or not np.array_equal(eng._obj_betas, betas):
+        eng.objective_setup(betas)
+        eng._obj_betas = betas.copy()
+    if not hasattr(eng, "grads"):
+        eng.init_train_state(ema=False)
+    key = random.split(rng, world)[rank] if world > 1 else rng   # independent noise per shard
+    used, eps = eng.draws((int(key[0]), int(key[1])), local)
+    eng.compute_grads(x0, used, eps, global_batch=local * world)
+    parallel.all_reduce_sum_(eng.grads)
+    parallel.all_reduce_sum_(eng.loss_sum)
+    optimizer.apply_gradient(eng.grads, learning_rate=learning_rate, max_norm=FLAGS.grad_clip,
+                             ema=None if ema is None else ema.params.flat, mu=FLAGS.mu)
+    metrics = {"loss": eng.loss_sum / float(local * world), "grad": optimizer.grad_norm, "lr": learning_rate}
+    return optimizer, metrics
+
+
+def train(train_batches, valid_batches, sigmas, output_dir=None, verbose=True):
+    """train_ncsn.py:291-496 (the MNIST / toy plotting branches are out of scope)."""
+    objective = _objective()
+    first = next(iter(valid_batches))
+    input_shape = tuple(first.shape[1:])
+    rng = random.PRNGKey(FLAGS.seed)
+    rng, model_rng, _ = random.split(rng, 3)
+    local_bs = parallel.shard_size(FLAGS.batch_size)
+    model = create_model(model_rng, input_shape, model_kwargs(), batch_size=local_bs, verbose=verbose)
+    optimizer = create_optimizer(model, FLAGS.learning_rate)
+    ema = train_utils.EMAHelper(FLAGS.mu, model.arena.clone()) if FLAGS.ema else None
+    early_stop = train_utils.EarlyStopping(patience=1)
+    writer = None
+    if output_dir and parallel.rank() == 0:
+        os.makedirs(output_dir, exist_ok=True)
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(os.path.join(output_dir, "train"))
+        except Exception:  # tensorboard is optional
+            writer = None
+    steps_per_epoch = train_batches.examples
+    total_steps = FLAGS.max_steps or FLAGS.epochs * steps_per_epoch
+    global_step, t0 = 0, time.time()
+    done = False
+    for epoch in range(FLAGS.epochs):
+        for batch in train_batches:
+            rng, train_rng = random.split(rng)
+            global_step += 1
+            lr = lr_at(global_step)
+            optimizer, metrics = train_step(objective, parallel.shard_rows(batch), optimizer, sigmas, train_rng, lr, ema)
+            if global_step % FLAGS.logging_freq == 0 and parallel.rank() == 0:
+                dt = time.time() - t0
+                metrics.update({"batch/s": FLAGS.logging_freq / dt, "ms/batch": 1e3 * dt / FLAGS.logging_freq})
+                train_utils.log_metrics(metrics, global_step, total_steps, epoch=epoch, summary_writer=writer,
+                                        verbose=verbose)
+                t0 = time.time()
+            if global_step % FLAGS.snapshot_freq == 0 or global_step == total_steps:
+                rng, eval_rng = random.split(rng)
+                ev = evaluate(valid_batches, optimizer.target, sigmas, eval_rng)
+                improved, early_stop = early_stop.update(ev["loss"])
+                if parallel.rank() == 0:
+                    logging.info("eval step %d: loss %.6f", global_step, ev["loss"])
+                    if FLAGS.save_ckpt and output_dir:
+                        checkpoints.save_checkpoint(output_dir, (optimizer, ema, early_stop), global_step,
+                                                    keep=FLAGS.checkpoints_to_keep)
+                if FLAGS.early_stopping and early_stop.should_stop:
+                    done = True
+            if FLAGS.max_steps and global_step >= FLAGS.max_steps:
+                done = True
+            if done:
+                break
+        if done:
+            break
+    if writer is not None:
+        writer.flush()
+    return optimizer
+
+
+def sample(scorenet, sigmas, rng, sample_shape, num_samples=2400, sampling="ald", epsilon=1e-3, steps=100,
+           denoise=True):
+    """train_ncsn.py:499-551: initial noise from `rng`, dispatch on the sampler, collate metrics."""
+    if sampling == "ddpm":
+        algorithm = ebm_utils.diffusion_dynamics
+    elif sampling in ("ald", "cas"):
+        raise ValueError(f"--sampling={sampling}: the NCSN samplers are outside the B200 hot path (use ddpm)")
+    else:
+        raise ValueError(f"Unknown sampling algorithm: {sampling}")
+    init_rng, ld_rng = random.split(rng)
+    init = random.normal(init_rng, (num_samples, *sample_shape))
+    generated, collection, ld_metrics = algorithm(ld_rng, scorenet, sigmas, init, epsilon, steps, denoise, False)
+    return generated, collection, ebm_utils.collate_sampling_metrics(ld_metrics)
+
+
+def main(argv):
+    del argv
+    parallel.init_from_env()
+    logging.info("platform: cuda (%s), ranks: %d", torch.cuda.get_device_name() if torch.cuda.is_available() else "none",
+                 parallel.world_size())
+    train_ds, eval_ds = input_pipeline.get_dataset(
+        dataset=FLAGS.dataset, data_shape=FLAGS.data_shape, problem=FLAGS.problem, batch_size=FLAGS.batch_size,
+        normalize=FLAGS.normalize, pca_ckpt=FLAGS.pca_ckpt, slice_ckpt=FLAGS.slice_ckpt,
+        dim_weights_ckpt=FLAGS.dim_weights_ckpt, synthetic=FLAGS.synthetic,
+        synthetic_examples=FLAGS.synthetic_examples, seed=FLAGS.seed)
+    sigmas = ebm_utils.create_noise_schedule(FLAGS.sigma_begin, FLAGS.sigma_end, FLAGS.num_sigmas, FLAGS.schedule_type)
+    train(train_ds, eval_ds, sigmas, FLAGS.model_dir, FLAGS.verbose)
+    parallel.shutdown()
+
+
+if __name__ == "__main__":
+    app.run(main)
