@@ -76,32 +76,30 @@ int train_bind(smd_plan* p) {
   return SMD_OK;
 }
 
-// plain (in,out) bf16 copies of the GEMM weights: B operands of the dX GEMMs
-int train_pack(smd_plan* p, const float* params, cudaStream_t st) {
+// plain (in,out) bf16 copies of the GEMM weights: B operands of the dX GEMMs (jobs of the one-launch repack)
+void train_pack_jobs(smd_plan* p) {
   TrainState& ts = p->train;
   uint8_t* ws = p->ws;
   const int Md = p->cfg.mlp_dims, C = p->cfg.channels;
   const int Cp = (C + 63) / 64 * 64;
-  auto cast = [&](const std::string& name, size_t off, size_t n) {
-    launch_cast_bf16(p->P(params, name), ts.at<__nv_bfloat16>(ws, off), n, st); CNT();
+  auto cast = [&](const std::string& name, size_t off, int K, int N, int ld) {
+    add_pack_job_ptr(p, name, ts.at<void>(ws, off), K, N, 1, ld);
   };
   for (int l = 0; l < ts.L; ++l) {
     const std::string s = "l" + std::to_string(l) + ".";
-    cast(s + "attn.qkv.kernel", ts.off_w_qkv[l], 128 * 384);
-    cast(s + "attn.out.kernel", ts.off_w_o[l], 128 * 128);
-    cast(s + "ffn1.kernel", ts.off_w_ffn1[l], static_cast<size_t>(128) * Md);
-    cast(s + "ffn2.kernel", ts.off_w_ffn2[l], static_cast<size_t>(Md) * 128);
+    cast(s + "attn.qkv.kernel", ts.off_w_qkv[l], 128, 384, 384);
+    cast(s + "attn.out.kernel", ts.off_w_o[l], 128, 128, 128);
+    cast(s + "ffn1.kernel", ts.off_w_ffn1[l], 128, Md, Md);
+    cast(s + "ffn2.kernel", ts.off_w_ffn2[l], Md, 128, 128);
   }
-  if (ts.L) cast("post.kernel", ts.off_w_post, static_cast<size_t>(128) * Md);
+  if (ts.L) cast("post.kernel", ts.off_w_post, 128, Md, Md);
   for (int k = 0; k < ts.K; ++k) {
     const std::string s = "k" + std::to_string(k) + ".";
-    cast(s + "res.a.kernel", ts.off_w_a[k], static_cast<size_t>(Md) * Md);
-    cast(s + "res.b.kernel", ts.off_w_b[k], static_cast<size_t>(Md) * Md);
-    cast(s + "film.ss.kernel", ts.off_w_ss[k], static_cast<size_t>(512) * 2 * Md);
+    cast(s + "res.a.kernel", ts.off_w_a[k], Md, Md, Md);
+    cast(s + "res.b.kernel", ts.off_w_b[k], Md, Md, Md);
+    cast(s + "film.ss.kernel", ts.off_w_ss[k], 512, 2 * Md, 2 * Md);
   }
-  launch_cast_pad_bf16(p->P(params, "out.kernel"), ts.at<__nv_bfloat16>(ws, ts.off_w_out), Md, C, Cp, st); CNT();
-  SMD_LAUNCH_CHECK("train_pack");
-  return SMD_OK;
+  cast("out.kernel", ts.off_w_out, Md, C, Cp);   // zero-padded to Cp columns (padding zeroed at bind)
 }
 
 static cudaError_t gemm_k(const GemmOp& op0, int rows, int K, int splits, const GemmEpilogue& e, cudaStream_t st) {

@@ -27,165 +27,159 @@ struct LnFilmBwdArgs {
   int M, N, S;           // S in {1, 32}: rows per sample
 };
 
-template <int NCH>
-__global__ void __launch_bounds__(256)
+// blockDim.x = N / 4 threads (N <= 4096): each thread owns one float4 column group; 4 rows per iteration so
+// that 8 independent 16-byte loads per thread are in flight and one block reduction serves 4 rows.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
-  __shared__ float red[2][8][2];
+  constexpr int RPI = 4;
+  __shared__ float red[2][32][2 * RPI];
+  __shared__ float tot[2][2 * RPI];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
   const int r0 = blockIdx.x * 32;
   const int N = a.N;
+  const int c = tid * 4;
   const float inv_n = 1.0f / static_cast<float>(N);
   const bool film = a.ss != nullptr;
-  float gam[NCH][4], bet[NCH][4], sc[NCH][4], sh[NCH][4];
-  float acc_dg[NCH][4], acc_db[NCH][4], acc_bias[NCH][4], acc_dsc[NCH][4], acc_dsh[NCH][4];
-#pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int c = tid * 4 + 1024 * j;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc_dg[j][i] = acc_db[j][i] = acc_bias[j][i] = acc_dsc[j][i] = acc_dsh[j][i] = 0.f;
-      gam[j][i] = (c < N) ? a.gamma[c + i] : 0.f;
-      bet[j][i] = (c < N) ? a.beta[c + i] : 0.f;
-      sc[j][i] = 1.f; sh[j][i] = 0.f;
-    }
-  }
   const bool per_block_sample = (a.S == 32);
-  if (film && per_block_sample) {
+  float gam[4], bet[4], sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc_dg[4] = {0, 0, 0, 0}, acc_db[4] = {0, 0, 0, 0}, acc_bias[4] = {0, 0, 0, 0};
+  float acc_dsc[4] = {0, 0, 0, 0}, acc_dsh[4] = {0, 0, 0, 0};
+  {
+    const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(a.beta + c);
+    gam[0] = g4.x; gam[1] = g4.y; gam[2] = g4.z; gam[3] = g4.w;
+    bet[0] = b4.x; bet[1] = b4.y; bet[2] = b4.z; bet[3] = b4.w;
+  }
+  if (film && per_block_sample && r0 < a.M) {
     const float* sp = a.ss + static_cast<size_t>(r0 / 32) * 2 * N;
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int c = tid * 4 + 1024 * j;
-      if (c < N) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { sc[j][i] = sp[c + i]; sh[j][i] = sp[N + c + i]; }
-      }
-    }
+    const float4 s4 = *reinterpret_cast<const float4*>(sp + c);
+    const float4 h4 = *reinterpret_cast<const float4*>(sp + N + c);
+    sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+    sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
   }
-  for (int r = 0; r < 32; ++r) {
-    const int row = r0 + r;
-    const bool ok = row < a.M;   // block-uniform
-    float dxh[NCH][4], xh[NCH][4];
-    float p1 = 0.f, p2 = 0.f, rstd = 0.f;
-    if (ok) {
-      const float s1 = a.stats[2 * static_cast<size_t>(row)], s2 = a.stats[2 * static_cast<size_t>(row) + 1];
-      const float mean = s1 * inv_n;
-      rstd = rsqrtf(s2 * inv_n - mean * mean + 1e-6f);
-      if (film && !per_block_sample) {
-        const float* sp = a.ss + static_cast<size_t>(row / a.S) * 2 * N;
+  for (int r = 0; r < 32; r += RPI) {
+    const int buf = (r / RPI) & 1;
+    float dxh[RPI][4], xh[RPI][4], rstd[RPI], part[2 * RPI];
+    float4 g4[RPI], u4[RPI];
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const int c = tid * 4 + 1024 * j;
-          if (c < N) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { sc[j][i] = sp[c + i]; sh[j][i] = sp[N + c + i]; }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const int c = tid * 4 + 1024 * j;
-        if (c < N) {
-          const float4 g4 = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
-          const float4 u4 = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
-          const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-          const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-          float dsc_row[4], dsh_row[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x = (uu[i] - mean) * rstd;
-            const float yln = x * gam[j][i] + bet[j][i];
-            const float f = film ? (sc[j][i] * yln + sh[j][i]) : yln;
-            const float dact = (a.act == 2) ? gg[i] * swish_grad(f) : gg[i];
-            const float dyln = film ? dact * sc[j][i] : dact;
-            dsh_row[i] = dact; dsc_row[i] = dact * yln;
-            acc_db[j][i] += dyln;
-            acc_dg[j][i] += dyln * x;
-            const float d = dyln * gam[j][i];
-            dxh[j][i] = d; xh[j][i] = x;
-            p1 += d; p2 += d * x;
-          }
-          if (film) {
-            if (per_block_sample) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { acc_dsc[j][i] += dsc_row[i]; acc_dsh[j][i] += dsh_row[i]; }
-            } else if (a.dss) {
-              float* dp = a.dss + static_cast<size_t>(row / a.S) * 2 * N;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (a.dss_accum) { dp[c + i] += dsc_row[i]; dp[N + c + i] += dsh_row[i]; }
-                else { dp[c + i] = dsc_row[i]; dp[N + c + i] = dsh_row[i]; }
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { dxh[j][i] = 0.f; xh[j][i] = 0.f; }
-        }
+    for (int q = 0; q < RPI; ++q) {   // issue all loads first
+      const int row = r0 + r + q;
+      if (row < a.M) {
+        g4[q] = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
+        u4[q] = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
+      } else {
+        g4[q] = make_float4(0, 0, 0, 0); u4[q] = make_float4(0, 0, 0, 0);
       }
     }
-    p1 = warp_sum(p1); p2 = warp_sum(p2);
-    if (lane == 0) { red[r & 1][warp][0] = p1; red[r & 1][warp][1] = p2; }
-    __syncthreads();
-    if (ok) {
-      float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) { t1 += red[r & 1][w][0]; t2 += red[r & 1][w][1]; }
-      const float m1 = t1 * inv_n, m2 = t2 * inv_n;
+    for (int q = 0; q < RPI; ++q) {
+      const int row = r0 + r + q;
+      part[2 * q] = 0.f; part[2 * q + 1] = 0.f; rstd[q] = 0.f;
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const int c = tid * 4 + 1024 * j;
-        if (c < N) {
-          float dx[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dx[i] = rstd * (dxh[j][i] - m1 - xh[j][i] * m2);
-          if (a.dres) {
-            const float4 d4 = *reinterpret_cast<const float4*>(a.dres + static_cast<size_t>(row) * N + c);
-            dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc_bias[j][i] += dx[i];
-          *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * N + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
-          if (a.dx16) {
-            __nv_bfloat162 q0 = __floats2bfloat162_rn(dx[0], dx[1]);
-            __nv_bfloat162 q1 = __floats2bfloat162_rn(dx[2], dx[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&q0);
-            pk.y = *reinterpret_cast<uint32_t*>(&q1);
-            *reinterpret_cast<uint2*>(a.dx16 + static_cast<size_t>(row) * N + c) = pk;
-          }
+      for (int i = 0; i < 4; ++i) { dxh[q][i] = 0.f; xh[q][i] = 0.f; }
+      if (row < a.M) {
+        const float s1 = a.stats[2 * static_cast<size_t>(row)], s2 = a.stats[2 * static_cast<size_t>(row) + 1];
+        const float mean = s1 * inv_n;
+        rstd[q] = rsqrtf(s2 * inv_n - mean * mean + 1e-6f);
+        if (film && !per_block_sample) {
+          const float* sp = a.ss + static_cast<size_t>(row / a.S) * 2 * N;
+          const float4 s4 = *reinterpret_cast<const float4*>(sp + c);
+          const float4 h4 = *reinterpret_cast<const float4*>(sp + N + c);
+          sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+          sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
         }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int c = tid * 4 + 1024 * j;
-    if (c < N) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        atomicAdd(a.dgamma + c + i, acc_dg[j][i]);
-        atomicAdd(a.dbeta + c + i, acc_db[j][i]);
-        if (a.dbias) atomicAdd(a.dbias + c + i, acc_bias[j][i]);
-      }
-      if (film && per_block_sample && a.dss && r0 < a.M) {
-        float* dp = a.dss + static_cast<size_t>(r0 / 32) * 2 * N;
+        const float gg[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w};
+        const float uu[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
+        float dsc_row[4], dsh_row[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (a.dss_accum) { dp[c + i] += acc_dsc[j][i]; dp[N + c + i] += acc_dsh[j][i]; }
-          else { dp[c + i] = acc_dsc[j][i]; dp[N + c + i] = acc_dsh[j][i]; }
+          const float x = (uu[i] - mean) * rstd[q];
+          const float yln = x * gam[i] + bet[i];
+          const float f = film ? (sc[i] * yln + sh[i]) : yln;
+          const float dact = (a.act == 2) ? gg[i] * swish_grad(f) : gg[i];
+          const float dyln = film ? dact * sc[i] : dact;
+          dsh_row[i] = dact; dsc_row[i] = dact * yln;
+          acc_db[i] += dyln;
+          acc_dg[i] += dyln * x;
+          const float d = dyln * gam[i];
+          dxh[q][i] = d; xh[q][i] = x;
+          part[2 * q] += d; part[2 * q + 1] += d * x;
+        }
+        if (film) {
+          if (per_block_sample) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc_dsc[i] += dsc_row[i]; acc_dsh[i] += dsh_row[i]; }
+          } else if (a.dss) {
+            float* dp = a.dss + static_cast<size_t>(row / a.S) * 2 * N;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (a.dss_accum) { dp[c + i] += dsc_row[i]; dp[N + c + i] += dsh_row[i]; }
+              else { dp[c + i] = dsc_row[i]; dp[N + c + i] = dsh_row[i]; }
+            }
+          }
         }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * RPI; ++j) {
+      const float v = warp_sum(part[j]);
+      if (lane == 0) red[buf][warp][j] = v;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < 2 * RPI) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[buf][w][lane];
+      tot[buf][lane] = t * inv_n;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      const int row = r0 + r + q;
+      if (row < a.M) {
+        const float m1 = tot[buf][2 * q], m2 = tot[buf][2 * q + 1];
+        float dx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dx[i] = rstd[q] * (dxh[q][i] - m1 - xh[q][i] * m2);
+        if (a.dres) {
+          const float4 d4 = *reinterpret_cast<const float4*>(a.dres + static_cast<size_t>(row) * N + c);
+          dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_bias[i] += dx[i];
+        *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * N + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        if (a.dx16) {
+          __nv_bfloat162 q0 = __floats2bfloat162_rn(dx[0], dx[1]);
+          __nv_bfloat162 q1 = __floats2bfloat162_rn(dx[2], dx[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&q0);
+          pk.y = *reinterpret_cast<uint32_t*>(&q1);
+          *reinterpret_cast<uint2*>(a.dx16 + static_cast<size_t>(row) * N + c) = pk;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(a.dgamma + c + i, acc_dg[i]);
+    atomicAdd(a.dbeta + c + i, acc_db[i]);
+    if (a.dbias) atomicAdd(a.dbias + c + i, acc_bias[i]);
+  }
+  if (film && per_block_sample && a.dss && r0 < a.M) {
+    float* dp = a.dss + static_cast<size_t>(r0 / 32) * 2 * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (a.dss_accum) { dp[c + i] += acc_dsc[i]; dp[N + c + i] += acc_dsh[i]; }
+      else { dp[c + i] = acc_dsc[i]; dp[N + c + i] = acc_dsh[i]; }
     }
   }
 }
 
 inline void launch_ln_film_act_bwd(const LnFilmBwdArgs& a, cudaStream_t st) {
   const int blocks = (a.M + 31) / 32;
-  const int nch = (a.N + 1023) / 1024;
-  if (nch == 1) ln_film_act_bwd_kernel<1><<<blocks, 256, 0, st>>>(a);
-  else if (nch == 2) ln_film_act_bwd_kernel<2><<<blocks, 256, 0, st>>>(a);
-  else if (nch == 3) ln_film_act_bwd_kernel<3><<<blocks, 256, 0, st>>>(a);
-  else ln_film_act_bwd_kernel<4><<<blocks, 256, 0, st>>>(a);
+  if (a.N / 4 <= 512) ln_film_act_bwd_kernel<512><<<blocks, a.N / 4, 0, st>>>(a);
+  else ln_film_act_bwd_kernel<1024><<<blocks, a.N / 4, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -272,21 +266,42 @@ inline void launch_ln128_bwd(const Ln128BwdArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[n] += sum_m in[m][n]
 // ---------------------------------------------------------------------------------------------------
+// fp32: one column per thread; bf16: two adjacent columns per thread (4-byte loads); 64 rows per block
 template <typename T>
 __global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int M, int N) {
-  const int n = blockIdx.x * 128 + threadIdx.x;
-  const int m0 = blockIdx.y * 256, m1 = min(M, m0 + 256);
-  if (n >= N) return;
-  float s = 0.f;
-  for (int m = m0; m < m1; ++m) {
-    if constexpr (sizeof(T) == 2) s += __bfloat162float(in[static_cast<size_t>(m) * ld + n]);
-    else s += in[static_cast<size_t>(m) * ld + n];
+  const int m0 = blockIdx.y * 64, m1 = min(M, m0 + 64);
+  if constexpr (sizeof(T) == 2) {
+    const int n = (blockIdx.x * 128 + threadIdx.x) * 2;
+    if (n >= N) return;
+    float s0 = 0.f, s1 = 0.f;
+    if (n + 1 < N && (ld & 1) == 0) {
+#pragma unroll 8
+      for (int m = m0; m < m1; ++m) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + static_cast<size_t>(m) * ld + n));
+        s0 += f.x; s1 += f.y;
+      }
+      atomicAdd(out + n, s0); atomicAdd(out + n + 1, s1);
+    } else {
+      for (int m = m0; m < m1; ++m) s0 += __bfloat162float(in[static_cast<size_t>(m) * ld + n]);
+      atomicAdd(out + n, s0);
+      if (n + 1 < N) {
+        for (int m = m0; m < m1; ++m) s1 += __bfloat162float(in[static_cast<size_t>(m) * ld + n + 1]);
+        atomicAdd(out + n + 1, s1);
+      }
+    }
+  } else {
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int m = m0; m < m1; ++m) s += in[static_cast<size_t>(m) * ld + n];
+    atomicAdd(out + n, s);
   }
-  atomicAdd(out + n, s);
 }
 template <typename T>
 inline void launch_colsum(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
-  dim3 grid((N + 127) / 128, (M + 255) / 256);
+  const int cols_per_block = (sizeof(T) == 2) ? 256 : 128;
+  dim3 grid((N + cols_per_block - 1) / cols_per_block, (M + 63) / 64);
   colsum_kernel<T><<<grid, 128, 0, st>>>(in, ld, out, M, N);
 }
 
@@ -429,65 +444,13 @@ inline void launch_embed_bwd(const float* x, const float* dh, float* dW, int M, 
   embed_bwd_kernel<<<grid, 128, 0, st>>>(x, dh, dW, M, C);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// small fp32 linear layers of the FiLM generator: weight gradient and input gradient
-// ---------------------------------------------------------------------------------------------------
-// dW[k][n] (+)= sum_r x[r][k] g[r][n]; block = 128 columns x 8 k-rows
-__global__ void __launch_bounds__(128)
-small_linear_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dW, int R,
-                          int K, int N) {
-  __shared__ float sx[64][8];
-  const int n = blockIdx.x * 128 + threadIdx.x;
-  const int k0 = blockIdx.y * 8;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int rb = 0; rb < R; rb += 64) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 8; i += 128) {
-      const int rr = i / 8, kk = i % 8;
-      sx[rr][kk] = (rb + rr < R && k0 + kk < K) ? x[static_cast<size_t>(rb + rr) * K + k0 + kk] : 0.f;
-    }
-    __syncthreads();
-    const int lim = min(64, R - rb);
-    if (n < N) {
-      for (int rr = 0; rr < lim; ++rr) {
-        const float gv = g[static_cast<size_t>(rb + rr) * N + n];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(sx[rr][i], gv, acc[i]);
-      }
-    }
-  }
-  if (n < N)
-    for (int i = 0; i < 8 && k0 + i < K; ++i) atomicAdd(dW + static_cast<size_t>(k0 + i) * N + n, acc[i]);
-}
+// small fp32 linear layers of the FiLM generator: weight gradient and input gradient (tiled SGEMM, kernels.cu)
 inline void launch_small_linear_bwd_w(const float* x, const float* g, float* dW, int R, int K, int N, cudaStream_t st) {
-  dim3 grid((N + 127) / 128, (K + 7) / 8);
-  small_linear_bwd_w_kernel<<<grid, 128, 0, st>>>(x, g, dW, R, K, N);
-}
-// dx[r][k] = (sum_n g[r][n] W[k][n]) * (pre ? swish'(pre[r][k]) : 1); one CTA per row r, one warp per k (looped)
-__global__ void __launch_bounds__(256)
-small_linear_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ W, const float* __restrict__ pre,
-                          float* __restrict__ dx, int K, int N) {
-  extern __shared__ float sg[];  // [N]
-  const int r = blockIdx.x;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) sg[i] = g[static_cast<size_t>(r) * N + i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < K; k += 8) {
-    const float* wr = W + static_cast<size_t>(k) * N;
-    float s = 0.f;
-    for (int n = lane; n < N; n += 32) s = fmaf(sg[n], __ldg(wr + n), s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (pre) s *= swish_grad(pre[static_cast<size_t>(r) * K + k]);
-      dx[static_cast<size_t>(r) * K + k] = s;
-    }
-  }
+  launch_sgemm_small(2, x, g, nullptr, dW, nullptr, nullptr, K, N, R, 0, st);   // dW[K][N] = x[R][K]^T g[R][N]
 }
 inline void launch_small_linear_bwd_x(const float* g, const float* W, const float* pre, float* dx, int R, int K, int N,
                                       cudaStream_t st) {
-  small_linear_bwd_x_kernel<<<R, 256, N * sizeof(float), st>>>(g, W, pre, dx, K, N);
+  launch_sgemm_small(1, g, W, nullptr, dx, nullptr, pre, R, K, N, 0, st);       // dx[R][K] = g[R][N] W[K][N]^T
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -56,7 +56,8 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kCG == 1) ? 4 : 6;
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kScratchBytes = 4 * 32 * 33 * 4;                    // per-epilogue-warp transpose scratch
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kScratchBytes + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
@@ -206,26 +207,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    // ===================== epilogue warps (TMEM -> registers -> smem transpose -> coalesced global) ============
+    // tcgen05.ld hands each thread one ROW of the tile; a row-per-thread global access would be 32 scattered 16-byte
+    // transactions per instruction, so every global tile access goes through a per-warp 32x33 shared-memory scratch
+    // and is issued as whole 128-byte (fp32) / 64-byte (bf16) row segments.
     const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may access
+    float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + q * (32 * 33);
+    uint32_t* scrw = reinterpret_cast<uint32_t*>(scr);
+    const int f_r = static_cast<int>(lane >> 3), f_c = static_cast<int>(lane & 7u) * 4;  // fp32: 4 rows x 128 B / instr
+    const int h_r = static_cast<int>(lane >> 2), h_c = static_cast<int>(lane & 3u) * 8;  // bf16: 8 rows x 64 B / instr
     int acc = 0; uint32_t acc_phase = 0;
     const float oscale = (ep.out_scale != 0.0f) ? ep.out_scale : 1.0f;
+    const bool do_ln = (ep.ln_gamma != nullptr);
+    const bool aligned_ok = ((ep.residual == nullptr) || (ep.ld_res & 3) == 0) &&
+                            ((ep.out_f32 == nullptr) || (ep.ld_f32 & 3) == 0) &&
+                            ((ep.out_bf16 == nullptr && ep.out_bf16_pre == nullptr) || (ep.ld_bf16 & 7) == 0) &&
+                            ((ep.gelu_grad_of == nullptr) || (ep.ld_gg & 7) == 0);
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int mn = tile / splits;
       const bool first_split = (tile % splits) == 0;
-      const int row = (mn / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u + lane);
+      const int row_base = (mn / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u);
+      const int row = row_base + static_cast<int>(lane);
       const int n0 = (mn % num_n) * BN;
       const bool row_ok = row < sh.M;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
-      const bool do_ln = (ep.ln_gamma != nullptr);
       float s1 = 0.f, s2 = 0.f;
       float mean = 0.f, rstd = 0.f;
       const int npass = do_ln ? 2 : 1;
       for (int pass = 0; pass < npass; ++pass) {
         for (int c0 = 0; c0 < BN; c0 += 32) {
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row guard below
+          __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
           uint32_t r[32];
           const bool half = (BN - c0) < 32;  // 16-column tail
           if (!half) {
@@ -239,46 +252,162 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tmem_ld_wait();
           const int ncols = half ? 16 : 32;
           const int col0 = n0 + c0;
-          if (!row_ok) continue;
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
-          const bool full_chunk = (col0 + ncols <= sh.N);
-          // LayerNorm pass 1 with an fp32 output: take v back from what this thread stored in pass 0 (the
-          // residual may alias the output buffer, so it must not be re-added)
           const bool reload = (pass == 1) && (ep.out_f32 != nullptr);
+          const bool write_bf16 = (ep.out_bf16 != nullptr) && (do_ln ? (pass == 1) : true);
+
+          if (!half && aligned_ok && col0 + 32 <= sh.N) {
+            // ------------------------------ fast path: full 32-column chunk ------------------------------
+            if (reload) {
+              // LayerNorm pass 1: take v back from what this warp stored in pass 0 (the residual may alias the
+              // output buffer, so it must not be re-added); __syncwarp orders the warp's own global writes
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + f_r, grow = row_base + rr;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < sh.M) t = *reinterpret_cast<const float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c);
+                float* d = scr + rr * 33 + f_c;
+                d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = scr[lane * 33 + i];
+              __syncwarp();
+            } else {
+              if (ep.bias != nullptr && first_split) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += __ldg(ep.bias + col0 + i);
+              }
+              if (ep.residual != nullptr && first_split) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + f_r, grow = row_base + rr;
+                  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (grow < sh.M) t = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + col0 + f_c);
+                  float* d = scr + rr * 33 + f_c;
+                  d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
+                __syncwarp();
+              }
+              if (ep.gelu_grad_of != nullptr) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                  const int rr = it * 8 + h_r, grow = row_base + rr;
+                  uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                  if (grow < sh.M) t = *reinterpret_cast<const uint4*>(ep.gelu_grad_of + static_cast<size_t>(grow) * ep.ld_gg + col0 + h_c);
+                  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&t);
+                  float* d = scr + rr * 33 + h_c;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hp[j]); d[2 * j] = f.x; d[2 * j + 1] = f.y; }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= gelu_tanh_grad_f(scr[lane * 33 + i]);
+                __syncwarp();
+              }
+            }
+            if (pass == 0) {
+              if (ep.row_stats != nullptr || do_ln) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+              }
+              if (ep.out_f32 != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + f_r, grow = row_base + rr;
+                  if (grow < sh.M) {
+                    const float* sp = scr + rr * 33 + f_c;
+                    float* op = ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c;
+                    if (ep.atomic_out) {
+                      atomicAdd(op, sp[0]); atomicAdd(op + 1, sp[1]); atomicAdd(op + 2, sp[2]); atomicAdd(op + 3, sp[3]);
+                    } else {
+                      *reinterpret_cast<float4*>(op) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    }
+                  }
+                }
+                __syncwarp();
+              }
+              if (ep.out_bf16_pre != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                  scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                  const int rr = it * 8 + h_r, grow = row_base + rr;
+                  if (grow < sh.M) {
+                    const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
+                    *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                        make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                  }
+                }
+                __syncwarp();
+              }
+            }
+            if (write_bf16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float w0, w1;
+                if (do_ln) {
+                  w0 = (v[2 * j] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + 2 * j)) + __ldg(ep.ln_beta + col0 + 2 * j);
+                  w1 = (v[2 * j + 1] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + 2 * j + 1)) + __ldg(ep.ln_beta + col0 + 2 * j + 1);
+                } else {
+                  w0 = act_apply(v[2 * j], ep.act);
+                  w1 = act_apply(v[2 * j + 1], ep.act);
+                }
+                __nv_bfloat162 pk = __floats2bfloat162_rn(w0, w1);
+                scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + h_r, grow = row_base + rr;
+                if (grow < sh.M) {
+                  const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
+                  *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                      make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                }
+              }
+              __syncwarp();
+            }
+            continue;
+          }
+
+          // ------------------------------ slow path: ragged / unaligned chunk (row per thread) ---------------
+          if (!row_ok) continue;
           if (reload) {
             const float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i < ncols && col0 + i < sh.N) v[i] = op[i];
-          }
-          if (ep.bias != nullptr && first_split && !reload) {
+          } else {
+            if (ep.bias != nullptr && first_split) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols && col0 + i < sh.N) v[i] += __ldg(ep.bias + col0 + i);
-          }
-          if (ep.residual != nullptr && first_split && !reload) {
-            const float* rp = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
-            if (full_chunk && (ep.ld_res & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                if (i < ncols) {
-                  const float4 t = *reinterpret_cast<const float4*>(rp + i);
-                  v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-                }
-              }
-            } else {
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols && col0 + i < sh.N) v[i] += __ldg(ep.bias + col0 + i);
+            }
+            if (ep.residual != nullptr && first_split) {
+              const float* rp = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (i < ncols && col0 + i < sh.N) v[i] += rp[i];
             }
-          }
-          if (ep.gelu_grad_of != nullptr && !reload) {
-            const __nv_bfloat16* gp = ep.gelu_grad_of + static_cast<size_t>(row) * ep.ld_gg + col0;
+            if (ep.gelu_grad_of != nullptr) {
+              const __nv_bfloat16* gp = ep.gelu_grad_of + static_cast<size_t>(row) * ep.ld_gg + col0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols && col0 + i < sh.N) v[i] *= gelu_tanh_grad_f(__bfloat162float(gp[i]));
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols && col0 + i < sh.N) v[i] *= gelu_tanh_grad_f(__bfloat162float(gp[i]));
+            }
           }
           if (pass == 0) {
             if (ep.row_stats != nullptr || do_ln) {
@@ -288,75 +417,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (ep.out_f32 != nullptr) {
               float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
-              if (ep.atomic_out) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < ncols && col0 + i < sh.N) atomicAdd(op + i, v[i]);
-              } else if (full_chunk && (ep.ld_f32 & 3) == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  if (i < ncols) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < ncols && col0 + i < sh.N) op[i] = v[i];
+              for (int i = 0; i < 32; ++i) {
+                if (i < ncols && col0 + i < sh.N) {
+                  if (ep.atomic_out) atomicAdd(op + i, v[i]); else op[i] = v[i];
+                }
               }
             }
             if (ep.out_bf16_pre != nullptr) {
               __nv_bfloat16* op = ep.out_bf16_pre + static_cast<size_t>(row) * ep.ld_bf16 + col0;
-              if (full_chunk && (ep.ld_bf16 & 7) == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  if (i < ncols) {
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                    *reinterpret_cast<uint4*>(op + i) = pk;
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(v[i]);
-              }
-            }
-          }
-          const bool write_bf16 = (ep.out_bf16 != nullptr) && (do_ln ? (pass == 1) : true);
-          if (write_bf16) {
-            float w[32];
-            if (do_ln) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int c = (col0 + i < sh.N) ? (col0 + i) : 0;
-                w[i] = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + c)) + __ldg(ep.ln_beta + c);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) w[i] = act_apply(v[i], ep.act);
-            }
-            __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
-            if (full_chunk && (ep.ld_bf16 & 7) == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (i < ncols) {
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(w[i], w[i + 1]);
-                  __nv_bfloat162 p1 = __floats2bfloat162_rn(w[i + 2], w[i + 3]);
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(w[i + 4], w[i + 5]);
-                  __nv_bfloat162 p3 = __floats2bfloat162_rn(w[i + 6], w[i + 7]);
-                  uint4 pk;
-                  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                  *reinterpret_cast<uint4*>(op + i) = pk;
-                }
-              }
-            } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(w[i]);
+                if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+          if (write_bf16) {
+            __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < ncols && col0 + i < sh.N) {
+                float w;
+                if (do_ln) w = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + i)) + __ldg(ep.ln_beta + col0 + i);
+                else w = act_apply(v[i], ep.act);
+                op[i] = __float2bfloat16_rn(w);
+              }
             }
           }
         }  // column chunks

@@ -221,40 +221,92 @@ void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R
   noise_encoding_kernel<<<(R * 64 + 127) / 128, 128, 0, st>>>(t, freqs, enc, R);
 }
 
-// y[r, n] = act(sum_k x[r,k] W[k,n] + b[n]);  block: 128 columns x 8 rows
-__global__ void __launch_bounds__(128)
-small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
-                    float* __restrict__ y, float* __restrict__ pre, int R, int K, int N, int act) {
-  extern __shared__ float sx[];  // [8][K]
-  const int r0 = blockIdx.y * 8;
-  const int nr = min(8, R - r0);
-  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
-    const int rr = i / K;
-    sx[i] = (rr < nr) ? x[static_cast<size_t>(r0 + rr) * K + (i % K)] : 0.f;
-  }
-  __syncthreads();
-  const int n = blockIdx.x * 128 + threadIdx.x;
-  if (n >= N) return;
-  float acc[8];
+// Tiled fp32 SGEMM for the small FiLM-generator layers (forward and backward), 64x64 tile, 4x4 per thread.
+//   MODE 0 (NN): C[M][N] = A[M][K] . B[K][N]          forward  y = x W
+//   MODE 1 (NT): C[M][N] = A[M][K] . B[N][K]^T        input grad  dx = g W^T
+//   MODE 2 (TN): C[M][N] = A[K][M]^T . B[K][N]        weight grad dW = x^T g
+// Epilogue: + bias[n]; optional pre-activation copy; act (2 = swish); optional * swish'(mul_pre[m][n]).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ bias,
+                   float* __restrict__ C, float* __restrict__ pre_out, const float* __restrict__ mul_pre, int M, int N,
+                   int K, int act) {
+  __shared__ float As[16][68];
+  __shared__ float Bs[16][68];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float w = __ldg(W + static_cast<size_t>(k) * N + n);
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(sx[i * K + k], w, acc[i]);
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // ---- stage A tile as As[kk][m] ----
+    if (MODE == 2) {  // A[K][M]: contiguous in m
+      for (int i = tid; i < 16 * 64; i += 256) {
+        const int kk = i >> 6, m = i & 63;
+        As[kk][m] = (k0 + kk < K && m0 + m < M) ? A[static_cast<size_t>(k0 + kk) * M + m0 + m] : 0.f;
+      }
+    } else {          // A[M][K]: contiguous in k
+      for (int i = tid; i < 16 * 64; i += 256) {
+        const int m = i >> 4, kk = i & 15;
+        As[kk][m] = (k0 + kk < K && m0 + m < M) ? A[static_cast<size_t>(m0 + m) * K + k0 + kk] : 0.f;
+      }
+    }
+    // ---- stage B tile as Bs[kk][n] ----
+    if (MODE == 1) {  // B[N][K]: contiguous in k
+      for (int i = tid; i < 16 * 64; i += 256) {
+        const int n = i >> 4, kk = i & 15;
+        Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? B[static_cast<size_t>(n0 + n) * K + k0 + kk] : 0.f;
+      }
+    } else {          // B[K][N]: contiguous in n
+      for (int i = tid; i < 16 * 64; i += 256) {
+        const int kk = i >> 6, n = i & 63;
+        Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? B[static_cast<size_t>(k0 + kk) * N + n0 + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
   }
-  const float bb = b ? b[n] : 0.f;
-  for (int i = 0; i < nr; ++i) {
-    float v = acc[i] + bb;
-    if (pre) pre[static_cast<size_t>(r0 + i) * N + n] = v;
-    if (act == 2) v = v / (1.0f + expf(-v));
-    y[static_cast<size_t>(r0 + i) * N + n] = v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      const size_t o = static_cast<size_t>(m) * N + n;
+      if (pre_out) pre_out[o] = v;
+      if (act == 2) v = v / (1.0f + expf(-v));
+      if (mul_pre) v *= swish_grad(mul_pre[o]);
+      C[o] = v;
+    }
   }
+}
+void launch_sgemm_small(int mode, const float* A, const float* B, const float* bias, float* C, float* pre_out,
+                        const float* mul_pre, int M, int N, int K, int act, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (mode == 0) sgemm_small_kernel<0><<<grid, 256, 0, st>>>(A, B, bias, C, pre_out, mul_pre, M, N, K, act);
+  else if (mode == 1) sgemm_small_kernel<1><<<grid, 256, 0, st>>>(A, B, bias, C, pre_out, mul_pre, M, N, K, act);
+  else sgemm_small_kernel<2><<<grid, 256, 0, st>>>(A, B, bias, C, pre_out, mul_pre, M, N, K, act);
 }
 void launch_small_linear(const float* x, const float* W, const float* b, float* y, int R, int K, int N, int act,
                          cudaStream_t st, float* pre) {
-  dim3 grid((N + 127) / 128, (R + 7) / 8);
-  small_linear_kernel<<<grid, 128, 8 * K * sizeof(float), st>>>(x, W, b, y, pre, R, K, N, act);
+  launch_sgemm_small(0, x, W, b, y, pre, nullptr, R, N, K, act, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -277,6 +329,43 @@ void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int
   dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
   pack_transpose_bf16_kernel<<<grid, block, 0, st>>>(src, dst, K, N);
 }
+// All weight repacks of one optimizer step in ONE launch: every 32x32 tile of every job is one CTA.
+__global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs,
+                                                         int njobs) {
+  __shared__ float tile[32][33];
+  __shared__ PackJob job;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int j = 0;
+    while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].tile0) ++j;
+    job = jobs[j];
+  }
+  __syncthreads();
+  const int t = blockIdx.x - job.tile0;
+  const int k0 = (t / job.tiles_n) * 32, n0 = (t % job.tiles_n) * 32;
+  const float* src = params + job.src_off;
+  __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+  const int K = job.K, N = job.N;
+  if (job.mode == 0) {   // dst[n][k] = src[k][n]
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      tile[i][threadIdx.x] = (k < K && n < N) ? src[static_cast<size_t>(k) * N + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int n = n0 + i, k = k0 + threadIdx.x;
+      if (n < N && k < K) dst[static_cast<size_t>(n) * job.ld + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  } else {               // dst[k][n] = src[k][n] with row pitch ld
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (k < K && n < N) dst[static_cast<size_t>(k) * job.ld + n] = __float2bfloat16_rn(src[static_cast<size_t>(k) * N + n]);
+    }
+  }
+}
+void launch_pack_multi(const float* params, const PackJob* jobs_dev, int njobs, int total_tiles, cudaStream_t st) {
+  pack_multi_kernel<<<total_tiles, dim3(32, 8), 0, st>>>(params, jobs_dev, njobs);
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)

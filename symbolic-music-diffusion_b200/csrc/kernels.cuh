@@ -132,8 +132,15 @@ void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R
 void launch_small_linear(const float* x, const float* W, const float* b, float* y, int R, int K, int N, int act,
                          cudaStream_t st, float* pre_act_out = nullptr);
 
+// tiled fp32 SGEMM (mode 0: A.B, 1: A.B^T, 2: A^T.B) with bias / pre-activation save / swish / * swish'(mul_pre)
+void launch_sgemm_small(int mode, const float* A, const float* B, const float* bias, float* C, float* pre_out,
+                        const float* mul_pre, int M, int N, int K, int act, cudaStream_t st);
+
 // bf16 dst[n][k] = src[k][n]  (fp32 (in,out) Dense kernel -> K-major tensor-core operand)
 void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int N, cudaStream_t st);
+// one launch for a list of repack jobs (mode 0: transpose to [N][K] with pitch ld; mode 1: plain cast, pitch ld)
+struct PackJob { long long src_off; void* dst; int K, N, mode, ld, tile0, tiles_n; };
+void launch_pack_multi(const float* params, const PackJob* jobs_dev, int njobs, int total_tiles, cudaStream_t st);
 // bf16 dst[i] = src[i]
 void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
 

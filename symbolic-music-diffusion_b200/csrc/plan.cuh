@@ -66,6 +66,8 @@ struct smd_plan {
   size_t ws_bytes = 0;
   uint8_t* ws = nullptr;
   bool packed = false;
+  std::vector<smd::PackJob> pack_jobs;
+  int pack_tiles = 0;
   // ---- GEMM ops ----
   std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b;
   GemmOp op_post, op_out, op_in;
@@ -101,5 +103,6 @@ inline GemmEpilogue epi() {
 int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
                 float* y, cudaStream_t st, TrainState* save);
 int train_bind(smd_plan* p);
-int train_pack(smd_plan* p, const float* params, cudaStream_t st);
+void train_pack_jobs(smd_plan* p);
+void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld);
 }  // namespace smd

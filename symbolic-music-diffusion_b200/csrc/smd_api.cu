@@ -145,6 +145,7 @@ static void build_workspace(smd_plan* p) {
   ws_add(p, "slots", kMaxT * 4);
   ws_add(p, "t_ptr", 64);
   ws_add(p, "abar", (kMaxT + 1) * 4);
+  ws_add(p, "packjobs", 256 * sizeof(PackJob));
   if (c.training) train_workspace(p->train, c, p->Mp, p->K, [&](const std::string& n, size_t b) { return ws_add(p, n, b); });
 }
 
@@ -399,6 +400,53 @@ __global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uin
     out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, i, n));
 }
 
+static void add_pack_job(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld) {
+  add_pack_job_ptr(p, src, dst, K, N, mode, ld);
+}
+void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld) {
+  PackJob j;
+  j.src_off = p->off.at(src); j.dst = dst; j.K = K; j.N = N; j.mode = mode; j.ld = ld;
+  j.tiles_n = (N + 31) / 32;
+  j.tile0 = p->pack_tiles;
+  p->pack_tiles += ((K + 31) / 32) * j.tiles_n;
+  p->pack_jobs.push_back(j);
+}
+
+// job list: transposed [out][in] copies for the forward GEMMs (+ plain (in,out) copies for dX when training)
+static int build_pack_jobs(smd_plan* plan) {
+  const smd_config& c = plan->cfg;
+  const int Md = c.mlp_dims, C = c.channels;
+  plan->pack_jobs.clear();
+  plan->pack_tiles = 0;
+  auto T = [&](const std::string& src, const std::string& dst, int K, int N) {
+    add_pack_job(plan, src, plan->buf<void>(dst), K, N, 0, K);
+  };
+  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
+    for (int l = 0; l < c.num_layers; ++l) {
+      const std::string s = "l" + std::to_string(l) + ".", d = "w.l" + std::to_string(l) + ".";
+      T(s + "attn.qkv.kernel", d + "qkv", kE, 3 * kE);
+      T(s + "attn.out.kernel", d + "o", kE, kE);
+      T(s + "ffn1.kernel", d + "ffn1", kE, Md);
+      T(s + "ffn2.kernel", d + "ffn2", Md, kE);
+    }
+    T("post.kernel", "w.post", kE, Md);
+  } else {
+    T("in.kernel", "w.in", C, Md);
+  }
+  for (int k = 0; k < plan->K; ++k) {
+    const std::string s = "k" + std::to_string(k) + ".res.", d = "w.k" + std::to_string(k) + ".";
+    T(s + "a.kernel", d + "a", Md, Md);
+    T(s + "b.kernel", d + "b", Md, Md);
+  }
+  T("out.kernel", "w.out", Md, C);
+  if (c.training) train_pack_jobs(plan);
+  if (plan->pack_jobs.size() > 256) { set_error("too many pack jobs"); return SMD_ERR_INVALID; }
+  SMD_CUDA(cudaMemcpy(plan->buf<PackJob>("packjobs"), plan->pack_jobs.data(), plan->pack_jobs.size() * sizeof(PackJob),
+                      cudaMemcpyHostToDevice));
+  return SMD_OK;
+}
+
+
 }  // namespace smd
 
 // =====================================================================================================
@@ -478,37 +526,17 @@ int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
     }
   SMD_CUDA(cudaMemcpy(plan->buf<float>("posenc"), pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
   if (plan->cfg.training) { rc = train_bind(plan); if (rc) return rc; }
+  rc = build_pack_jobs(plan);
+  if (rc) return rc;
   return SMD_OK;
 }
 
 int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
   if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const smd_config& c = plan->cfg;
-  const int Md = c.mlp_dims, C = c.channels;
-  auto pack = [&](const std::string& src, const std::string& dst, int K, int N) {
-    launch_pack_transpose_bf16(plan->P(params, src), plan->buf<__nv_bfloat16>(dst), K, N, st); CNT();
-  };
-  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
-    for (int l = 0; l < c.num_layers; ++l) {
-      const std::string s = "l" + std::to_string(l) + ".", d = "w.l" + std::to_string(l) + ".";
-      pack(s + "attn.qkv.kernel", d + "qkv", kE, 3 * kE);
-      pack(s + "attn.out.kernel", d + "o", kE, kE);
-      pack(s + "ffn1.kernel", d + "ffn1", kE, Md);
-      pack(s + "ffn2.kernel", d + "ffn2", Md, kE);
-    }
-    pack("post.kernel", "w.post", kE, Md);
-  } else {
-    pack("in.kernel", "w.in", C, Md);
-  }
-  for (int k = 0; k < plan->K; ++k) {
-    const std::string s = "k" + std::to_string(k) + ".res.", d = "w.k" + std::to_string(k) + ".";
-    pack(s + "a.kernel", d + "a", Md, Md);
-    pack(s + "b.kernel", d + "b", Md, Md);
-  }
-  pack("out.kernel", "w.out", Md, C);
+  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), static_cast<int>(plan->pack_jobs.size()), plan->pack_tiles, st);
+  CNT();
   SMD_LAUNCH_CHECK("pack_weights");
-  if (c.training) { int rc = train_pack(plan, params, st); if (rc) return rc; }
   plan->packed = true;
   return SMD_OK;
 }
