@@ -51,6 +51,8 @@ typedef struct smd_config {
   int max_batch;       /* largest number of examples one call may pass */
   int cta_group;       /* 1 or 2: tcgen05 cta_group used by the GEMMs (2 = CTA pairs, M=256 tiles) */
   int training;        /* 1: reserve the saved-activation / gradient buffers of smd_ddpm_train_step */
+  int sampler_T;       /* > 0: reserve a (K, sampler_T, 2*mlp_dims) FiLM table so the sampler evaluates the FiLM
+                          generator once per schedule instead of once per step (all samples share t) */
 } smd_config;
 
 const char* smd_last_error(void);

@@ -109,7 +109,7 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
   if (groups < 1) groups = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * kCG));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = SM::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];

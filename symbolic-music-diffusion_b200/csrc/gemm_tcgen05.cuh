@@ -56,14 +56,22 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kCG == 1) ? 4 : 6;
   static constexpr int kBarBytes = 256;
-  static constexpr int kScratchBytes = 4 * 32 * 33 * 4;                    // per-epilogue-warp transpose scratch
+  static constexpr int kEpiWarps = 8;                                       // 2 warps per TMEM lane quadrant
+  static constexpr int kScratchBytes = kEpiWarps * 32 * 33 * 4;            // per-epilogue-warp transpose scratch
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kScratchBytes + 1024;  // + alignment slack
 };
+
+// MUFU.TANH (abs error ~5e-4, far below the bf16 rounding of everything that consumes it)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   const float c = 0.7978845608028654f;
   const float u = c * (x + 0.044715f * x * x * x);
-  const float th = tanhf(u);
+  const float th = tanh_fast(u);
   return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * c * (1.0f + 3.0f * 0.044715f * x * x);
 }
 
@@ -71,7 +79,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_GELU_TANH) {
     const float c = 0.7978845608028654f;
     float u = c * (v + 0.044715f * v * v * v);
-    return 0.5f * v * (1.0f + tanhf(u));
+    return 0.5f * v * (1.0f + tanh_fast(u));
   } else if (act == ACT_SWISH) {
     return v / (1.0f + __expf(-v));
   }
@@ -79,7 +87,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 template <int kCG>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape sh, const GemmEpilogue ep) {
   using SM = GemmSmem<kCG>;
@@ -120,7 +128,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4 * kCG);
+      mbar_init(&tmem_empty[i], SM::kEpiWarps * kCG);
     }
     fence_barrier_init();
   }
@@ -211,8 +219,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // tcgen05.ld hands each thread one ROW of the tile; a row-per-thread global access would be 32 scattered 16-byte
     // transactions per instruction, so every global tile access goes through a per-warp 32x33 shared-memory scratch
     // and is issued as whole 128-byte (fp32) / 64-byte (bf16) row segments.
-    const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may access
-    float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + q * (32 * 33);
+    const uint32_t q = warp & 3u;          // TMEM lane quadrant this warp may access
+    const int eg = static_cast<int>(warp - 4u) >> 2;   // column group 0/1: the two warps of a quadrant split the chunks
+    float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * (32 * 33);
     uint32_t* scrw = reinterpret_cast<uint32_t*>(scr);
     const int f_r = static_cast<int>(lane >> 3), f_c = static_cast<int>(lane & 7u) * 4;  // fp32: 4 rows x 128 B / instr
     const int h_r = static_cast<int>(lane >> 2), h_c = static_cast<int>(lane & 3u) * 8;  // bf16: 8 rows x 64 B / instr
@@ -236,8 +245,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float s1 = 0.f, s2 = 0.f;
       float mean = 0.f, rstd = 0.f;
       const int npass = do_ln ? 2 : 1;
+      // full-row LayerNorm needs one warp to see the whole row: group 1 sits those tiles out
+      const int c_begin = do_ln ? (eg == 0 ? 0 : BN) : eg * 32;
+      const int c_step = do_ln ? 32 : 64;
+      // software prefetch of the residual / gelu-grad tiles of the NEXT chunk (their global latency would
+      // otherwise be fully exposed: only two warps per SM sub-partition work on the epilogue)
+      float4 rpre[8];
+      uint4 gpre[4];
+      const bool pre_res = (ep.residual != nullptr) && first_split && aligned_ok;
+      const bool pre_gg = (ep.gelu_grad_of != nullptr) && aligned_ok;
+      auto chunk_fast = [&](int c) { return (BN - c) >= 32 && aligned_ok && (n0 + c + 32 <= sh.N); };
+      auto prefetch = [&](int c) {
+        const int colp = n0 + c;
+        if (pre_res) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row_base + it * 4 + f_r;
+            rpre[it] = (grow < sh.M) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + colp + f_c)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (pre_gg) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int grow = row_base + it * 8 + h_r;
+            gpre[it] = (grow < sh.M) ? *reinterpret_cast<const uint4*>(ep.gelu_grad_of + static_cast<size_t>(grow) * ep.ld_gg + colp + h_c)
+                                     : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      };
+      if (c_begin < BN && chunk_fast(c_begin)) prefetch(c_begin);
       for (int pass = 0; pass < npass; ++pass) {
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < BN; c0 += c_step) {
           __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
           uint32_t r[32];
           const bool half = (BN - c0) < 32;  // 16-column tail
@@ -283,12 +322,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if (ep.residual != nullptr && first_split) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
-                  const int rr = it * 4 + f_r, grow = row_base + rr;
-                  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (grow < sh.M) t = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + col0 + f_c);
-                  float* d = scr + rr * 33 + f_c;
-                  d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                  float* d = scr + (it * 4 + f_r) * 33 + f_c;
+                  d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
                 }
+              }
+              if (ep.gelu_grad_of != nullptr) {
+                // staged after the residual below (scr is reused); keep the raw words in registers meanwhile
+              }
+              // issue the next chunk's global loads now: they complete while this chunk is processed
+              uint4 gcur[4];
+              if (pre_gg) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) gcur[it] = gpre[it];
+              }
+              {
+                const int cn = c0 + c_step;
+                if (cn < BN && chunk_fast(cn) && pass == 0) prefetch(cn);
+                else if (pass == 0 && npass == 2 && cn >= BN) { /* pass 1 reloads from out_f32 */ }
+              }
+              if (ep.residual != nullptr && first_split) {
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
@@ -297,11 +349,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if (ep.gelu_grad_of != nullptr) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
-                  const int rr = it * 8 + h_r, grow = row_base + rr;
-                  uint4 t = make_uint4(0u, 0u, 0u, 0u);
-                  if (grow < sh.M) t = *reinterpret_cast<const uint4*>(ep.gelu_grad_of + static_cast<size_t>(grow) * ep.ld_gg + col0 + h_c);
-                  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&t);
-                  float* d = scr + rr * 33 + h_c;
+                  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&gcur[it]);
+                  float* d = scr + (it * 8 + h_r) * 33 + h_c;
 #pragma unroll
                   for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hp[j]); d[2 * j] = f.x; d[2 * j + 1] = f.y; }
                 }

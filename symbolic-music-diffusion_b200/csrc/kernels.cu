@@ -149,7 +149,8 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 __global__ void __launch_bounds__(256)
 ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ g,
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S) {
+                   int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
+                   const int* __restrict__ film_row_dev) {
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -171,7 +172,7 @@ ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats,
   const float mean = s1 * inv_n;
   const float var = s2 * inv_n - mean * mean;
   const float rstd = rsqrtf(var + 1e-6f);
-  const size_t frow = film_bcast ? 0 : static_cast<size_t>(m / S);
+  const size_t frow = film_row_dev ? static_cast<size_t>(*film_row_dev) : (film_bcast ? 0 : static_cast<size_t>(m / S));
   const float* sc = scale ? scale + frow * film_ld : nullptr;
   const float* sh = shift ? shift + frow * film_ld : nullptr;
   __nv_bfloat16* orow = out + static_cast<size_t>(m) * N;
@@ -200,9 +201,10 @@ ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats,
 }
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
-                        int S, cudaStream_t st) {
+                        int S, cudaStream_t st, const int* film_row_dev) {
   const int blocks = (M + 7) / 8;
-  ln_film_act_kernel<<<blocks, 256, 0, st>>>(u, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N, S);
+  ln_film_act_kernel<<<blocks, 256, 0, st>>>(u, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N, S,
+                                             film_row_dev);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -241,32 +243,41 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ B, con
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    // ---- stage A tile as As[kk][m] ----
-    if (MODE == 2) {  // A[K][M]: contiguous in m
-      for (int i = tid; i < 16 * 64; i += 256) {
+  // register double-buffering: the global loads of chunk k0+16 are in flight while chunk k0 is multiplied
+  float ra[4], rb[4];
+  auto load_regs = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 256 * j;
+      if (MODE == 2) {  // A[K][M]: contiguous in m
         const int kk = i >> 6, m = i & 63;
-        As[kk][m] = (k0 + kk < K && m0 + m < M) ? A[static_cast<size_t>(k0 + kk) * M + m0 + m] : 0.f;
-      }
-    } else {          // A[M][K]: contiguous in k
-      for (int i = tid; i < 16 * 64; i += 256) {
+        ra[j] = (k0 + kk < K && m0 + m < M) ? A[static_cast<size_t>(k0 + kk) * M + m0 + m] : 0.f;
+      } else {          // A[M][K]: contiguous in k
         const int m = i >> 4, kk = i & 15;
-        As[kk][m] = (k0 + kk < K && m0 + m < M) ? A[static_cast<size_t>(m0 + m) * K + k0 + kk] : 0.f;
+        ra[j] = (k0 + kk < K && m0 + m < M) ? A[static_cast<size_t>(m0 + m) * K + k0 + kk] : 0.f;
       }
-    }
-    // ---- stage B tile as Bs[kk][n] ----
-    if (MODE == 1) {  // B[N][K]: contiguous in k
-      for (int i = tid; i < 16 * 64; i += 256) {
+      if (MODE == 1) {  // B[N][K]: contiguous in k
         const int n = i >> 4, kk = i & 15;
-        Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? B[static_cast<size_t>(n0 + n) * K + k0 + kk] : 0.f;
-      }
-    } else {          // B[K][N]: contiguous in n
-      for (int i = tid; i < 16 * 64; i += 256) {
+        rb[j] = (k0 + kk < K && n0 + n < N) ? B[static_cast<size_t>(n0 + n) * K + k0 + kk] : 0.f;
+      } else {          // B[K][N]: contiguous in n
         const int kk = i >> 6, n = i & 63;
-        Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? B[static_cast<size_t>(k0 + kk) * N + n0 + n] : 0.f;
+        rb[j] = (k0 + kk < K && n0 + n < N) ? B[static_cast<size_t>(k0 + kk) * N + n0 + n] : 0.f;
       }
     }
+  };
+  auto store_regs = [&]() {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 256 * j;
+      if (MODE == 2) As[i >> 6][i & 63] = ra[j]; else As[i & 15][i >> 4] = ra[j];
+      if (MODE == 1) Bs[i & 15][i >> 4] = rb[j]; else Bs[i >> 6][i & 63] = rb[j];
+    }
+  };
+  load_regs(0);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    store_regs();
     __syncthreads();
+    if (k0 + 16 < K) load_regs(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -333,14 +344,9 @@ void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int
 __global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs,
                                                          int njobs) {
   __shared__ float tile[32][33];
-  __shared__ PackJob job;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    int j = 0;
-    while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].tile0) ++j;
-    job = jobs[j];
-  }
-  __syncthreads();
-  const int t = blockIdx.x - job.tile0;
+  const PackJob job = jobs[blockIdx.y];           // grid = (max tiles of any job, njobs): surplus CTAs exit at once
+  const int t = blockIdx.x;
+  if (t >= ((job.K + 31) / 32) * job.tiles_n) return;
   const int k0 = (t / job.tiles_n) * 32, n0 = (t % job.tiles_n) * 32;
   const float* src = params + job.src_off;
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
@@ -362,8 +368,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict
     }
   }
 }
-void launch_pack_multi(const float* params, const PackJob* jobs_dev, int njobs, int total_tiles, cudaStream_t st) {
-  pack_multi_kernel<<<total_tiles, dim3(32, 8), 0, st>>>(params, jobs_dev, njobs);
+void launch_pack_multi(const float* params, const PackJob* jobs_dev, int njobs, int max_tiles, cudaStream_t st) {
+  pack_multi_kernel<<<dim3(max_tiles, njobs), dim3(32, 8), 0, st>>>(params, jobs_dev, njobs);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {

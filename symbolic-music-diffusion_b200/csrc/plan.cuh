@@ -74,6 +74,12 @@ struct smd_plan {
   // sampler
   int T = 0;
   int T_obj = 0;  // schedule length of the training objective
+  // FiLM table of the sampler: [K][T][2*Md]; when film_tab_on, run_forward skips the generator and the tail reads
+  // row film_row (host) or *film_row_dev (graph replay) of the table
+  bool film_tab_ready = false, film_tab_on = false;
+  int film_row = 0;
+  const int* film_row_dev = nullptr;
+  const float* film_tab_params = nullptr;
   bool sampler_ready = false;
   cudaGraphExec_t graph_exec = nullptr;
   int graph_n = -1;

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -146,6 +147,14 @@ static void build_workspace(smd_plan* p) {
   ws_add(p, "t_ptr", 64);
   ws_add(p, "abar", (kMaxT + 1) * 4);
   ws_add(p, "packjobs", 256 * sizeof(PackJob));
+  if (c.sampler_T > 0) {
+    const size_t T = c.sampler_T;
+    ws_add(p, "ftab.t", T * 4);
+    ws_add(p, "ftab.enc", T * kFilmEmb * 4);
+    ws_add(p, "ftab.e1", T * kFilmHid * 4);
+    ws_add(p, "ftab.e2", T * kFilmHid * 4);
+    ws_add(p, "ftab", K * T * 2 * Md * 4);
+  }
   if (c.training) train_workspace(p->train, c, p->Mp, p->K, [&](const std::string& n, size_t b) { return ws_add(p, n, b); });
 }
 
@@ -219,6 +228,11 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
   for (int k = 0; k < p->K; ++k) {
     const std::string pre = "k" + std::to_string(k) + ".res.";
     const float* scale = ss + static_cast<size_t>(k) * p->cfg.max_batch * 2 * Md;
+    const int* frow_dev = nullptr;
+    if (p->film_tab_on) {
+      scale = p->buf<float>("ftab") + static_cast<size_t>(k) * p->T * 2 * Md;
+      if (p->film_row_dev) frow_dev = p->film_row_dev; else scale += static_cast<size_t>(p->film_row) * 2 * Md;
+    }
     const float* shift = scale + Md;
     float* u_in = u;
     float* r1_out = r1;
@@ -230,7 +244,7 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
       act_b = save->act_b(p->ws, k); u_out = save->u(p->ws, k + 1);
     }
     launch_ln_film_act(u_in, stats + (2 * k) * sstride, p->P(params, pre + "ln_a.scale"), p->P(params, pre + "ln_a.bias"),
-                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st); CNT();
+                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st, frow_dev); CNT();
     GemmEpilogue e = epi();
     e.bias = p->P(params, pre + "a.bias");
     e.out_f32 = r1_out; e.ld_f32 = Md;
@@ -240,7 +254,7 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
     if (save) { if (!retarget_a(&opa, act_a, p->Mp) || !retarget_a(&opb, act_b, p->Mp)) return SMD_ERR_CUDA; }
     SMD_CUDA(launch_gemm(opa, M, e, st));
     launch_ln_film_act(r1_out, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
-                       p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st); CNT();
+                       p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st, frow_dev); CNT();
     e = epi();
     e.bias = p->P(params, pre + "b.bias");
     e.residual = u_in; e.ld_res = Md;
@@ -272,7 +286,8 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
   const int M = batch * S;
   float* stats = p->buf<float>("stats");
   SMD_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * p->K + 1) * p->Mp * 2 * 4, st));
-  int rc = run_film(p, params, t, t_broadcast ? 1 : batch, st, save);
+  int rc = SMD_OK;
+  if (!p->film_tab_on) rc = run_film(p, params, t, t_broadcast ? 1 : batch, st, save);
   if (rc) return rc;
   float* u0 = save ? save->u(p->ws, 0) : p->buf<float>("u");
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
@@ -407,8 +422,8 @@ void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int
   PackJob j;
   j.src_off = p->off.at(src); j.dst = dst; j.K = K; j.N = N; j.mode = mode; j.ld = ld;
   j.tiles_n = (N + 31) / 32;
-  j.tile0 = p->pack_tiles;
-  p->pack_tiles += ((K + 31) / 32) * j.tiles_n;
+  j.tile0 = 0;
+  p->pack_tiles = std::max(p->pack_tiles, ((K + 31) / 32) * j.tiles_n);   // max tiles of any job
   p->pack_jobs.push_back(j);
 }
 
@@ -538,6 +553,7 @@ int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
   CNT();
   SMD_LAUNCH_CHECK("pack_weights");
   plan->packed = true;
+  plan->film_tab_ready = false;   // parameters changed
   return SMD_OK;
 }
 
@@ -656,7 +672,39 @@ int smd_sampler_setup(smd_plan* plan, const float* host_betas, int T, const uint
   SMD_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
   plan->T = T;
   plan->sampler_ready = true;
+  plan->film_tab_ready = false;
   if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }
+  return SMD_OK;
+}
+
+__global__ void gather_cond_kernel(const float* __restrict__ coef, float* __restrict__ tv, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) tv[i] = coef[8 * i + 5];
+}
+
+// FiLM scale/shift for every step of the schedule (all samples share t, so this replaces 3K small launches per
+// reverse step by one table lookup): ftab[k][t][:] = DenseFiLM_k(sqrt(alpha_bar_t))   (models/ncsn.py:44-61)
+static int ensure_film_table(smd_plan* plan, const float* params, cudaStream_t st) {
+  if (plan->cfg.sampler_T <= 0 || plan->T > plan->cfg.sampler_T) return SMD_OK;   // per-step generator instead
+  if (plan->film_tab_ready && plan->film_tab_params == params) return SMD_OK;
+  const int T = plan->T, Md = plan->cfg.mlp_dims;
+  float* tv = plan->buf<float>("ftab.t");
+  float* enc = plan->buf<float>("ftab.enc");
+  float* e1 = plan->buf<float>("ftab.e1");
+  float* e2 = plan->buf<float>("ftab.e2");
+  float* tab = plan->buf<float>("ftab");
+  gather_cond_kernel<<<(T + 255) / 256, 256, 0, st>>>(plan->buf<float>("coef"), tv, T); CNT();
+  launch_noise_encoding(tv, plan->buf<float>("freqs"), enc, T, st); CNT();
+  for (int k = 0; k < plan->K; ++k) {
+    const std::string pre = "k" + std::to_string(k) + ".film.";
+    launch_small_linear(enc, plan->P(params, pre + "d1.kernel"), plan->P(params, pre + "d1.bias"), e1, T, kFilmEmb, kFilmHid, 2, st); CNT();
+    launch_small_linear(e1, plan->P(params, pre + "d2.kernel"), plan->P(params, pre + "d2.bias"), e2, T, kFilmHid, kFilmHid, 0, st); CNT();
+    launch_small_linear(e2, plan->P(params, pre + "ss.kernel"), plan->P(params, pre + "ss.bias"),
+                        tab + static_cast<size_t>(k) * T * 2 * Md, T, kFilmHid, 2 * Md, 0, st); CNT();
+  }
+  SMD_LAUNCH_CHECK("film table");
+  plan->film_tab_ready = true;
+  plan->film_tab_params = params;
   return SMD_OK;
 }
 
@@ -667,7 +715,12 @@ static int reverse_step_impl(smd_plan* plan, const float* params, const float* x
   float* tvec = plan->buf<float>("tvec");
   int* t_ptr = plan->buf<int>("t_ptr");
   const float* coef = plan->buf<float>("coef");
-  if (t >= 0) {
+  const bool use_tab = plan->film_tab_ready && plan->film_tab_params == params;
+  if (use_tab) {
+    plan->film_tab_on = true;
+    plan->film_row = (t >= 0) ? t : 0;
+    plan->film_row_dev = (t >= 0) ? nullptr : t_ptr;
+  } else if (t >= 0) {
     // conditioning value sqrt(alpha_prod_t), shared by every sample (utils/ebm_utils.py:367-369)
     SMD_CUDA(cudaMemcpyAsync(tvec, coef + 8 * t + 5, 4, cudaMemcpyDeviceToDevice, st));
   } else {
@@ -675,6 +728,8 @@ static int reverse_step_impl(smd_plan* plan, const float* params, const float* x
   }
   float* eh = eps_hat ? eps_hat : plan->buf<float>("eps_hat");
   int rc = run_forward(plan, params, x, tvec, 1, n, eh, st, nullptr);
+  plan->film_tab_on = false;
+  plan->film_row_dev = nullptr;
   if (rc) return rc;
   ReverseStepArgs a;
   memset(&a, 0, sizeof(a));
@@ -698,6 +753,8 @@ int smd_ddpm_reverse_step(smd_plan* plan, const float* params, const float* x, i
   if (!plan->sampler_ready) { set_error("smd_sampler_setup has not been called"); return SMD_ERR_STATE; }
   if (t < 0 || t >= plan->T) { set_error("t out of range"); return SMD_ERR_INVALID; }
   if (n < 1 || n > plan->cfg.max_batch) { set_error("n out of range"); return SMD_ERR_INVALID; }
+  int rc0 = ensure_film_table(plan, params, static_cast<cudaStream_t>(stream));
+  if (rc0) return rc0;
   return reverse_step_impl(plan, params, x, n, t, z, infill_x, infill_mask, infill_z, x_next, eps_hat_or_null,
                            collection, metrics, static_cast<cudaStream_t>(stream));
 }
@@ -711,6 +768,7 @@ int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int st
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int T = plan->T;
   if (metrics) SMD_CUDA(cudaMemsetAsync(metrics, 0, sizeof(float) * 4 * T, st));
+  { int rc0 = ensure_film_table(plan, params, st); if (rc0) return rc0; }
   if (!use_graph) {
     for (int i = 0; i < steps; ++i) {
       int rc = reverse_step_impl(plan, params, x, n, T - 1 - i, nullptr, infill_x, infill_mask, nullptr, x, nullptr,

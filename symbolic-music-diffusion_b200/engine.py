@@ -53,7 +53,7 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 class Engine:
     def __init__(self, cfg: ModelConfig, max_batch: int, cta_group: int = 2, training: bool = False,
-                 device: Optional[str] = None):
+                 device: Optional[str] = None, sampler_T: Optional[int] = None):
         if cfg.arch not in ARCHS:
             raise ValueError(f"unknown architecture {cfg.arch!r}")
         self.cfg = cfg
@@ -61,7 +61,8 @@ class Engine:
         self.lib = _lib.load_library()
         c = _lib.SmdConfig(ARCHS[cfg.arch], cfg.num_layers, cfg.num_heads, cfg.num_mlp_layers, cfg.mlp_dims,
                            cfg.seq_len if ARCHS[cfg.arch] == 0 else 1, cfg.channels, self.max_batch,
-                           int(cta_group), int(training))
+                           int(cta_group), int(training),
+                           int((0 if training else 1000) if sampler_T is None else sampler_T))
         h = C.c_void_p()
         _lib.check(self.lib.smd_plan_create(C.byref(c), C.byref(h)))
         self._plan = h
