@@ -83,12 +83,37 @@ inline int device_sm_count() {
   return sms;
 }
 
-template <int kCG>
-inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
+// feature bits a launch needs, and whether it qualifies for a specialised (fast-path-only) instantiation
+inline uint32_t epi_needs(const GemmEpilogue& e) {
+  uint32_t f = 0;
+  if (e.bias) f |= F_BIAS;
+  if (e.residual) f |= F_RES;
+  if (e.out_f32) f |= F_F32;
+  if (e.out_bf16) f |= F_BF16;
+  if (e.out_bf16_pre) f |= F_PRE;
+  if (e.row_stats) f |= F_STATS;
+  if (e.ln_gamma) f |= F_LN;
+  if (e.gelu_grad_of) f |= F_GG;
+  if (e.atomic_out) f |= F_ATOMIC;
+  if (e.act != ACT_NONE) f |= F_ACT;
+  if (e.out_scale != 0.0f && e.out_scale != 1.0f) f |= F_SCALE;
+  return f;
+}
+inline bool epi_clean(const GemmOp& op, const GemmEpilogue& e) {
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return (op.N % 32 == 0) && (op.BN % 32 == 0) && (!e.residual || ((e.ld_res & 3) == 0 && a16(e.residual))) &&
+         (!e.out_f32 || ((e.ld_f32 & 3) == 0 && a16(e.out_f32))) &&
+         ((!e.out_bf16 && !e.out_bf16_pre) || (e.ld_bf16 & 7) == 0) && (!e.out_bf16 || a16(e.out_bf16)) &&
+         (!e.out_bf16_pre || a16(e.out_bf16_pre)) && (!e.gelu_grad_of || ((e.ld_gg & 7) == 0 && a16(e.gelu_grad_of))) &&
+         (!e.bias || a16(e.bias)) && (!e.ln_gamma || (a16(e.ln_gamma) && a16(e.ln_beta)));
+}
+
+template <int kCG, uint32_t kF>
+inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
   using SM = GemmSmem<kCG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG, kF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SM::kTotal);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -120,7 +145,22 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCG>, op.tmA, op.tmB, sh, ep);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCG, kF>, op.tmA, op.tmB, sh, ep);
+}
+
+template <int kCG>
+inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
+  const uint32_t need = epi_needs(ep);
+  if (epi_clean(op, ep)) {
+    auto fits = [&](uint32_t kind) { return (need & ~kind) == 0; };
+    if (fits(kEpiF32)) return launch_gemm_inst<kCG, kEpiF32>(op, M, ep, st);
+    if (fits(kEpiAtomic)) return launch_gemm_inst<kCG, kEpiAtomic>(op, M, ep, st);
+    if (fits(kEpiF32Res)) return launch_gemm_inst<kCG, kEpiF32Res>(op, M, ep, st);
+    if (fits(kEpiAct)) return launch_gemm_inst<kCG, kEpiAct>(op, M, ep, st);
+    if (fits(kEpiGG)) return launch_gemm_inst<kCG, kEpiGG>(op, M, ep, st);
+    if (fits(kEpiLn)) return launch_gemm_inst<kCG, kEpiLn>(op, M, ep, st);
+  }
+  return launch_gemm_inst<kCG, kEpiGeneric>(op, M, ep, st);
 }
 
 inline cudaError_t launch_gemm(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {

@@ -17,6 +17,21 @@ namespace smd {
 
 enum : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SWISH = 2 };
 
+// Compile-time epilogue feature mask: the kernel is instantiated for a handful of feature sets so that each launch
+// carries only the epilogue code it needs (the all-features build was ~23k SASS instructions and stalled on
+// instruction fetch).  kEpiGeneric keeps every feature, the ragged / unaligned row-per-thread path included.
+enum : uint32_t {
+  F_BIAS = 1u, F_RES = 2u, F_F32 = 4u, F_BF16 = 8u, F_PRE = 16u, F_STATS = 32u, F_LN = 64u, F_GG = 128u,
+  F_ATOMIC = 256u, F_ACT = 512u, F_RAGGED = 1024u, F_SCALE = 2048u
+};
+static constexpr uint32_t kEpiGeneric = 0xFFFu;
+static constexpr uint32_t kEpiF32 = F_BIAS | F_F32 | F_STATS;                     // qkv, post, res-block a, dX outputs
+static constexpr uint32_t kEpiF32Res = F_BIAS | F_RES | F_F32 | F_STATS;          // res-block b
+static constexpr uint32_t kEpiAct = F_BIAS | F_ACT | F_BF16 | F_PRE;              // FFN up (+GELU)
+static constexpr uint32_t kEpiLn = F_BIAS | F_RES | F_F32 | F_LN | F_BF16;        // attention out / FFN down + LayerNorm
+static constexpr uint32_t kEpiGG = F_GG | F_BF16;                                 // FFN backward (x gelu')
+static constexpr uint32_t kEpiAtomic = F_F32 | F_ATOMIC;                          // split-K weight gradients
+
 struct GemmEpilogue {
   const float* bias;            // [N] or null
   const float* residual;        // fp32 [M][ld_res] or null  (v = acc + bias + residual)
@@ -86,7 +101,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-template <int kCG>
+template <int kCG, uint32_t kF>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape sh, const GemmEpilogue ep) {
@@ -219,19 +234,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // tcgen05.ld hands each thread one ROW of the tile; a row-per-thread global access would be 32 scattered 16-byte
     // transactions per instruction, so every global tile access goes through a per-warp 32x33 shared-memory scratch
     // and is issued as whole 128-byte (fp32) / 64-byte (bf16) row segments.
-    const uint32_t q = warp & 3u;          // TMEM lane quadrant this warp may access
+    constexpr bool H_BIAS = (kF & F_BIAS) != 0, H_RES = (kF & F_RES) != 0, H_F32 = (kF & F_F32) != 0;
+    constexpr bool H_BF16 = (kF & F_BF16) != 0, H_PRE = (kF & F_PRE) != 0, H_STATS = (kF & F_STATS) != 0;
+    constexpr bool H_LN = (kF & F_LN) != 0, H_GG = (kF & F_GG) != 0, H_ATOMIC = (kF & F_ATOMIC) != 0;
+    constexpr bool H_ACT = (kF & F_ACT) != 0, H_RAGGED = (kF & F_RAGGED) != 0, H_SCALE = (kF & F_SCALE) != 0;
+    const uint32_t q = warp & 3u;                      // TMEM lane quadrant this warp may access
     const int eg = static_cast<int>(warp - 4u) >> 2;   // column group 0/1: the two warps of a quadrant split the chunks
     float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * (32 * 33);
     uint32_t* scrw = reinterpret_cast<uint32_t*>(scr);
     const int f_r = static_cast<int>(lane >> 3), f_c = static_cast<int>(lane & 7u) * 4;  // fp32: 4 rows x 128 B / instr
     const int h_r = static_cast<int>(lane >> 2), h_c = static_cast<int>(lane & 3u) * 8;  // bf16: 8 rows x 64 B / instr
     int acc = 0; uint32_t acc_phase = 0;
-    const float oscale = (ep.out_scale != 0.0f) ? ep.out_scale : 1.0f;
-    const bool do_ln = (ep.ln_gamma != nullptr);
-    const bool aligned_ok = ((ep.residual == nullptr) || (ep.ld_res & 3) == 0) &&
-                            ((ep.out_f32 == nullptr) || (ep.ld_f32 & 3) == 0) &&
-                            ((ep.out_bf16 == nullptr && ep.out_bf16_pre == nullptr) || (ep.ld_bf16 & 7) == 0) &&
-                            ((ep.gelu_grad_of == nullptr) || (ep.ld_gg & 7) == 0);
+    const float oscale = (H_SCALE && ep.out_scale != 0.0f) ? ep.out_scale : 1.0f;
+    const bool has_bias = H_BIAS && ep.bias != nullptr;
+    const bool has_res = H_RES && ep.residual != nullptr;
+    const bool has_f32 = H_F32 && ep.out_f32 != nullptr;
+    const bool has_bf16 = H_BF16 && ep.out_bf16 != nullptr;
+    const bool has_pre = H_PRE && ep.out_bf16_pre != nullptr;
+    const bool has_stats = H_STATS && ep.row_stats != nullptr;
+    const bool do_ln = H_LN && ep.ln_gamma != nullptr;
+    const bool has_gg = H_GG && ep.gelu_grad_of != nullptr;
+    const bool atomic_out = H_ATOMIC && ep.atomic_out != 0;
+    const int act = H_ACT ? ep.act : ACT_NONE;
+    const bool aligned_ok = !H_RAGGED ||
+                            ((!has_res || (ep.ld_res & 3) == 0) && (!has_f32 || (ep.ld_f32 & 3) == 0) &&
+                             ((!has_bf16 && !has_pre) || (ep.ld_bf16 & 7) == 0) && (!has_gg || (ep.ld_gg & 7) == 0));
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int mn = tile / splits;
       const bool first_split = (tile % splits) == 0;
@@ -250,27 +277,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int c_step = do_ln ? 32 : 64;
       // software prefetch of the residual / gelu-grad tiles of the NEXT chunk (their global latency would
       // otherwise be fully exposed: only two warps per SM sub-partition work on the epilogue)
-      float4 rpre[8];
-      uint4 gpre[4];
-      const bool pre_res = (ep.residual != nullptr) && first_split && aligned_ok;
-      const bool pre_gg = (ep.gelu_grad_of != nullptr) && aligned_ok;
-      auto chunk_fast = [&](int c) { return (BN - c) >= 32 && aligned_ok && (n0 + c + 32 <= sh.N); };
+      float4 rpre[H_RES ? 8 : 1];
+      uint4 gpre[H_GG ? 4 : 1];
+      const bool pre_res = has_res && first_split && aligned_ok;
+      const bool pre_gg = has_gg && aligned_ok;
+      auto chunk_fast = [&](int c) {
+        return !H_RAGGED || ((BN - c) >= 32 && aligned_ok && (n0 + c + 32 <= sh.N));
+      };
       auto prefetch = [&](int c) {
         const int colp = n0 + c;
-        if (pre_res) {
+        if constexpr (H_RES) {
+          if (pre_res) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = row_base + it * 4 + f_r;
-            rpre[it] = (grow < sh.M) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + colp + f_c)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row_base + it * 4 + f_r;
+              rpre[it] = (grow < sh.M) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + colp + f_c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
-        if (pre_gg) {
+        if constexpr (H_GG) {
+          if (pre_gg) {
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int grow = row_base + it * 8 + h_r;
-            gpre[it] = (grow < sh.M) ? *reinterpret_cast<const uint4*>(ep.gelu_grad_of + static_cast<size_t>(grow) * ep.ld_gg + colp + h_c)
-                                     : make_uint4(0u, 0u, 0u, 0u);
+            for (int it = 0; it < 4; ++it) {
+              const int grow = row_base + it * 8 + h_r;
+              gpre[it] = (grow < sh.M) ? *reinterpret_cast<const uint4*>(ep.gelu_grad_of + static_cast<size_t>(grow) * ep.ld_gg + colp + h_c)
+                                       : make_uint4(0u, 0u, 0u, 0u);
+            }
           }
         }
       };
@@ -279,7 +312,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int c0 = c_begin; c0 < BN; c0 += c_step) {
           __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
           uint32_t r[32];
-          const bool half = (BN - c0) < 32;  // 16-column tail
+          bool half = false;
+          if constexpr (H_RAGGED) half = (BN - c0) < 32;  // 16-column tail
           if (!half) {
             tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
           } else {
@@ -292,12 +326,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const int ncols = half ? 16 : 32;
           const int col0 = n0 + c0;
           float v[32];
+          if constexpr (H_SCALE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
-          const bool reload = (pass == 1) && (ep.out_f32 != nullptr);
-          const bool write_bf16 = (ep.out_bf16 != nullptr) && (do_ln ? (pass == 1) : true);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          }
+          const bool reload = H_LN && (pass == 1) && has_f32;
+          const bool write_bf16 = has_bf16 && (do_ln ? (pass == 1) : true);
 
-          if (!half && aligned_ok && col0 + 32 <= sh.N) {
+          if (chunk_fast(c0)) {
             // ------------------------------ fast path: full 32-column chunk ------------------------------
             if (reload) {
               // LayerNorm pass 1: take v back from what this warp stored in pass 0 (the residual may alias the
@@ -315,80 +354,132 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               for (int i = 0; i < 32; ++i) v[i] = scr[lane * 33 + i];
               __syncwarp();
             } else {
-              if (ep.bias != nullptr && first_split) {
+              if constexpr (H_BIAS) {
+                if (has_bias && first_split) {
+                  const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(ep.bias + col0 + i);
-              }
-              if (ep.residual != nullptr && first_split) {
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                  float* d = scr + (it * 4 + f_r) * 33 + f_c;
-                  d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 b = __ldg(b4 + i);
+                    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                  }
                 }
               }
-              if (ep.gelu_grad_of != nullptr) {
-                // staged after the residual below (scr is reused); keep the raw words in registers meanwhile
+              uint4 gcur[H_GG ? 4 : 1];
+              if constexpr (H_RES) {
+                if (pre_res) {
+#pragma unroll
+                  for (int it = 0; it < 8; ++it) {
+                    float* d = scr + (it * 4 + f_r) * 33 + f_c;
+                    d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
+                  }
+                }
+              }
+              if constexpr (H_GG) {
+                if (pre_gg) {
+#pragma unroll
+                  for (int it = 0; it < 4; ++it) gcur[it] = gpre[it];
+                }
               }
               // issue the next chunk's global loads now: they complete while this chunk is processed
-              uint4 gcur[4];
-              if (pre_gg) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) gcur[it] = gpre[it];
-              }
-              {
+              if (pass == 0) {
                 const int cn = c0 + c_step;
-                if (cn < BN && chunk_fast(cn) && pass == 0) prefetch(cn);
-                else if (pass == 0 && npass == 2 && cn >= BN) { /* pass 1 reloads from out_f32 */ }
+                if (cn < BN && chunk_fast(cn)) prefetch(cn);
               }
-              if (ep.residual != nullptr && first_split) {
-                __syncwarp();
+              if constexpr (H_RES) {
+                if (pre_res) {
+                  __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
-                __syncwarp();
-              }
-              if (ep.gelu_grad_of != nullptr) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&gcur[it]);
-                  float* d = scr + (it * 8 + h_r) * 33 + h_c;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hp[j]); d[2 * j] = f.x; d[2 * j + 1] = f.y; }
+                  for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
+                  __syncwarp();
                 }
-                __syncwarp();
+              }
+              if constexpr (H_GG) {
+                if (pre_gg) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= gelu_tanh_grad_f(scr[lane * 33 + i]);
-                __syncwarp();
+                  for (int it = 0; it < 4; ++it) {
+                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&gcur[it]);
+                    float* d = scr + (it * 8 + h_r) * 33 + h_c;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hp[j]); d[2 * j] = f.x; d[2 * j + 1] = f.y; }
+                  }
+                  __syncwarp();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] *= gelu_tanh_grad_f(scr[lane * 33 + i]);
+                  __syncwarp();
+                }
               }
             }
             if (pass == 0) {
-              if (ep.row_stats != nullptr || do_ln) {
+              if constexpr (H_STATS || H_LN) {
+                if (has_stats || do_ln) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+                  for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+                }
               }
-              if (ep.out_f32 != nullptr) {
+              if constexpr (H_F32) {
+                if (has_f32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
-                __syncwarp();
+                  for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+                  __syncwarp();
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                  const int rr = it * 4 + f_r, grow = row_base + rr;
-                  if (grow < sh.M) {
-                    const float* sp = scr + rr * 33 + f_c;
-                    float* op = ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c;
-                    if (ep.atomic_out) {
-                      atomicAdd(op, sp[0]); atomicAdd(op + 1, sp[1]); atomicAdd(op + 2, sp[2]); atomicAdd(op + 3, sp[3]);
-                    } else {
-                      *reinterpret_cast<float4*>(op) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                  for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + f_r, grow = row_base + rr;
+                    if (grow < sh.M) {
+                      const float* sp = scr + rr * 33 + f_c;
+                      float* op = ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c;
+                      if (H_ATOMIC && atomic_out) {
+                        atomicAdd(op, sp[0]); atomicAdd(op + 1, sp[1]); atomicAdd(op + 2, sp[2]); atomicAdd(op + 3, sp[3]);
+                      } else {
+                        *reinterpret_cast<float4*>(op) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                      }
                     }
                   }
+                  __syncwarp();
                 }
-                __syncwarp();
               }
-              if (ep.out_bf16_pre != nullptr) {
+              if constexpr (H_PRE) {
+                if (has_pre) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                  scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+                  for (int j = 0; j < 16; ++j) {
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+                  }
+                  __syncwarp();
+#pragma unroll
+                  for (int it = 0; it < 4; ++it) {
+                    const int rr = it * 8 + h_r, grow = row_base + rr;
+                    if (grow < sh.M) {
+                      const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
+                      *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                          make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                    }
+                  }
+                  __syncwarp();
+                }
+              }
+            }
+            if constexpr (H_BF16) {
+              if (write_bf16) {
+                if (H_LN && do_ln) {
+                  const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0);
+                  const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+                    const float w0 = (v[4 * i] - mean) * (rstd * g.x) + b.x;
+                    const float w1 = (v[4 * i + 1] - mean) * (rstd * g.y) + b.y;
+                    const float w2 = (v[4 * i + 2] - mean) * (rstd * g.z) + b.z;
+                    const float w3 = (v[4 * i + 3] - mean) * (rstd * g.w) + b.w;
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(w0, w1), p1 = __floats2bfloat162_rn(w2, w3);
+                    scrw[lane * 33 + 2 * i] = *reinterpret_cast<uint32_t*>(&p0);
+                    scrw[lane * 33 + 2 * i + 1] = *reinterpret_cast<uint32_t*>(&p1);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(act_apply(v[2 * j], act), act_apply(v[2 * j + 1], act));
+                    scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+                  }
                 }
                 __syncwarp();
 #pragma unroll
@@ -396,99 +487,75 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   const int rr = it * 8 + h_r, grow = row_base + rr;
                   if (grow < sh.M) {
                     const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                    *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                    *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
                         make_uint4(sp[0], sp[1], sp[2], sp[3]);
                   }
                 }
                 __syncwarp();
               }
             }
-            if (write_bf16) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float w0, w1;
-                if (do_ln) {
-                  w0 = (v[2 * j] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + 2 * j)) + __ldg(ep.ln_beta + col0 + 2 * j);
-                  w1 = (v[2 * j + 1] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + 2 * j + 1)) + __ldg(ep.ln_beta + col0 + 2 * j + 1);
-                } else {
-                  w0 = act_apply(v[2 * j], ep.act);
-                  w1 = act_apply(v[2 * j + 1], ep.act);
-                }
-                __nv_bfloat162 pk = __floats2bfloat162_rn(w0, w1);
-                scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
-              }
-              __syncwarp();
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int rr = it * 8 + h_r, grow = row_base + rr;
-                if (grow < sh.M) {
-                  const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                  *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
-                      make_uint4(sp[0], sp[1], sp[2], sp[3]);
-                }
-              }
-              __syncwarp();
-            }
             continue;
           }
 
-          // ------------------------------ slow path: ragged / unaligned chunk (row per thread) ---------------
-          if (!row_ok) continue;
-          if (reload) {
-            const float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols && col0 + i < sh.N) v[i] = op[i];
-          } else {
-            if (ep.bias != nullptr && first_split) {
+          if constexpr (H_RAGGED) {
+            // ------------------------------ slow path: ragged / unaligned chunk (row per thread) -------------
+            if (!row_ok) continue;
+            if (reload) {
+              const float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < ncols && col0 + i < sh.N) v[i] += __ldg(ep.bias + col0 + i);
-            }
-            if (ep.residual != nullptr && first_split) {
-              const float* rp = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
+                if (i < ncols && col0 + i < sh.N) v[i] = op[i];
+            } else {
+              if (has_bias && first_split) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols && col0 + i < sh.N) v[i] += rp[i];
-            }
-            if (ep.gelu_grad_of != nullptr) {
-              const __nv_bfloat16* gp = ep.gelu_grad_of + static_cast<size_t>(row) * ep.ld_gg + col0;
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) v[i] += __ldg(ep.bias + col0 + i);
+              }
+              if (has_res && first_split) {
+                const float* rp = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols && col0 + i < sh.N) v[i] *= gelu_tanh_grad_f(__bfloat162float(gp[i]));
-            }
-          }
-          if (pass == 0) {
-            if (ep.row_stats != nullptr || do_ln) {
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) v[i] += rp[i];
+              }
+              if (has_gg) {
+                const __nv_bfloat16* gp = ep.gelu_grad_of + static_cast<size_t>(row) * ep.ld_gg + col0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols && col0 + i < sh.N) { s1 += v[i]; s2 += v[i] * v[i]; }
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) v[i] *= gelu_tanh_grad_f(__bfloat162float(gp[i]));
+              }
             }
-            if (ep.out_f32 != nullptr) {
-              float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+            if (pass == 0) {
+              if (has_stats || do_ln) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) { s1 += v[i]; s2 += v[i] * v[i]; }
+              }
+              if (has_f32) {
+                float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if (i < ncols && col0 + i < sh.N) {
+                    if (atomic_out) atomicAdd(op + i, v[i]); else op[i] = v[i];
+                  }
+                }
+              }
+              if (has_pre) {
+                __nv_bfloat16* op = ep.out_bf16_pre + static_cast<size_t>(row) * ep.ld_bf16 + col0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(v[i]);
+              }
+            }
+            if (write_bf16) {
+              __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 if (i < ncols && col0 + i < sh.N) {
-                  if (ep.atomic_out) atomicAdd(op + i, v[i]); else op[i] = v[i];
+                  float w;
+                  if (do_ln) w = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + i)) + __ldg(ep.ln_beta + col0 + i);
+                  else w = act_apply(v[i], act);
+                  op[i] = __float2bfloat16_rn(w);
                 }
-              }
-            }
-            if (ep.out_bf16_pre != nullptr) {
-              __nv_bfloat16* op = ep.out_bf16_pre + static_cast<size_t>(row) * ep.ld_bf16 + col0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols && col0 + i < sh.N) op[i] = __float2bfloat16_rn(v[i]);
-            }
-          }
-          if (write_bf16) {
-            __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < ncols && col0 + i < sh.N) {
-                float w;
-                if (do_ln) w = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + i)) + __ldg(ep.ln_beta + col0 + i);
-                else w = act_apply(v[i], ep.act);
-                op[i] = __float2bfloat16_rn(w);
               }
             }
           }
@@ -501,9 +568,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           rstd = rsqrtf(var + 1e-6f);
         }
       }  // passes
-      if (ep.row_stats != nullptr && row_ok) {
-        atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row), s1);
-        atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row) + 1, s2);
+      if constexpr (H_STATS) {
+        if (has_stats && row_ok) {
+          atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row), s1);
+          atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row) + 1, s2);
+        }
       }
       // release this accumulator stage back to the MMA issuer
       tcgen05_fence_before();

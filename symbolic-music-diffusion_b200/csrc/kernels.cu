@@ -340,36 +340,38 @@ void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int
   dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
   pack_transpose_bf16_kernel<<<grid, block, 0, st>>>(src, dst, K, N);
 }
-// All weight repacks of one optimizer step in ONE launch: every 32x32 tile of every job is one CTA.
+// All weight repacks of one optimizer step in ONE launch: blockmap[b] = (job, tile) for every 64x64 tile.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs,
-                                                         int njobs) {
-  __shared__ float tile[32][33];
-  const PackJob job = jobs[blockIdx.y];           // grid = (max tiles of any job, njobs): surplus CTAs exit at once
-  const int t = blockIdx.x;
-  if (t >= ((job.K + 31) / 32) * job.tiles_n) return;
-  const int k0 = (t / job.tiles_n) * 32, n0 = (t % job.tiles_n) * 32;
+                                                         const int2* __restrict__ blockmap) {
+  __shared__ float tile[64][65];
+  const int2 bm = blockmap[blockIdx.x];
+  const PackJob job = jobs[bm.x];
+  const int t = bm.y;
+  const int k0 = (t / job.tiles_n) * 64, n0 = (t % job.tiles_n) * 64;
   const float* src = params + job.src_off;
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
   const int K = job.K, N = job.N;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
   if (job.mode == 0) {   // dst[n][k] = src[k][n]
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int k = k0 + i, n = n0 + threadIdx.x;
-      tile[i][threadIdx.x] = (k < K && n < N) ? src[static_cast<size_t>(k) * N + n] : 0.f;
+    for (int i = ty; i < 64; i += 4) {
+      const int k = k0 + i, n = n0 + tx;
+      tile[i][tx] = (k < K && n < N) ? src[static_cast<size_t>(k) * N + n] : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int n = n0 + i, k = k0 + threadIdx.x;
-      if (n < N && k < K) dst[static_cast<size_t>(n) * job.ld + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    for (int i = ty; i < 64; i += 4) {
+      const int n = n0 + i, k = k0 + tx;
+      if (n < N && k < K) dst[static_cast<size_t>(n) * job.ld + k] = __float2bfloat16_rn(tile[tx][i]);
     }
   } else {               // dst[k][n] = src[k][n] with row pitch ld
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int k = k0 + i, n = n0 + threadIdx.x;
+    for (int i = ty; i < 64; i += 4) {
+      const int k = k0 + i, n = n0 + tx;
       if (k < K && n < N) dst[static_cast<size_t>(k) * job.ld + n] = __float2bfloat16_rn(src[static_cast<size_t>(k) * N + n]);
     }
   }
 }
-void launch_pack_multi(const float* params, const PackJob* jobs_dev, int njobs, int max_tiles, cudaStream_t st) {
-  pack_multi_kernel<<<dim3(max_tiles, njobs), dim3(32, 8), 0, st>>>(params, jobs_dev, njobs);
+void launch_pack_multi(const float* params, const PackJob* jobs_dev, const void* blockmap_dev, int total_tiles,
+                       cudaStream_t st) {
+  pack_multi_kernel<<<total_tiles, 256, 0, st>>>(params, jobs_dev, static_cast<const int2*>(blockmap_dev));
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {

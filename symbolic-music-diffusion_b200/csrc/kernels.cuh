@@ -140,7 +140,8 @@ void launch_sgemm_small(int mode, const float* A, const float* B, const float* b
 void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int N, cudaStream_t st);
 // one launch for a list of repack jobs (mode 0: transpose to [N][K] with pitch ld; mode 1: plain cast, pitch ld)
 struct PackJob { long long src_off; void* dst; int K, N, mode, ld, tile0, tiles_n; };
-void launch_pack_multi(const float* params, const PackJob* jobs_dev, int njobs, int total_tiles, cudaStream_t st);
+void launch_pack_multi(const float* params, const PackJob* jobs_dev, const void* blockmap_dev, int total_tiles,
+                       cudaStream_t st);
 // bf16 dst[i] = src[i]
 void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
 

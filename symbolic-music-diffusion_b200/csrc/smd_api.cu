@@ -147,6 +147,7 @@ static void build_workspace(smd_plan* p) {
   ws_add(p, "t_ptr", 64);
   ws_add(p, "abar", (kMaxT + 1) * 4);
   ws_add(p, "packjobs", 256 * sizeof(PackJob));
+  ws_add(p, "packmap", 65536 * 8);
   if (c.sampler_T > 0) {
     const size_t T = c.sampler_T;
     ws_add(p, "ftab.t", T * 4);
@@ -421,9 +422,9 @@ static void add_pack_job(smd_plan* p, const std::string& src, void* dst, int K, 
 void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld) {
   PackJob j;
   j.src_off = p->off.at(src); j.dst = dst; j.K = K; j.N = N; j.mode = mode; j.ld = ld;
-  j.tiles_n = (N + 31) / 32;
-  j.tile0 = 0;
-  p->pack_tiles = std::max(p->pack_tiles, ((K + 31) / 32) * j.tiles_n);   // max tiles of any job
+  j.tiles_n = (N + 63) / 64;
+  j.tile0 = p->pack_tiles;
+  p->pack_tiles += ((K + 63) / 64) * j.tiles_n;
   p->pack_jobs.push_back(j);
 }
 
@@ -458,6 +459,14 @@ static int build_pack_jobs(smd_plan* plan) {
   if (plan->pack_jobs.size() > 256) { set_error("too many pack jobs"); return SMD_ERR_INVALID; }
   SMD_CUDA(cudaMemcpy(plan->buf<PackJob>("packjobs"), plan->pack_jobs.data(), plan->pack_jobs.size() * sizeof(PackJob),
                       cudaMemcpyHostToDevice));
+  if (plan->pack_tiles > 65536) { set_error("too many pack tiles"); return SMD_ERR_INVALID; }
+  std::vector<int> bm(static_cast<size_t>(plan->pack_tiles) * 2);
+  for (size_t j = 0; j < plan->pack_jobs.size(); ++j) {
+    const PackJob& pj = plan->pack_jobs[j];
+    const int nt = ((pj.K + 63) / 64) * pj.tiles_n;
+    for (int t = 0; t < nt; ++t) { bm[2 * (pj.tile0 + t)] = static_cast<int>(j); bm[2 * (pj.tile0 + t) + 1] = t; }
+  }
+  SMD_CUDA(cudaMemcpy(plan->buf<int>("packmap"), bm.data(), bm.size() * sizeof(int), cudaMemcpyHostToDevice));
   return SMD_OK;
 }
 
@@ -549,7 +558,7 @@ int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
 int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
   if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), static_cast<int>(plan->pack_jobs.size()), plan->pack_tiles, st);
+  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), plan->buf<void>("packmap"), plan->pack_tiles, st);
   CNT();
   SMD_LAUNCH_CHECK("pack_weights");
   plan->packed = true;
