@@ -158,7 +158,8 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
     if (fits(kEpiF32Res)) return launch_gemm_inst<kCG, kEpiF32Res>(op, M, ep, st);
     if (fits(kEpiAct)) return launch_gemm_inst<kCG, kEpiAct>(op, M, ep, st);
     if (fits(kEpiGG)) return launch_gemm_inst<kCG, kEpiGG>(op, M, ep, st);
-    if (fits(kEpiLn)) return launch_gemm_inst<kCG, kEpiLn>(op, M, ep, st);
+    if ((need & F_LN) && fits(kEpiLn) && op.N == op.BN && op.BN <= 128 && op.BN % 64 == 0 && op.k_splits <= 1)
+      return launch_gemm_inst<kCG, kEpiLn>(op, M, ep, st);
   }
   return launch_gemm_inst<kCG, kEpiGeneric>(op, M, ep, st);
 }

@@ -259,6 +259,131 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool aligned_ok = !H_RAGGED ||
                             ((!has_res || (ep.ld_res & 3) == 0) && (!has_f32 || (ep.ld_f32 & 3) == 0) &&
                              ((!has_bf16 && !has_pre) || (ep.ld_bf16 & 7) == 0) && (!has_gg || (ep.ld_gg & 7) == 0));
+    if constexpr (H_LN && !H_RAGGED) {
+      // ---------- single-pass full-row LayerNorm epilogue (N == BN <= 128: attention out-proj, FFN down) ----------
+      // The two warps of a TMEM quadrant split the row's chunks, keep their values in registers, exchange the
+      // per-row (sum, sumsq) partials through shared memory (named barrier of 64 threads) and each normalises
+      // and stores its own chunks: no second TMEM pass, no global re-read.
+      float* scr_partner = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) +
+                           ((warp - 4u) ^ 4u) * (32 * 33);
+      const int nchunk = BN / 64;
+      const float inv_n = 1.0f / static_cast<float>(sh.N);
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        const int row_base = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
+        float vv[2][32];
+        float s1 = 0.f, s2 = 0.f;
+        float4 rpre[8];
+        auto prefetch = [&](int c) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row_base + it * 4 + f_r;
+            rpre[it] = (has_res && grow < sh.M)
+                           ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + c + f_c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        prefetch(eg * 32);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j < nchunk) {
+            const int c0 = eg * 32 + 64 * j;
+            __syncwarp();
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vv[j][i] = __uint_as_float(r[i]);
+            if (has_bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(ep.bias + c0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(b4 + i);
+                vv[j][4 * i] += b.x; vv[j][4 * i + 1] += b.y; vv[j][4 * i + 2] += b.z; vv[j][4 * i + 3] += b.w;
+              }
+            }
+            if (has_res) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                float* d = scr + (it * 4 + f_r) * 33 + f_c;
+                d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
+              }
+              if (j + 1 < nchunk) prefetch(eg * 32 + 64 * (j + 1));
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vv[j][i] += scr[lane * 33 + i];
+              __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { s1 += vv[j][i]; s2 += vv[j][i] * vv[j][i]; }
+            if (has_f32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = vv[j][i];
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + f_r, grow = row_base + rr;
+                if (grow < sh.M) {
+                  const float* sp = scr + rr * 33 + f_c;
+                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + c0 + f_c) =
+                      make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        // all TMEM reads of this tile are done: hand the accumulator stage back before the normalisation
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        // exchange the row partials with the partner warp of this quadrant
+        scr[lane * 33] = s1; scr[lane * 33 + 1] = s2;
+        asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");
+        const float t1 = s1 + scr_partner[lane * 33], t2 = s2 + scr_partner[lane * 33 + 1];
+        asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");
+        const float mean = t1 * inv_n;
+        const float rstd = rsqrtf(t2 * inv_n - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
+        if (has_bf16) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j < nchunk) {
+              const int c0 = eg * 32 + 64 * j;
+              const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + c0);
+              const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + c0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+                const float w0 = (vv[j][4 * i] - mean) * (rstd * g.x) + b.x;
+                const float w1 = (vv[j][4 * i + 1] - mean) * (rstd * g.y) + b.y;
+                const float w2 = (vv[j][4 * i + 2] - mean) * (rstd * g.z) + b.z;
+                const float w3 = (vv[j][4 * i + 3] - mean) * (rstd * g.w) + b.w;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(w0, w1), p1 = __floats2bfloat162_rn(w2, w3);
+                scrw[lane * 33 + 2 * i] = *reinterpret_cast<uint32_t*>(&p0);
+                scrw[lane * 33 + 2 * i + 1] = *reinterpret_cast<uint32_t*>(&p1);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + h_r, grow = row_base + rr;
+                if (grow < sh.M) {
+                  const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
+                  *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + c0 + h_c) =
+                      make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+    } else
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int mn = tile / splits;
       const bool first_split = (tile % splits) == 0;
