@@ -165,7 +165,8 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   CNT();
   launch_colsum<float>(dpred32, C, G("out.bias"), M, C, st); CNT();
 
-  float* g32 = F32(ts.off_g32a);    // dX GEMM outputs (gradient wrt a bf16 activation)
+  // dX GEMM outputs (gradient wrt a bf16 activation), stored as bf16: half the epilogue / LayerNorm-backward bytes
+  __nv_bfloat16* g16 = B16(ts.off_g32a);
   float* du32 = F32(ts.off_g32b);   // gradient of the fp32 residual stream u
   __nv_bfloat16* du16 = B16(ts.off_g16a);
   __nv_bfloat16* dr16 = B16(ts.off_g16b);
@@ -181,11 +182,11 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     e.atomic_out = sp > 1;
     SMD_CUDA(gemm_k(ts.dWout, Md, Mk, sp, e, st));
     e = epi();
-    e.out_f32 = g32; e.ld_f32 = Md;
+    e.out_bf16 = g16; e.ld_bf16 = Md;
     SMD_CUDA(launch_gemm(ts.dXout, M, e, st));
     LnFilmBwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.g = g32; a.u = ts.u(ws, ts.K); a.stats = stats + (2 * ts.K) * sstride;
+    a.g16 = g16; a.u = ts.u(ws, ts.K); a.stats = stats + (2 * ts.K) * sstride;
     a.gamma = p->P(params, "out_ln.scale"); a.beta = p->P(params, "out_ln.bias");
     a.dx32 = du32; a.dx16 = du16;
     a.dgamma = G("out_ln.scale"); a.dbeta = G("out_ln.bias");
@@ -196,22 +197,25 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
 
   // ---------------- FiLM'd residual blocks ----------------
   float* ssbuf = p->buf<float>("ss");
-  float* dss = F32(ts.off_dss);
+  float* dss_all = F32(ts.off_dss);
+  { int rcs = ensure_side_stream(p); if (rcs) return rcs; }
+  cudaStream_t side = p->side_stream;
   for (int k = ts.K - 1; k >= 0; --k) {
     const std::string pre = "k" + std::to_string(k) + ".";
     const float* ss_k = ssbuf + static_cast<size_t>(k) * c.max_batch * 2 * Md;
+    float* dss = dss_all + static_cast<size_t>(k) * c.max_batch * 2 * Md;
     GemmEpilogue e = epi();
     e.out_f32 = G(pre + "res.b.kernel"); e.ld_f32 = Md;
     SMD_CUDA(gemm_k(ts.dWb[k], Md, Mk, 1, e, st));
     e = epi();
-    e.out_f32 = g32; e.ld_f32 = Md;
+    e.out_bf16 = g16; e.ld_bf16 = Md;
     SMD_CUDA(launch_gemm(ts.dXb[k], M, e, st));
     LnFilmBwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.g = g32; a.u = ts.r1(ws, k); a.stats = stats + (2 * k + 1) * sstride;
+    a.g16 = g16; a.u = ts.r1(ws, k); a.stats = stats + (2 * k + 1) * sstride;
     a.gamma = p->P(params, pre + "res.ln_b.scale"); a.beta = p->P(params, pre + "res.ln_b.bias");
     a.ss = ss_k; a.act = 2;
-    a.dx32 = g32; a.dx16 = dr16;
+    a.dx32 = nullptr; a.dx16 = dr16;   // dr1 is only consumed as a bf16 GEMM operand (and its column sums)
     a.dgamma = G(pre + "res.ln_b.scale"); a.dbeta = G(pre + "res.ln_b.bias");
     a.dbias = G(pre + "res.a.bias");
     a.dss = dss; a.dss_accum = 0;
@@ -221,10 +225,10 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     e.out_f32 = G(pre + "res.a.kernel"); e.ld_f32 = Md;
     SMD_CUDA(gemm_k(ts.dWa[k], Md, Mk, 1, e, st));
     e = epi();
-    e.out_f32 = g32; e.ld_f32 = Md;
+    e.out_bf16 = g16; e.ld_bf16 = Md;
     SMD_CUDA(launch_gemm(ts.dXa[k], M, e, st));
     memset(&a, 0, sizeof(a));
-    a.g = g32; a.u = ts.u(ws, k); a.stats = stats + (2 * k) * sstride;
+    a.g16 = g16; a.u = ts.u(ws, k); a.stats = stats + (2 * k) * sstride;
     a.gamma = p->P(params, pre + "res.ln_a.scale"); a.beta = p->P(params, pre + "res.ln_a.bias");
     a.ss = ss_k; a.act = 2;
     a.dres = du32; a.dx32 = du32; a.dx16 = du16;
@@ -235,27 +239,31 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     launch_ln_film_act_bwd(a, st); CNT();
 
     // ---- FiLM generator backward (models/ncsn.py:47-61); no gradient flows into t ----
+    // independent of the rest of the backward pass: runs on the side stream once this block's dss is complete
+    SMD_CUDA(cudaEventRecord(p->ev_dss, st));
+    SMD_CUDA(cudaStreamWaitEvent(side, p->ev_dss, 0));
     float* enc = p->buf<float>("enc");
     float* e1pre = F32(ts.off_e1pre[k]);
     float* e1 = F32(ts.off_e1[k]);
     float* e2 = F32(ts.off_e2[k]);
     float* de2 = F32(ts.off_de2);
     float* de1 = F32(ts.off_de);
-    launch_colsum<float>(dss, 2 * Md, G(pre + "film.ss.bias"), batch, 2 * Md, st); CNT();
-    launch_cast_bf16(dss, B16(ts.off_dss16), static_cast<size_t>(batch) * 2 * Md, st); CNT();
-    launch_cast_bf16(e2, B16(ts.off_e2_16), static_cast<size_t>(batch) * 512, st); CNT();
+    launch_colsum<float>(dss, 2 * Md, G(pre + "film.ss.bias"), batch, 2 * Md, side); CNT();
+    launch_cast_bf16(dss, B16(ts.off_dss16), static_cast<size_t>(batch) * 2 * Md, side); CNT();
+    launch_cast_bf16(e2, B16(ts.off_e2_16), static_cast<size_t>(batch) * 512, side); CNT();
     e = epi();
     e.out_f32 = G(pre + "film.ss.kernel"); e.ld_f32 = 2 * Md;
-    SMD_CUDA(gemm_k(ts.dWss[k], 512, Bk, 1, e, st));
+    SMD_CUDA(gemm_k(ts.dWss[k], 512, Bk, 1, e, side));
     e = epi();
     e.out_f32 = de2; e.ld_f32 = 512;
-    SMD_CUDA(launch_gemm(ts.dXss[k], batch, e, st));
-    launch_colsum<float>(de2, 512, G(pre + "film.d2.bias"), batch, 512, st); CNT();
-    launch_small_linear_bwd_w(e1, de2, G(pre + "film.d2.kernel"), batch, 512, 512, st); CNT();
-    launch_small_linear_bwd_x(de2, p->P(params, pre + "film.d2.kernel"), e1pre, de1, batch, 512, 512, st); CNT();
-    launch_colsum<float>(de1, 512, G(pre + "film.d1.bias"), batch, 512, st); CNT();
-    launch_small_linear_bwd_w(enc, de1, G(pre + "film.d1.kernel"), batch, 128, 512, st); CNT();
+    SMD_CUDA(launch_gemm(ts.dXss[k], batch, e, side));
+    launch_colsum<float>(de2, 512, G(pre + "film.d2.bias"), batch, 512, side); CNT();
+    launch_small_linear_bwd_w(e1, de2, G(pre + "film.d2.kernel"), batch, 512, 512, side); CNT();
+    launch_small_linear_bwd_x(de2, p->P(params, pre + "film.d2.kernel"), e1pre, de1, batch, 512, 512, side); CNT();
+    launch_colsum<float>(de1, 512, G(pre + "film.d1.bias"), batch, 512, side); CNT();
+    launch_small_linear_bwd_w(enc, de1, G(pre + "film.d1.kernel"), batch, 128, 512, side); CNT();
   }
+  SMD_CUDA(cudaEventRecord(p->ev_join, side));
   SMD_LAUNCH_CHECK("backward tail");
 
   if (ts.L == 0) {
@@ -263,6 +271,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     GemmEpilogue e = epi();
     e.out_f32 = G("in.kernel"); e.ld_f32 = Md;
     SMD_CUDA(gemm_k(ts.dWin, C, Mk, 1, e, st));
+    SMD_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     SMD_LAUNCH_CHECK("backward dense");
     return SMD_OK;
   }
@@ -350,6 +359,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   }
   // ---------------- input projection ----------------
   launch_embed_bwd(xt, dh32, G("in.kernel"), M, C, st); CNT();
+  SMD_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
   SMD_LAUNCH_CHECK("backward trunk");
   return SMD_OK;
 }

@@ -9,7 +9,8 @@ namespace smd {
 // wide LayerNorm + FiLM + swish backward (models/shared.py:62-64 / 66-68), one CTA per 32 rows
 // ---------------------------------------------------------------------------------------------------
 struct LnFilmBwdArgs {
-  const float* g;        // [M][N] gradient wrt the bf16 activation that fed the GEMM
+  const float* g;        // [M][N] gradient wrt the bf16 activation that fed the GEMM (fp32), or null ->
+  const __nv_bfloat16* g16;  // the same gradient stored as bf16 (what the dX GEMM epilogue writes)
   const float* u;        // [M][N] LayerNorm input
   const float* stats;    // [M][2] (sum, sumsq) of u rows
   const float* gamma;    // [N]
@@ -17,7 +18,7 @@ struct LnFilmBwdArgs {
   const float* ss;       // FiLM [nsamples][2N] = [scale | shift], or null (plain LayerNorm)
   int act;               // 2: swish, 0: none
   const float* dres;     // [M][N] residual-path gradient added to dx, or null (may alias dx32)
-  float* dx32;           // [M][N]
+  float* dx32;           // [M][N], or null when only the bf16 copy / bias sums are needed
   __nv_bfloat16* dx16;   // [M][N] or null
   float* dgamma;         // [N] (atomics)
   float* dbeta;          // [N]
@@ -67,7 +68,14 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
     for (int q = 0; q < RPI; ++q) {   // issue all loads first
       const int row = r0 + r + q;
       if (row < a.M) {
-        g4[q] = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
+        if (a.g16) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(a.g16 + static_cast<size_t>(row) * N + c);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          g4[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          g4[q] = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
+        }
         u4[q] = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
       } else {
         g4[q] = make_float4(0, 0, 0, 0); u4[q] = make_float4(0, 0, 0, 0);
@@ -148,7 +156,7 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc_bias[i] += dx[i];
-        *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * N + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        if (a.dx32) *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * N + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
         if (a.dx16) {
           __nv_bfloat162 q0 = __floats2bfloat162_rn(dx[0], dx[1]);
           __nv_bfloat162 q1 = __floats2bfloat162_rn(dx[2], dx[3]);

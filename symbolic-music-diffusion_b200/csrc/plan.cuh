@@ -92,6 +92,9 @@ struct smd_plan {
   long long graph_nodes = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t own_event = nullptr;
+  // training: the FiLM generator (forward and backward) runs on a side stream, concurrently with the trunk
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_film = nullptr, ev_dss = nullptr, ev_join = nullptr;
   smd::TrainState train;
 
   template <typename Tp>
@@ -109,6 +112,7 @@ inline GemmEpilogue epi() {
 int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
                 float* y, cudaStream_t st, TrainState* save);
 int train_bind(smd_plan* p);
+int ensure_side_stream(smd_plan* p);
 void train_pack_jobs(smd_plan* p);
 void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld);
 }  // namespace smd

@@ -215,6 +215,16 @@ static int run_film(smd_plan* p, const float* params, const float* t, int R, cud
   return SMD_OK;
 }
 
+int ensure_side_stream(smd_plan* p) {
+  if (p->side_stream) return SMD_OK;
+  SMD_CUDA(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_film, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dss, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  return SMD_OK;
+}
+
 // The FiLM'd residual tail shared by both architectures (models/ncsn.py:173-178, models/shared.py:61-75).
 // On entry u (fp32 [M][Md]) and stats[0] hold the block input and its row statistics.
 static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadcast, float* y, cudaStream_t st,
@@ -288,7 +298,22 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
   float* stats = p->buf<float>("stats");
   SMD_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * p->K + 1) * p->Mp * 2 * 4, st));
   int rc = SMD_OK;
-  if (!p->film_tab_on) rc = run_film(p, params, t, t_broadcast ? 1 : batch, st, save);
+  bool film_on_side = false;
+  if (!p->film_tab_on) {
+    if (save) {
+      // training: the FiLM generator only feeds the tail, so it runs on a side stream next to the trunk
+      rc = ensure_side_stream(p);
+      if (rc) return rc;
+      SMD_CUDA(cudaEventRecord(p->ev_fork, st));
+      SMD_CUDA(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
+      rc = run_film(p, params, t, batch, p->side_stream, save);
+      if (rc) return rc;
+      SMD_CUDA(cudaEventRecord(p->ev_film, p->side_stream));
+      film_on_side = true;
+    } else {
+      rc = run_film(p, params, t, t_broadcast ? 1 : batch, st, save);
+    }
+  }
   if (rc) return rc;
   float* u0 = save ? save->u(p->ws, 0) : p->buf<float>("u");
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
@@ -361,6 +386,7 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
     SMD_CUDA(launch_gemm(p->op_in, M, e, st));
   }
   SMD_LAUNCH_CHECK("trunk");
+  if (film_on_side) SMD_CUDA(cudaStreamWaitEvent(st, p->ev_film, 0));
   return run_tail(p, params, M, S, t_broadcast, y, st, save);
 }
 
@@ -510,6 +536,11 @@ void smd_plan_destroy(smd_plan* plan) {
   if (!plan) return;
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->own_event) cudaEventDestroy(plan->own_event);
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+  if (plan->ev_film) cudaEventDestroy(plan->ev_film);
+  if (plan->ev_dss) cudaEventDestroy(plan->ev_dss);
+  if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  if (plan->side_stream) cudaStreamDestroy(plan->side_stream);
   if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
   delete plan;
 }

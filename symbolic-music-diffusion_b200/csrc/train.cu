@@ -46,7 +46,7 @@ void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
   ts.off_dqkv32 = add("t.dqkv32", M * 3 * kEt * 4);
   ts.off_dpred16 = add("t.dpred16", M * Cp * 2);
   ts.off_dpred32 = add("t.dpred32", M * c.channels * 4);
-  ts.off_dss = add("t.dss", B * 2 * Md * 4);
+  ts.off_dss = add("t.dss", static_cast<size_t>(K > 0 ? K : 1) * B * 2 * Md * 4);   // one [B][2Md] block per FiLM pair
   ts.off_de = add("t.de", B * 512 * 4);
   ts.off_de2 = add("t.de2", B * 512 * 4);
   ts.off_loss = add("t.loss", B * 4);
