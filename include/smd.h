@@ -71,6 +71,10 @@ size_t smd_workspace_bytes(const smd_plan* plan);
 int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes);
 /* Refresh the bf16 tensor-core operand copies from the fp32 arena (after init / restore / every optimizer step). */
 int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream);
+/* Same, when the bf16 shadow arena was already written by smd_clip_adam (only the padded out.kernel copy is rebuilt). */
+int smd_pack_weights_after_adam(smd_plan* plan, const float* params, smd_stream_t stream);
+/* Device pointer of the bf16 shadow of the parameter arena (same element offsets), NULL before the workspace is bound. */
+void* smd_shadow_arena(smd_plan* plan);
 
 /* ---- score network ---------------------------------------------------------------------------------------- */
 /* eps_hat = model(x, t).  x: (batch, S, C) fp32; t: (batch) fp32 noise level sqrt(alpha_bar), or a single
@@ -91,10 +95,12 @@ int smd_ddpm_loss(smd_plan* plan, const float* params, const float* x0, const fl
  * smd_clip_adam applies global-norm clipping (jax clip_grads), Adam (flax.optim.Adam) and optional EMA. */
 int smd_ddpm_grads(smd_plan* plan, const float* params, const float* x0, const float* used_alpha, const float* eps,
                    int batch, int global_batch, float* grads, float* loss_sum, smd_stream_t stream);
-/* scratch: >= 1024 floats of zero-initialised-by-callee scratch; grad_norm_out[0] = post-clip global L2 norm. */
-int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, float* ema_or_null, long long n,
-                  float lr, int step, float max_norm, float beta1, float beta2, float eps, float ema_mu,
-                  float* scratch, float* grad_norm_out, smd_stream_t stream);
+/* scratch: >= 1024 floats of zero-initialised-by-callee scratch; grad_norm_out[0] = post-clip global L2 norm.
+ * bf16_shadow_or_null: the plan's bf16 shadow arena (smd_shadow_arena): the updated parameters are also written
+ * there in the same pass, after which smd_pack_weights_after_adam (not smd_pack_weights) completes the refresh. */
+int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, float* ema_or_null,
+                  void* bf16_shadow_or_null, long long n, float lr, int step, float max_norm, float beta1,
+                  float beta2, float eps, float ema_mu, float* scratch, float* grad_norm_out, smd_stream_t stream);
 int smd_ema_update(float* ema, const float* params, long long n, float mu, smd_stream_t stream);
 
 /* Random draws of diffusion_loss (utils/losses.py:270-294) on device with jax 0.2.8 threefry semantics:

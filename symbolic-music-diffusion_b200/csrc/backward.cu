@@ -37,69 +37,47 @@ int train_bind(smd_plan* p) {
   const int Cp = (C + 63) / 64 * 64;
   const uint64_t Mp = p->Mp;
   auto B16 = [&](size_t off) { return ts.at<__nv_bfloat16>(ws, off); };
+  // (in,out) weights straight from the bf16 shadow arena: [N = in][K = out], K-major
+  auto Wsh = [&](const std::string& n) { return p->buf<__nv_bfloat16>("wshadow") + p->off.at(n); };
+  auto KN = [&](int k) { return "k" + std::to_string(k) + "."; };
+  auto LN = [&](int l) { return "l" + std::to_string(l) + "."; };
   ts.dWb.resize(ts.K); ts.dXb.resize(ts.K); ts.dWa.resize(ts.K); ts.dXa.resize(ts.K);
   ts.dWss.resize(ts.K); ts.dXss.resize(ts.K);
   const uint64_t Bp = (static_cast<uint64_t>(c.max_batch) + 127) / 128 * 128;
   for (int k = 0; k < ts.K; ++k) {
     if (!make_dw(&ts.dWb[k], ts.act_b(ws, k), Md, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXb[k], B16(ts.off_g16a), Md, B16(ts.off_w_b[k]), Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXb[k], B16(ts.off_g16a), Md, Wsh(KN(k) + "res.b.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
     if (!make_dw(&ts.dWa[k], ts.act_a(ws, k), Md, B16(ts.off_g16b), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXa[k], B16(ts.off_g16b), Md, B16(ts.off_w_a[k]), Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXa[k], B16(ts.off_g16b), Md, Wsh(KN(k) + "res.a.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
     if (!make_dw(&ts.dWss[k], B16(ts.off_e2_16), 512, B16(ts.off_dss16), 2 * Md, 2 * Md, Bp, 1)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXss[k], B16(ts.off_dss16), 2 * Md, B16(ts.off_w_ss[k]), 512, Bp, 1)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXss[k], B16(ts.off_dss16), 2 * Md, Wsh(KN(k) + "film.ss.kernel"), 512, Bp, 1)) return SMD_ERR_CUDA;
   }
   // output projection: dpred16 is zero-padded to Cp columns; the plain weight copy is [Md][Cp]
   if (!make_gemm_op(&ts.dWout, ts.act_out(ws), static_cast<uint64_t>(Md), B16(ts.off_dpred16), static_cast<uint64_t>(Cp),
                     C, static_cast<int>(Mp), (Cp >= 256) ? 256 : Cp, (Cp / cg >= 64 && Cp % (64 * cg) == 0) ? cg : 1, 1, 1))
     return SMD_ERR_CUDA;
-  if (!make_gemm_op(&ts.dXout, B16(ts.off_dpred16), Mp, B16(ts.off_w_out), static_cast<uint64_t>(Md), Md, Cp,
+  if (!make_gemm_op(&ts.dXout, B16(ts.off_dpred16), Mp, p->buf<__nv_bfloat16>("w.out_pad"), static_cast<uint64_t>(Md), Md, Cp,
                     choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
   if (ts.L > 0) {
     if (!make_dw(&ts.dWpost, ts.a_post(ws), 128, B16(ts.off_g16a), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXpost, B16(ts.off_g16a), Md, B16(ts.off_w_post), 128, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXpost, B16(ts.off_g16a), Md, Wsh("post.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
     ts.dW2.resize(ts.L); ts.dX2.resize(ts.L); ts.dW1.resize(ts.L); ts.dX1.resize(ts.L);
     ts.dWo.resize(ts.L); ts.dXo.resize(ts.L); ts.dWqkv.resize(ts.L); ts.dXqkv.resize(ts.L);
     for (int l = 0; l < ts.L; ++l) {
       if (!make_dw(&ts.dW2[l], ts.hidden(ws, l), Md, B16(ts.off_dh16), 128, 128, Mp, cg)) return SMD_ERR_CUDA;
-      if (!make_dx(&ts.dX2[l], B16(ts.off_dh16), 128, B16(ts.off_w_ffn2[l]), Md, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dX2[l], B16(ts.off_dh16), 128, Wsh(LN(l) + "ffn2.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
       if (!make_dw(&ts.dW1[l], ts.a2(ws, l), 128, B16(ts.off_g16b), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
-      if (!make_dx(&ts.dX1[l], B16(ts.off_g16b), Md, B16(ts.off_w_ffn1[l]), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dX1[l], B16(ts.off_g16b), Md, Wsh(LN(l) + "ffn1.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
       if (!make_dw(&ts.dWo[l], ts.o(ws, l), 128, B16(ts.off_dh16), 128, 128, Mp, 1)) return SMD_ERR_CUDA;
-      if (!make_dx(&ts.dXo[l], B16(ts.off_dh16), 128, B16(ts.off_w_o[l]), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dXo[l], B16(ts.off_dh16), 128, Wsh(LN(l) + "attn.out.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
       if (!make_dw(&ts.dWqkv[l], ts.a1(ws, l), 128, B16(ts.off_dqkv16), 384, 384, Mp, 1)) return SMD_ERR_CUDA;
       ts.dWqkv[l].BN = 128;
-      if (!make_dx(&ts.dXqkv[l], B16(ts.off_dqkv16), 384, B16(ts.off_w_qkv[l]), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dXqkv[l], B16(ts.off_dqkv16), 384, Wsh(LN(l) + "attn.qkv.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
     }
   } else {
     if (!make_dw(&ts.dWin, p->buf<__nv_bfloat16>("xb"), C, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
   }
   return SMD_OK;
-}
-
-// plain (in,out) bf16 copies of the GEMM weights: B operands of the dX GEMMs (jobs of the one-launch repack)
-void train_pack_jobs(smd_plan* p) {
-  TrainState& ts = p->train;
-  uint8_t* ws = p->ws;
-  const int Md = p->cfg.mlp_dims, C = p->cfg.channels;
-  const int Cp = (C + 63) / 64 * 64;
-  auto cast = [&](const std::string& name, size_t off, int K, int N, int ld) {
-    add_pack_job_ptr(p, name, ts.at<void>(ws, off), K, N, 1, ld);
-  };
-  for (int l = 0; l < ts.L; ++l) {
-    const std::string s = "l" + std::to_string(l) + ".";
-    cast(s + "attn.qkv.kernel", ts.off_w_qkv[l], 128, 384, 384);
-    cast(s + "attn.out.kernel", ts.off_w_o[l], 128, 128, 128);
-    cast(s + "ffn1.kernel", ts.off_w_ffn1[l], 128, Md, Md);
-    cast(s + "ffn2.kernel", ts.off_w_ffn2[l], Md, 128, 128);
-  }
-  if (ts.L) cast("post.kernel", ts.off_w_post, 128, Md, Md);
-  for (int k = 0; k < ts.K; ++k) {
-    const std::string s = "k" + std::to_string(k) + ".";
-    cast(s + "res.a.kernel", ts.off_w_a[k], Md, Md, Md);
-    cast(s + "res.b.kernel", ts.off_w_b[k], Md, Md, Md);
-    cast(s + "film.ss.kernel", ts.off_w_ss[k], 512, 2 * Md, 2 * Md);
-  }
-  cast("out.kernel", ts.off_w_out, Md, C, Cp);   // zero-padded to Cp columns (padding zeroed at bind)
 }
 
 static cudaError_t gemm_k(const GemmOp& op0, int rows, int K, int splits, const GemmEpilogue& e, cudaStream_t st) {

@@ -113,6 +113,5 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
                 float* y, cudaStream_t st, TrainState* save);
 int train_bind(smd_plan* p);
 int ensure_side_stream(smd_plan* p);
-void train_pack_jobs(smd_plan* p);
 void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld);
 }  // namespace smd

@@ -28,7 +28,7 @@ static void add_tensor(smd_plan* p, const std::string& name, std::initializer_li
   for (; i < 4; ++i) t.shape[i] = 1;
   t.offset = p->arena;
   p->off[name] = t.offset;
-  p->arena += (t.size() + 3) / 4 * 4;  // keep every tensor 16-byte aligned
+  p->arena += (t.size() + 7) / 8 * 8;  // 32-byte aligned in fp32 => 16-byte aligned in the bf16 shadow arena (TMA)
   p->tensors.push_back(t);
 }
 
@@ -98,24 +98,13 @@ static void build_workspace(smd_plan* p) {
   const smd_config& c = p->cfg;
   const size_t Mp = p->Mp, Md = c.mlp_dims, C = c.channels, B = c.max_batch, K = p->K;
   const bool tr = c.arch == SMD_ARCH_TRANSFORMER_DDPM;
-  // packed bf16 weights ([out][in], K-major tensor-core operands)
-  if (tr) {
-    for (int l = 0; l < c.num_layers; ++l) {
-      const std::string pre = "w.l" + std::to_string(l) + ".";
-      ws_add(p, pre + "qkv", 3 * kE * kE * 2);
-      ws_add(p, pre + "o", kE * kE * 2);
-      ws_add(p, pre + "ffn1", Md * kE * 2);
-      ws_add(p, pre + "ffn2", kE * Md * 2);
-    }
-    ws_add(p, "w.post", Md * kE * 2);
-  } else {
-    ws_add(p, "w.in", Md * ((C + 63) / 64 * 64) * 2);
-  }
-  for (size_t k = 0; k < K; ++k) {
-    ws_add(p, "w.k" + std::to_string(k) + ".a", Md * Md * 2);
-    ws_add(p, "w.k" + std::to_string(k) + ".b", Md * Md * 2);
-  }
-  ws_add(p, "w.out", ((C + 15) / 16 * 16) * Md * 2);
+  // bf16 shadow of the whole parameter arena (same offsets): every GEMM weight operand is read from it in place --
+  // forward as an MN-major B operand ((in,out) = [K][N]), dX as a K-major B operand ([N=in][K=out]) -- so there
+  // are no transposed copies and the optimizer refreshes it in the same pass that updates the fp32 masters.
+  ws_add(p, "wshadow", static_cast<size_t>(p->arena) * 2);
+  // out.kernel is (Md, C) with C = 42 / 146: its 2C-byte row pitch is not TMA-addressable, so it gets a copy
+  // zero-padded to a multiple of 64 columns
+  ws_add(p, "w.out_pad", Md * ((C + 63) / 64 * 64) * 2);
   // activations
   if (tr) {
     ws_add(p, "h", Mp * kE * 4);
@@ -168,30 +157,41 @@ static void host_freqs(float* f) {
 static int build_ops(smd_plan* p) {
   const smd_config& c = p->cfg;
   const int Md = c.mlp_dims, C = c.channels, cg = c.cta_group;
+  const int Cp = (C + 63) / 64 * 64;
   const uint64_t Mp = p->Mp;
-  auto W = [&](const std::string& n) { return p->buf<void>(n); };
+  auto A = [&](const std::string& n) { return p->buf<void>(n); };
+  auto Wsh = [&](const std::string& n) { return static_cast<const void*>(p->buf<__nv_bfloat16>("wshadow") + p->off.at(n)); };
+  // forward GEMM: A K-major activations [Mp][K], B = (in,out) weight read MN-major ([K][N]) from the shadow arena
+  auto fwd = [&](GemmOp* op, const std::string& a, const std::string& w, int K, int N, int BN) {
+    return make_gemm_op(op, A(a), Mp, Wsh(w), static_cast<uint64_t>(N), N, K, BN, cg, 0, 1);
+  };
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
     p->op_qkv.resize(c.num_layers); p->op_o.resize(c.num_layers);
     p->op_ffn1.resize(c.num_layers); p->op_ffn2.resize(c.num_layers);
     for (int l = 0; l < c.num_layers; ++l) {
-      const std::string pre = "w.l" + std::to_string(l) + ".";
-      if (!make_gemm_op(&p->op_qkv[l], W("a"), Mp, W(pre + "qkv"), 3 * kE, 3 * kE, kE, 128, cg, 0, 0)) return SMD_ERR_CUDA;
-      if (!make_gemm_op(&p->op_o[l], W("o"), Mp, W(pre + "o"), kE, kE, kE, 128, cg, 0, 0)) return SMD_ERR_CUDA;
-      if (!make_gemm_op(&p->op_ffn1[l], W("a"), Mp, W(pre + "ffn1"), Md, Md, kE, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
-      if (!make_gemm_op(&p->op_ffn2[l], W("hidden"), Mp, W(pre + "ffn2"), kE, kE, Md, 128, cg, 0, 0)) return SMD_ERR_CUDA;
+      const std::string pre = "l" + std::to_string(l) + ".";
+      if (!fwd(&p->op_qkv[l], "a", pre + "attn.qkv.kernel", kE, 3 * kE, 128)) return SMD_ERR_CUDA;
+      if (!fwd(&p->op_o[l], "o", pre + "attn.out.kernel", kE, kE, 128)) return SMD_ERR_CUDA;
+      if (!fwd(&p->op_ffn1[l], "a", pre + "ffn1.kernel", kE, Md, 256)) return SMD_ERR_CUDA;
+      if (!fwd(&p->op_ffn2[l], "hidden", pre + "ffn2.kernel", Md, kE, 128)) return SMD_ERR_CUDA;
     }
-    if (!make_gemm_op(&p->op_post, W("a"), Mp, W("w.post"), Md, Md, kE, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+    if (!fwd(&p->op_post, "a", "post.kernel", kE, Md, 256)) return SMD_ERR_CUDA;
   } else {
-    const int Cp = (C + 63) / 64 * 64;
-    if (!make_gemm_op(&p->op_in, W("xb"), Mp, W("w.in"), Md, Md, Cp, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+    if (!fwd(&p->op_in, "xb", "in.kernel", C, Md, 256)) return SMD_ERR_CUDA;
   }
   p->op_a.resize(p->K); p->op_b.resize(p->K);
   for (int k = 0; k < p->K; ++k) {
-    const std::string pre = "w.k" + std::to_string(k) + ".";
-    if (!make_gemm_op(&p->op_a[k], W("act"), Mp, W(pre + "a"), Md, Md, Md, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
-    if (!make_gemm_op(&p->op_b[k], W("act"), Mp, W(pre + "b"), Md, Md, Md, choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+    const std::string pre = "k" + std::to_string(k) + ".res.";
+    if (!fwd(&p->op_a[k], "act", pre + "a.kernel", Md, Md, 256)) return SMD_ERR_CUDA;
+    if (!fwd(&p->op_b[k], "act", pre + "b.kernel", Md, Md, 256)) return SMD_ERR_CUDA;
   }
-  if (!make_gemm_op(&p->op_out, W("act"), Mp, W("w.out"), C, C, Md, choose_bn(C, cg), cg, 0, 0)) return SMD_ERR_CUDA;
+  // output projection from the padded copy [Md][Cp]: N = C columns are valid, the tile is Cp (<= 256) wide
+  {
+    const int BN = Cp >= 256 ? 256 : Cp;
+    const int ocg = (BN % (64 * cg) == 0) ? cg : 1;
+    if (!make_gemm_op(&p->op_out, A("act"), Mp, A("w.out_pad"), static_cast<uint64_t>(Cp), C, Md, BN, ocg, 0, 1))
+      return SMD_ERR_CUDA;
+  }
   return SMD_OK;
 }
 
@@ -454,38 +454,15 @@ void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int
   p->pack_jobs.push_back(j);
 }
 
-// job list: transposed [out][in] copies for the forward GEMMs (+ plain (in,out) copies for dX when training)
+// the only repack job left: out.kernel -> zero-padded [Md][Cp] copy (everything else is read from the bf16 shadow)
 static int build_pack_jobs(smd_plan* plan) {
   const smd_config& c = plan->cfg;
-  const int Md = c.mlp_dims, C = c.channels;
+  const int Md = c.mlp_dims, C = c.channels, Cp = (C + 63) / 64 * 64;
   plan->pack_jobs.clear();
   plan->pack_tiles = 0;
-  auto T = [&](const std::string& src, const std::string& dst, int K, int N) {
-    add_pack_job(plan, src, plan->buf<void>(dst), K, N, 0, K);
-  };
-  if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
-    for (int l = 0; l < c.num_layers; ++l) {
-      const std::string s = "l" + std::to_string(l) + ".", d = "w.l" + std::to_string(l) + ".";
-      T(s + "attn.qkv.kernel", d + "qkv", kE, 3 * kE);
-      T(s + "attn.out.kernel", d + "o", kE, kE);
-      T(s + "ffn1.kernel", d + "ffn1", kE, Md);
-      T(s + "ffn2.kernel", d + "ffn2", Md, kE);
-    }
-    T("post.kernel", "w.post", kE, Md);
-  } else {
-    T("in.kernel", "w.in", C, Md);
-  }
-  for (int k = 0; k < plan->K; ++k) {
-    const std::string s = "k" + std::to_string(k) + ".res.", d = "w.k" + std::to_string(k) + ".";
-    T(s + "a.kernel", d + "a", Md, Md);
-    T(s + "b.kernel", d + "b", Md, Md);
-  }
-  T("out.kernel", "w.out", Md, C);
-  if (c.training) train_pack_jobs(plan);
-  if (plan->pack_jobs.size() > 256) { set_error("too many pack jobs"); return SMD_ERR_INVALID; }
+  add_pack_job_ptr(plan, "out.kernel", plan->buf<void>("w.out_pad"), Md, C, 1, Cp);
   SMD_CUDA(cudaMemcpy(plan->buf<PackJob>("packjobs"), plan->pack_jobs.data(), plan->pack_jobs.size() * sizeof(PackJob),
                       cudaMemcpyHostToDevice));
-  if (plan->pack_tiles > 65536) { set_error("too many pack tiles"); return SMD_ERR_INVALID; }
   std::vector<int> bm(static_cast<size_t>(plan->pack_tiles) * 2);
   for (size_t j = 0; j < plan->pack_jobs.size(); ++j) {
     const PackJob& pj = plan->pack_jobs[j];
@@ -495,7 +472,6 @@ static int build_pack_jobs(smd_plan* plan) {
   SMD_CUDA(cudaMemcpy(plan->buf<int>("packmap"), bm.data(), bm.size() * sizeof(int), cudaMemcpyHostToDevice));
   return SMD_OK;
 }
-
 
 }  // namespace smd
 
@@ -586,16 +562,27 @@ int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
   return SMD_OK;
 }
 
-int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
+static int refresh_operands(smd_plan* plan, const float* params, bool shadow_is_fresh, cudaStream_t st) {
   if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), plan->buf<void>("packmap"), plan->pack_tiles, st);
-  CNT();
+  if (!shadow_is_fresh) {
+    launch_cast_bf16(params, plan->buf<__nv_bfloat16>("wshadow"), static_cast<size_t>(plan->arena), st); CNT();
+  }
+  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), plan->buf<void>("packmap"), plan->pack_tiles, st); CNT();
   SMD_LAUNCH_CHECK("pack_weights");
   plan->packed = true;
   plan->film_tab_ready = false;   // parameters changed
   return SMD_OK;
 }
+
+int smd_pack_weights(smd_plan* plan, const float* params, smd_stream_t stream) {
+  return refresh_operands(plan, params, false, static_cast<cudaStream_t>(stream));
+}
+
+int smd_pack_weights_after_adam(smd_plan* plan, const float* params, smd_stream_t stream) {
+  return refresh_operands(plan, params, true, static_cast<cudaStream_t>(stream));
+}
+
+void* smd_shadow_arena(smd_plan* plan) { return plan->ws ? plan->buf<void>("wshadow") : nullptr; }
 
 int smd_forward(smd_plan* plan, const float* params, const float* x, const float* t, int t_broadcast, int batch,
                 float* y, smd_stream_t stream) {

@@ -50,22 +50,7 @@ void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
   ts.off_de = add("t.de", B * 512 * 4);
   ts.off_de2 = add("t.de2", B * 512 * 4);
   ts.off_loss = add("t.loss", B * 4);
-  // plain (in,out) bf16 weight copies: the K-major B operand of every dX GEMM
-  for (int l = 0; l < ts.L; ++l) {
-    ts.off_w_qkv.push_back(add(nm("wqkv", l), kEt * 3 * kEt * 2));
-    ts.off_w_o.push_back(add(nm("wo", l), kEt * kEt * 2));
-    ts.off_w_ffn1.push_back(add(nm("wffn1_", l), kEt * Md * 2));
-    ts.off_w_ffn2.push_back(add(nm("wffn2_", l), Md * kEt * 2));
-  }
-  if (ts.L) ts.off_w_post = add("t.wpost", kEt * Md * 2);
-  else ts.off_w_in = add("t.win", Cp * Md * 2);
-  for (int k = 0; k < K; ++k) {
-    ts.off_w_a.push_back(add(nm("wa", k), Md * Md * 2));
-    ts.off_w_b.push_back(add(nm("wb", k), Md * Md * 2));
-  }
-  ts.off_w_out = add("t.wout", Md * Cp * 2);
   const size_t Bp = (B + 127) / 128 * 128;
-  for (int k = 0; k < K; ++k) ts.off_w_ss.push_back(add(nm("wss", k), 512 * 2 * Md * 2));
   ts.off_e2_16 = add("t.e2_16", Bp * 512 * 2);
   ts.off_dss16 = add("t.dss16", Bp * 2 * Md * 2);
 }
@@ -97,7 +82,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 float* __restrict__ ema, long long n, float lr, float max_norm, float b1, float b2, float eps,
+                 float* __restrict__ ema, __nv_bfloat16* __restrict__ shadow, long long n, float lr, float max_norm, float b1, float b2, float eps,
                  float bc1, float bc2, float mu, const float* __restrict__ sumsq, float* __restrict__ gnorm_out) {
   const float norm = sqrtf(*sumsq);
   // jax.experimental.optimizers.clip_grads: g if norm < max else g * (max / norm)
@@ -112,6 +97,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     const float mh = mi / bc1, vh = vi / bc2;
     const float pi = p[i] - lr * mh / (sqrtf(vh) + eps);
     p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
     if (ema) ema[i] = ema[i] * mu + pi * (1.0f - mu);
   }
 }
@@ -128,9 +114,9 @@ using namespace smd;
 
 extern "C" {
 
-int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, float* ema_or_null, long long n,
-                  float lr, int step, float max_norm, float beta1, float beta2, float eps, float ema_mu,
-                  float* scratch, float* grad_norm_out, smd_stream_t stream) {
+int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, float* ema_or_null,
+                  void* bf16_shadow_or_null, long long n, float lr, int step, float max_norm, float beta1,
+                  float beta2, float eps, float ema_mu, float* scratch, float* grad_norm_out, smd_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n <= 0 || !scratch) { set_error("bad arguments"); return SMD_ERR_INVALID; }
   if (cudaMemsetAsync(scratch, 0, sizeof(float), st) != cudaSuccess) { set_error("memset failed"); return SMD_ERR_CUDA; }
@@ -140,7 +126,8 @@ int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, flo
   const double t = static_cast<double>(step) + 1.0;
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), t));
-  clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, adam_m, adam_v, ema_or_null, n, lr, max_norm, beta1, beta2,
+  clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, adam_m, adam_v, ema_or_null,
+                                           static_cast<__nv_bfloat16*>(bf16_shadow_or_null), n, lr, max_norm, beta1, beta2,
                                            eps, bc1, bc2, ema_mu, scratch, grad_norm_out);
   g_launches.fetch_add(1);
   cudaError_t e = cudaGetLastError();

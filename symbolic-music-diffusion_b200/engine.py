@@ -197,7 +197,7 @@ class Engine:
     def clip_adam(self, grads, m, v, lr: float, step: int, max_norm: float, scratch, gnorm, ema=None,
                   beta1=0.9, beta2=0.999, eps=1e-8, mu=0.999):
         _lib.check(self.lib.smd_clip_adam(self.params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                          _ptr(ema), self.arena_floats, float(lr), int(step), float(max_norm),
+                                          _ptr(ema), self.lib.smd_shadow_arena(self._plan), self.arena_floats, float(lr), int(step), float(max_norm),
                                           float(beta1), float(beta2), float(eps), float(mu), scratch.data_ptr(),
                                           gnorm.data_ptr(), self._stream()))
 
@@ -247,7 +247,8 @@ class Engine:
         self.clip_adam(self.grads, self.adam_m, self.adam_v, lr, self.opt_step, grad_clip, self._scratch,
                        self.grad_norm, ema=self.ema_params, mu=mu)
         self.opt_step += 1
-        self.repack()
+        # the fused clip+Adam kernel already refreshed the bf16 shadow arena; only the padded out.kernel copy is left
+        _lib.check(self.lib.smd_pack_weights_after_adam(self._plan, self.params.data_ptr(), self._stream()))
 
     def train_step(self, x0, used_alpha, eps, lr: float, grad_clip: float = 1.0, process_group=None,
                    world_size: int = 1):

@@ -36,7 +36,9 @@ _SIGNATURES = {
     "smd_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "smd_ddpm_loss": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "smd_ddpm_grads": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
-    "smd_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, C.c_longlong, C.c_float, C.c_int, C.c_float, C.c_float,
+    "smd_pack_weights_after_adam": (C.c_int, [_P, _P, _P]),
+    "smd_shadow_arena": (_P, [_P]),
+    "smd_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_longlong, C.c_float, C.c_int, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     "smd_ema_update": (C.c_int, [_P, _P, C.c_longlong, C.c_float, _P]),
     "smd_objective_setup": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, _P]),

@@ -29,7 +29,7 @@ class Optimizer:
         from . import lib as _lib
         mn = 3.0e38 if max_norm == float("inf") else float(max_norm)
         _lib.check(eng.lib.smd_clip_adam(self.target.arena.flat.data_ptr(), grad.data_ptr(), self.grad_ema.data_ptr(),
-                                         self.grad_sq_ema.data_ptr(), None if ema is None else ema.data_ptr(),
+                                         self.grad_sq_ema.data_ptr(), None if ema is None else ema.data_ptr(), None,
                                          self.target.arena.flat.numel(), lr, self.step, mn, self.beta1, self.beta2,
                                          self.eps, mu, self._scratch.data_ptr(), self.grad_norm.data_ptr(),
                                          torch.cuda.current_stream().cuda_stream))
