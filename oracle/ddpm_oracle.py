@@ -135,7 +135,15 @@ def dense_res_block(x: Tensor, scale: Tensor, shift: Tensor, p: Dict[str, Tensor
     o = scale * o + shift
     o = swish(o)
     o = dense(o, p[prefix + "a.kernel"], p[prefix + "a.bias"], emulate_bf16)
-    o = layer_norm(o, p[prefix + "ln_b.scale"], p[prefix + "ln_b.bias"])
+    if emulate_bf16:
+        # the CUDA path stores this intermediate as bf16 (it only feeds the next LayerNorm), but takes the
+        # LayerNorm statistics from the fp32 accumulators
+        mean = o.mean(dim=-1, keepdim=True)
+        var = (o * o).mean(dim=-1, keepdim=True) - mean * mean
+        oq = _q(o, True)
+        o = (oq - mean) * (torch.rsqrt(var + 1e-6) * p[prefix + "ln_b.scale"]) + p[prefix + "ln_b.bias"]
+    else:
+        o = layer_norm(o, p[prefix + "ln_b.scale"], p[prefix + "ln_b.bias"])
     o = scale * o + shift
     o = swish(o)
     o = dense(o, p[prefix + "b.kernel"], p[prefix + "b.bias"], emulate_bf16)

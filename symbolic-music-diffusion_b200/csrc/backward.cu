@@ -190,7 +190,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     SMD_CUDA(launch_gemm(ts.dXb[k], M, e, st));
     LnFilmBwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.g16 = g16; a.u = ts.r1(ws, k); a.stats = stats + (2 * k + 1) * sstride;
+    a.g16 = g16; a.u16 = reinterpret_cast<const __nv_bfloat16*>(ts.r1(ws, k)); a.stats = stats + (2 * k + 1) * sstride;
     a.gamma = p->P(params, pre + "res.ln_b.scale"); a.beta = p->P(params, pre + "res.ln_b.bias");
     a.ss = ss_k; a.act = 2;
     a.dx32 = nullptr; a.dx16 = dr16;   // dr1 is only consumed as a bf16 GEMM operand (and its column sums)

@@ -11,7 +11,8 @@ namespace smd {
 struct LnFilmBwdArgs {
   const float* g;        // [M][N] gradient wrt the bf16 activation that fed the GEMM (fp32), or null ->
   const __nv_bfloat16* g16;  // the same gradient stored as bf16 (what the dX GEMM epilogue writes)
-  const float* u;        // [M][N] LayerNorm input
+  const float* u;        // [M][N] LayerNorm input (fp32), or null ->
+  const __nv_bfloat16* u16;  // the LayerNorm input stored as bf16
   const float* stats;    // [M][2] (sum, sumsq) of u rows
   const float* gamma;    // [N]
   const float* beta;     // [N]
@@ -76,7 +77,14 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
         } else {
           g4[q] = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
         }
-        u4[q] = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
+        if (a.u16) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(a.u16 + static_cast<size_t>(row) * N + c);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          u4[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          u4[q] = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
+        }
       } else {
         g4[q] = make_float4(0, 0, 0, 0); u4[q] = make_float4(0, 0, 0, 0);
       }

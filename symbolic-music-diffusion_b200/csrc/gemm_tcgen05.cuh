@@ -27,7 +27,7 @@ enum : uint32_t {
 static constexpr uint32_t kEpiGeneric = 0xFFFu;
 static constexpr uint32_t kEpiF32 = F_BIAS | F_F32 | F_STATS;                     // qkv, post, res-block a, dX outputs
 static constexpr uint32_t kEpiF32Res = F_BIAS | F_RES | F_F32 | F_STATS;          // res-block b
-static constexpr uint32_t kEpiAct = F_BIAS | F_ACT | F_BF16 | F_PRE;              // FFN up (+GELU)
+static constexpr uint32_t kEpiAct = F_BIAS | F_ACT | F_BF16 | F_PRE | F_STATS;    // FFN up (+GELU); res-block a (bf16 + row stats)
 static constexpr uint32_t kEpiLn = F_BIAS | F_RES | F_F32 | F_LN | F_BF16;        // attention out / FFN down + LayerNorm
 static constexpr uint32_t kEpiGG = F_GG | F_BF16;                                 // FFN backward (x gelu')
 static constexpr uint32_t kEpiAtomic = F_F32 | F_ATOMIC;                          // split-K weight gradients

@@ -105,8 +105,13 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float s = 0.f;
+    const float4* kr = reinterpret_cast<const float4*>(&sK[j * 128 + h * DH]);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) s = fmaf(q[d], sK[j * 128 + h * DH + d], s);
+    for (int d4 = 0; d4 < DH / 4; ++d4) {
+      const float4 k4 = kr[d4];   // one 16-byte broadcast read per 4 MACs
+      s = fmaf(q[4 * d4], k4.x, s); s = fmaf(q[4 * d4 + 1], k4.y, s);
+      s = fmaf(q[4 * d4 + 2], k4.z, s); s = fmaf(q[4 * d4 + 3], k4.w, s);
+    }
     sc[j] = s;
     mx = fmaxf(mx, s);
   }
@@ -121,8 +126,13 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
   for (int j = 0; j < 32; ++j) {
     const float p = sc[j] * inv;
     sc[j] = p;
+    const float4* vr = reinterpret_cast<const float4*>(&sV[j * 128 + h * DH]);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, sV[j * 128 + h * DH + d], acc[d]);
+    for (int d4 = 0; d4 < DH / 4; ++d4) {
+      const float4 v4 = vr[d4];
+      acc[4 * d4] = fmaf(p, v4.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p, v4.y, acc[4 * d4 + 1]);
+      acc[4 * d4 + 2] = fmaf(p, v4.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p, v4.w, acc[4 * d4 + 3]);
+    }
   }
   __nv_bfloat16* orow = o + (static_cast<size_t>(b) * 32 + lane) * 128 + h * DH;
 #pragma unroll
@@ -147,14 +157,25 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 // LayerNorm-apply + FiLM + activation -> bf16 (one warp per row)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ g,
+ln_film_act_kernel(const float* __restrict__ u, const __nv_bfloat16* __restrict__ u16,
+                   const float* __restrict__ stats, const float* __restrict__ g,
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
                    int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
                    const int* __restrict__ film_row_dev) {
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
-  const float* ur = u + static_cast<size_t>(m) * N;
+  const float* ur = u ? u + static_cast<size_t>(m) * N : nullptr;
+  const __nv_bfloat16* ur16 = u16 ? u16 + static_cast<size_t>(m) * N : nullptr;
+  auto load4 = [&](int c) {
+    if (ur16) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(ur16 + c);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    return *reinterpret_cast<const float4*>(ur + c);
+  };
   float s1, s2;
   if (stats != nullptr) {
     s1 = stats[2 * static_cast<size_t>(m)];
@@ -162,7 +183,7 @@ ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats,
   } else {
     s1 = 0.f; s2 = 0.f;
     for (int c = lane * 4; c < N; c += 128) {
-      const float4 t = *reinterpret_cast<const float4*>(ur + c);
+      const float4 t = load4(c);
       s1 += t.x + t.y + t.z + t.w;
       s2 += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
     }
@@ -177,7 +198,7 @@ ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats,
   const float* sh = shift ? shift + frow * film_ld : nullptr;
   __nv_bfloat16* orow = out + static_cast<size_t>(m) * N;
   for (int c = lane * 4; c < N; c += 128) {
-    const float4 t = *reinterpret_cast<const float4*>(ur + c);
+    const float4 t = load4(c);
     const float4 g4 = *reinterpret_cast<const float4*>(g + c);
     const float4 b4 = *reinterpret_cast<const float4*>(bta + c);
     float y[4] = {(t.x - mean) * (rstd * g4.x) + b4.x, (t.y - mean) * (rstd * g4.y) + b4.y,
@@ -201,9 +222,9 @@ ln_film_act_kernel(const float* __restrict__ u, const float* __restrict__ stats,
 }
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
-                        int S, cudaStream_t st, const int* film_row_dev) {
+                        int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16) {
   const int blocks = (M + 7) / 8;
-  ln_film_act_kernel<<<blocks, 256, 0, st>>>(u, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N, S,
+  ln_film_act_kernel<<<blocks, 256, 0, st>>>(u, u16, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N, S,
                                              film_row_dev);
 }
 

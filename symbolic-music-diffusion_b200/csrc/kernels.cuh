@@ -123,7 +123,8 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 // stats[m] = (sum, sumsq) over the N columns; scale/shift rows selected by m / S (or row 0 if film_bcast)
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
-                        int S, cudaStream_t st, const int* film_row_dev = nullptr);
+                        int S, cudaStream_t st, const int* film_row_dev = nullptr,
+                        const __nv_bfloat16* u16 = nullptr);   // u16: the LayerNorm input stored as bf16 (u == null)
 
 // enc[r, j] = sin((5000 t_r) f_j), enc[r, 64 + j] = cos(...)                          (models/ncsn.py:25-41)
 void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R, cudaStream_t st);

@@ -246,26 +246,27 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
     }
     const float* shift = scale + Md;
     float* u_in = u;
-    float* r1_out = r1;
+    __nv_bfloat16* r1_out = reinterpret_cast<__nv_bfloat16*>(r1);   // r1 only feeds a LayerNorm: bf16 is enough
     __nv_bfloat16* act_a = act;
     __nv_bfloat16* act_b = act;
     float* u_out = u;
     if (save) {  // training keeps every block's tensors
-      u_in = save->u(p->ws, k); r1_out = save->r1(p->ws, k); act_a = save->act_a(p->ws, k);
+      u_in = save->u(p->ws, k); r1_out = reinterpret_cast<__nv_bfloat16*>(save->r1(p->ws, k)); act_a = save->act_a(p->ws, k);
       act_b = save->act_b(p->ws, k); u_out = save->u(p->ws, k + 1);
     }
     launch_ln_film_act(u_in, stats + (2 * k) * sstride, p->P(params, pre + "ln_a.scale"), p->P(params, pre + "ln_a.bias"),
                        scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st, frow_dev); CNT();
     GemmEpilogue e = epi();
     e.bias = p->P(params, pre + "a.bias");
-    e.out_f32 = r1_out; e.ld_f32 = Md;
+    e.out_bf16 = r1_out; e.ld_bf16 = Md;
     e.row_stats = stats + (2 * k + 1) * sstride;
     GemmOp opa = p->op_a[k];
     GemmOp opb = p->op_b[k];
     if (save) { if (!retarget_a(&opa, act_a, p->Mp) || !retarget_a(&opb, act_b, p->Mp)) return SMD_ERR_CUDA; }
     SMD_CUDA(launch_gemm(opa, M, e, st));
-    launch_ln_film_act(r1_out, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
-                       p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st, frow_dev); CNT();
+    launch_ln_film_act(nullptr, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
+                       p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st, frow_dev,
+                       r1_out); CNT();
     e = epi();
     e.bias = p->P(params, pre + "b.bias");
     e.residual = u_in; e.ld_res = Md;
