@@ -108,12 +108,12 @@ inline bool epi_clean(const GemmOp& op, const GemmEpilogue& e) {
          (!e.bias || a16(e.bias)) && (!e.ln_gamma || (a16(e.ln_gamma) && a16(e.ln_beta)));
 }
 
-template <int kCG, uint32_t kF>
+template <int kCG, uint32_t kF, int kEW = 8>
 inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
-  using SM = GemmSmem<kCG>;
+  using SM = GemmSmem<kCG, kEW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG, kF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG, kF, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SM::kTotal);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -134,7 +134,7 @@ inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue&
   if (groups < 1) groups = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * kCG));
-  cfg.blockDim = dim3(384);
+  cfg.blockDim = dim3(SM::kThreads);
   cfg.dynamicSmemBytes = SM::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
@@ -145,7 +145,7 @@ inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue&
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCG, kF>, op.tmA, op.tmB, sh, ep);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCG, kF, kEW>, op.tmA, op.tmB, sh, ep);
 }
 
 template <int kCG>
@@ -153,10 +153,12 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
   const uint32_t need = epi_needs(ep);
   if (epi_clean(op, ep)) {
     auto fits = [&](uint32_t kind) { return (need & ~kind) == 0; };
-    if (fits(kEpiF32)) return launch_gemm_inst<kCG, kEpiF32>(op, M, ep, st);
+    // short-K GEMMs are epilogue-bound: give them a third epilogue warp per TMEM quadrant
+    const bool short_k = op.K <= 256;
+    if (fits(kEpiF32)) return short_k ? launch_gemm_inst<kCG, kEpiF32, 12>(op, M, ep, st) : launch_gemm_inst<kCG, kEpiF32>(op, M, ep, st);
     if (fits(kEpiAtomic)) return launch_gemm_inst<kCG, kEpiAtomic>(op, M, ep, st);
     if (fits(kEpiF32Res)) return launch_gemm_inst<kCG, kEpiF32Res>(op, M, ep, st);
-    if (fits(kEpiAct)) return launch_gemm_inst<kCG, kEpiAct>(op, M, ep, st);
+    if (fits(kEpiAct)) return short_k ? launch_gemm_inst<kCG, kEpiAct, 12>(op, M, ep, st) : launch_gemm_inst<kCG, kEpiAct>(op, M, ep, st);
     if (fits(kEpiGG)) return launch_gemm_inst<kCG, kEpiGG>(op, M, ep, st);
     if ((need & F_LN) && fits(kEpiLn) && op.N == op.BN && op.BN <= 128 && op.BN % 64 == 0 && op.k_splits <= 1)
       return launch_gemm_inst<kCG, kEpiLn>(op, M, ep, st);

@@ -63,17 +63,21 @@ static constexpr int kBK = 64;
 static constexpr int kTmemCols = 512;
 static constexpr int kAccCols = 256;
 
-template <int kCG>
+// kEW = number of epilogue warps (8: two per TMEM lane quadrant; 12: three, for epilogue-bound small-K GEMMs).
+// The pipeline depth is whatever fits next to the epilogue scratch in the 227 KB of shared memory.
+template <int kCG, int kEW = 8>
 struct GemmSmem {
   static constexpr int kBRowsMax = 256 / kCG;
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB
   static constexpr int kBBytes = kBRowsMax * kBK * 2;      // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kCG == 1) ? 4 : 6;
   static constexpr int kBarBytes = 256;
-  static constexpr int kEpiWarps = 8;                                       // 2 warps per TMEM lane quadrant
+  static constexpr int kEpiWarps = kEW;
   static constexpr int kScratchBytes = kEpiWarps * 32 * 33 * 4;            // per-epilogue-warp transpose scratch
+  static constexpr int kMaxSmem = 232448;                                  // 227 KB
+  static constexpr int kStages = (kMaxSmem - 1024 - kBarBytes - kScratchBytes) / kStageBytes;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kScratchBytes + 1024;  // + alignment slack
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
 };
 
 // MUFU.TANH (abs error ~5e-4, far below the bf16 rounding of everything that consumes it)
@@ -101,11 +105,13 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-template <int kCG, uint32_t kF>
-__global__ void __launch_bounds__(384, 1)
+template <int kCG, uint32_t kF, int kEW = 8>
+__global__ void __launch_bounds__(128 + 32 * kEW, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape sh, const GemmEpilogue ep) {
-  using SM = GemmSmem<kCG>;
+  using SM = GemmSmem<kCG, kEW>;
+  static_assert(SM::kStages >= 3, "pipeline too shallow");
+  static_assert(!((kF & F_LN) && !(kF & F_RAGGED)) || kEW == 8, "the paired LayerNorm epilogue needs 8 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kStages * SM::kStageBytes);
@@ -399,7 +405,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int npass = do_ln ? 2 : 1;
       // full-row LayerNorm needs one warp to see the whole row: group 1 sits those tiles out
       const int c_begin = do_ln ? (eg == 0 ? 0 : BN) : eg * 32;
-      const int c_step = do_ln ? 32 : 64;
+      const int c_step = do_ln ? 32 : 32 * (kEW / 4);
       // software prefetch of the residual / gelu-grad tiles of the NEXT chunk (their global latency would
       // otherwise be fully exposed: only two warps per SM sub-partition work on the epilogue)
       float4 rpre[H_RES ? 8 : 1];

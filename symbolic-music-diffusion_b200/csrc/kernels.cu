@@ -154,78 +154,88 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm-apply + FiLM + activation -> bf16 (one warp per row)
+// LayerNorm-apply + FiLM + activation -> bf16.  Column-stationary: blockDim.x = N / 4 threads, each owning one
+// float4 column group whose gamma / beta / scale / shift stay in registers while the CTA streams 32 rows (one
+// sample when S == 32); the row statistics come from the producing GEMM's epilogue, so there is no reduction.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 ln_film_act_kernel(const float* __restrict__ u, const __nv_bfloat16* __restrict__ u16,
                    const float* __restrict__ stats, const float* __restrict__ g,
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
                    int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
                    const int* __restrict__ film_row_dev) {
-  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (m >= M) return;
-  const float* ur = u ? u + static_cast<size_t>(m) * N : nullptr;
-  const __nv_bfloat16* ur16 = u16 ? u16 + static_cast<size_t>(m) * N : nullptr;
-  auto load4 = [&](int c) {
-    if (ur16) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(ur16 + c);
-      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-      return make_float4(lo.x, lo.y, hi.x, hi.y);
-    }
-    return *reinterpret_cast<const float4*>(ur + c);
-  };
-  float s1, s2;
-  if (stats != nullptr) {
-    s1 = stats[2 * static_cast<size_t>(m)];
-    s2 = stats[2 * static_cast<size_t>(m) + 1];
-  } else {
-    s1 = 0.f; s2 = 0.f;
-    for (int c = lane * 4; c < N; c += 128) {
-      const float4 t = load4(c);
-      s1 += t.x + t.y + t.z + t.w;
-      s2 += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
-    }
-    s1 = warp_sum(s1); s2 = warp_sum(s2);
-  }
+  const int c = threadIdx.x * 4;
+  const int r0 = blockIdx.x * 32;
   const float inv_n = 1.0f / static_cast<float>(N);
-  const float mean = s1 * inv_n;
-  const float var = s2 * inv_n - mean * mean;
-  const float rstd = rsqrtf(var + 1e-6f);
-  const size_t frow = film_row_dev ? static_cast<size_t>(*film_row_dev) : (film_bcast ? 0 : static_cast<size_t>(m / S));
-  const float* sc = scale ? scale + frow * film_ld : nullptr;
-  const float* sh = shift ? shift + frow * film_ld : nullptr;
-  __nv_bfloat16* orow = out + static_cast<size_t>(m) * N;
-  for (int c = lane * 4; c < N; c += 128) {
-    const float4 t = load4(c);
-    const float4 g4 = *reinterpret_cast<const float4*>(g + c);
-    const float4 b4 = *reinterpret_cast<const float4*>(bta + c);
-    float y[4] = {(t.x - mean) * (rstd * g4.x) + b4.x, (t.y - mean) * (rstd * g4.y) + b4.y,
-                  (t.z - mean) * (rstd * g4.z) + b4.z, (t.w - mean) * (rstd * g4.w) + b4.w};
-    if (sc != nullptr) {
-      const float4 s4 = *reinterpret_cast<const float4*>(sc + c);
-      const float4 h4 = *reinterpret_cast<const float4*>(sh + c);
-      y[0] = s4.x * y[0] + h4.x; y[1] = s4.y * y[1] + h4.y; y[2] = s4.z * y[2] + h4.z; y[3] = s4.w * y[3] + h4.w;
-    }
-    if (act == 2) {
+  const float4 g4 = *reinterpret_cast<const float4*>(g + c);
+  const float4 b4 = *reinterpret_cast<const float4*>(bta + c);
+  const bool film = scale != nullptr;
+  const bool row_const_film = film && (film_row_dev != nullptr || film_bcast || S == 32);
+  float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row_const_film) {
+    const size_t frow = film_row_dev ? static_cast<size_t>(*film_row_dev) : (film_bcast ? 0 : static_cast<size_t>(r0 / S));
+    s4 = *reinterpret_cast<const float4*>(scale + frow * film_ld + c);
+    h4 = *reinterpret_cast<const float4*>(shift + frow * film_ld + c);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 32; r += 4) {
+    float4 x[4];
+    float mean[4], rstd[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = swishf(y[i]);
+    for (int q = 0; q < 4; ++q) {   // issue the four rows' loads first
+      const int row = r0 + r + q;
+      if (row < M) {
+        if (u16) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(u16 + static_cast<size_t>(row) * N + c);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          x[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          x[q] = *reinterpret_cast<const float4*>(u + static_cast<size_t>(row) * N + c);
+        }
+        const float2 st = *reinterpret_cast<const float2*>(stats + 2 * static_cast<size_t>(row));
+        mean[q] = st.x * inv_n;
+        rstd[q] = rsqrtf(st.y * inv_n - mean[q] * mean[q] + 1e-6f);
+      }
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&p0);
-    pk.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(orow + c) = pk;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int row = r0 + r + q;
+      if (row >= M) continue;
+      if (film && !row_const_film) {
+        const size_t frow = static_cast<size_t>(row / S);
+        s4 = *reinterpret_cast<const float4*>(scale + frow * film_ld + c);
+        h4 = *reinterpret_cast<const float4*>(shift + frow * film_ld + c);
+      }
+      float y[4] = {(x[q].x - mean[q]) * (rstd[q] * g4.x) + b4.x, (x[q].y - mean[q]) * (rstd[q] * g4.y) + b4.y,
+                    (x[q].z - mean[q]) * (rstd[q] * g4.z) + b4.z, (x[q].w - mean[q]) * (rstd[q] * g4.w) + b4.w};
+      if (film) {
+        y[0] = s4.x * y[0] + h4.x; y[1] = s4.y * y[1] + h4.y; y[2] = s4.z * y[2] + h4.z; y[3] = s4.w * y[3] + h4.w;
+      }
+      if (act == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = swishf(y[i]);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * N + c) = pk;
+    }
   }
 }
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
                         int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16) {
-  const int blocks = (M + 7) / 8;
-  ln_film_act_kernel<<<blocks, 256, 0, st>>>(u, u16, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N, S,
-                                             film_row_dev);
+  const int blocks = (M + 31) / 32;
+  if (N / 4 <= 512)
+    ln_film_act_kernel<512><<<blocks, N / 4, 0, st>>>(u, u16, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N,
+                                                    S, film_row_dev);
+  else
+    ln_film_act_kernel<1024><<<blocks, N / 4, 0, st>>>(u, u16, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M,
+                                                     N, S, film_row_dev);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -443,9 +443,6 @@ __global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uin
     out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, i, n));
 }
 
-static void add_pack_job(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld) {
-  add_pack_job_ptr(p, src, dst, K, N, mode, ld);
-}
 void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld) {
   PackJob j;
   j.src_off = p->off.at(src); j.dst = dst; j.K = K; j.N = N; j.mode = mode; j.ld = ld;

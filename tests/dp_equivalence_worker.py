@@ -1,0 +1,61 @@
+"""torchrun worker: data-parallel train_step over W ranks must equal the single-rank step on the whole batch
+(up to summation order).  Launched by tests/test_gpu_dp.py / scripts; prints 'dp-ok' on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from smd_b200 import Engine, ModelConfig, parallel  # noqa: E402
+
+
+def main():
+    parallel.init_from_env("nccl")
+    w, r = parallel.world_size(), parallel.rank()
+    cfg = ModelConfig(num_layers=2, num_heads=8, num_mlp_layers=1, channels=42)
+    B = 8 * w
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-1, 1, (B, 32, 42)).astype(np.float32)
+    eps = rng.standard_normal((B, 32, 42)).astype(np.float32)
+    used = rng.uniform(0.05, 0.99, (B,)).astype(np.float32)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def make(max_batch):
+        e = Engine(cfg, max_batch=max_batch, cta_group=2, training=True)
+        e.set_params(e.init_params(seed=7, perturb=0.02))
+        e.init_train_state()
+        return e
+
+    # data-parallel: each rank takes its rows, grads pre-scaled by 1/global batch, SUM all-reduce
+    e_dp = make(B // w)
+    sl = slice(r * (B // w), (r + 1) * (B // w))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    loss_dp, gn_dp = e_dp.train_step(t(x0[sl]), t(used[sl]), t(eps[sl]), lr=1e-3, world_size=w)
+    torch.cuda.synchronize()
+    # single rank on the whole batch (every rank computes it; compare on rank 0)
+    e_1 = make(B)
+    loss_1, gn_1 = e_1.train_step(t(x0), t(used), t(eps), lr=1e-3, world_size=1)
+    torch.cuda.synchronize()
+    dl = abs(float(loss_dp) - float(loss_1)) / abs(float(loss_1))
+    dg = abs(float(gn_dp) - float(gn_1)) / abs(float(gn_1))
+    dp_ = float((e_dp.params - e_1.params).abs().max())
+    gq = float((e_dp.grads - e_1.grads).norm() / e_1.grads.norm())
+    # every rank must hold identical parameters after the step
+    ref = e_dp.params.clone()
+    dist.broadcast(ref, src=0)
+    same = float((ref - e_dp.params).abs().max())
+    if r == 0:
+        print(f"world {w}: dloss {dl:.2e} dgnorm {dg:.2e} max|dparam| {dp_:.2e} grad rel-L2 {gq:.2e} rank-divergence {same:.1e}")
+    assert dl < 1e-4 and dg < 2e-3 and gq < 2e-3 and same == 0.0, (dl, dg, gq, same)
+    # one Adam step moves parameters by <= lr; the DP and single-rank updates must agree to a fraction of that
+    assert dp_ < 2e-3, dp_
+    if r == 0:
+        print("dp-ok")
+    parallel.shutdown()
+
+
+if __name__ == "__main__":
+    main()
