@@ -154,19 +154,71 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm-apply + FiLM + activation -> bf16.  Column-stationary: blockDim.x = N / 4 threads, each owning one
-// float4 column group whose gamma / beta / scale / shift stay in registers while the CTA streams 32 rows (one
-// sample when S == 32); the row statistics come from the producing GEMM's epilogue, so there is no reduction.
+// LayerNorm-apply + FiLM + activation -> bf16.  HBM-bound: the CTA streams its 32 rows (one sample when S == 32)
+// through a double-buffered shared-memory ring with bulk async copies (cp.async.bulk + mbarrier), 4 rows = up to
+// 32 KB per copy, so ~64 KB per CTA are in flight without tying up registers.  Column-stationary compute:
+// blockDim.x = N / 4 threads, each owning one float4 column group whose gamma / beta / scale / shift stay in
+// registers; the row statistics come from the producing GEMM's epilogue, so there is no reduction.
 // ---------------------------------------------------------------------------------------------------
-template <int MAXT>
+__device__ __forceinline__ uint32_t k_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void k_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void k_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(k_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void k_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   k_smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(k_smem_u32(bar))
+               : "memory");
+}
+
+template <int MAXT, bool IN_BF16>
 __global__ void __launch_bounds__(MAXT)
-ln_film_act_kernel(const float* __restrict__ u, const __nv_bfloat16* __restrict__ u16,
-                   const float* __restrict__ stats, const float* __restrict__ g,
+ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats, const float* __restrict__ g,
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
                    int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
                    const int* __restrict__ film_row_dev) {
+  extern __shared__ __align__(128) uint8_t lsm[];
+  constexpr int RPG = 4;                                   // rows per copy group
+  constexpr int ES = IN_BF16 ? 2 : 4;
+  const uint32_t row_bytes = static_cast<uint32_t>(N) * ES;
+  uint8_t* buf[2] = {lsm, lsm + RPG * row_bytes};
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lsm + 2 * RPG * row_bytes);
   const int c = threadIdx.x * 4;
   const int r0 = blockIdx.x * 32;
+  const int nrows = min(32, M - r0);
+  const int ngroups = (nrows + RPG - 1) / RPG;
+  const uint8_t* src = static_cast<const uint8_t*>(uin) + static_cast<size_t>(r0) * row_bytes;
+  if (threadIdx.x == 0) {
+    k_mbar_init(&bar[0], 1);
+    k_mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int grp) {
+    const int rows = min(RPG, nrows - grp * RPG);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * row_bytes;
+    k_mbar_expect_tx(&bar[grp & 1], bytes);
+    k_bulk_g2s(buf[grp & 1], src + static_cast<size_t>(grp) * RPG * row_bytes, bytes, &bar[grp & 1]);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (ngroups > 1) issue(1);
+  }
   const float inv_n = 1.0f / static_cast<float>(N);
   const float4 g4 = *reinterpret_cast<const float4*>(g + c);
   const float4 b4 = *reinterpret_cast<const float4*>(bta + c);
@@ -178,38 +230,32 @@ ln_film_act_kernel(const float* __restrict__ u, const __nv_bfloat16* __restrict_
     s4 = *reinterpret_cast<const float4*>(scale + frow * film_ld + c);
     h4 = *reinterpret_cast<const float4*>(shift + frow * film_ld + c);
   }
-#pragma unroll 1
-  for (int r = 0; r < 32; r += 4) {
-    float4 x[4];
-    float mean[4], rstd[4];
+  for (int grp = 0; grp < ngroups; ++grp) {
+    k_mbar_wait(&bar[grp & 1], static_cast<uint32_t>((grp >> 1) & 1));
+    const uint8_t* sb = buf[grp & 1];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {   // issue the four rows' loads first
-      const int row = r0 + r + q;
-      if (row < M) {
-        if (u16) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(u16 + static_cast<size_t>(row) * N + c);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-          x[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          x[q] = *reinterpret_cast<const float4*>(u + static_cast<size_t>(row) * N + c);
-        }
-        const float2 st = *reinterpret_cast<const float2*>(stats + 2 * static_cast<size_t>(row));
-        mean[q] = st.x * inv_n;
-        rstd[q] = rsqrtf(st.y * inv_n - mean[q] * mean[q] + 1e-6f);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int row = r0 + r + q;
+    for (int q = 0; q < RPG; ++q) {
+      const int row = r0 + grp * RPG + q;
       if (row >= M) continue;
+      float4 x;
+      if (IN_BF16) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(sb + static_cast<size_t>(q) * row_bytes + static_cast<size_t>(c) * 2);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        x = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        x = *reinterpret_cast<const float4*>(sb + static_cast<size_t>(q) * row_bytes + static_cast<size_t>(c) * 4);
+      }
+      const float2 st = *reinterpret_cast<const float2*>(stats + 2 * static_cast<size_t>(row));
+      const float mean = st.x * inv_n;
+      const float rstd = rsqrtf(st.y * inv_n - mean * mean + 1e-6f);
       if (film && !row_const_film) {
         const size_t frow = static_cast<size_t>(row / S);
         s4 = *reinterpret_cast<const float4*>(scale + frow * film_ld + c);
         h4 = *reinterpret_cast<const float4*>(shift + frow * film_ld + c);
       }
-      float y[4] = {(x[q].x - mean[q]) * (rstd[q] * g4.x) + b4.x, (x[q].y - mean[q]) * (rstd[q] * g4.y) + b4.y,
-                    (x[q].z - mean[q]) * (rstd[q] * g4.z) + b4.z, (x[q].w - mean[q]) * (rstd[q] * g4.w) + b4.w};
+      float y[4] = {(x.x - mean) * (rstd * g4.x) + b4.x, (x.y - mean) * (rstd * g4.y) + b4.y,
+                    (x.z - mean) * (rstd * g4.z) + b4.z, (x.w - mean) * (rstd * g4.w) + b4.w};
       if (film) {
         y[0] = s4.x * y[0] + h4.x; y[1] = s4.y * y[1] + h4.y; y[2] = s4.z * y[2] + h4.z; y[3] = s4.w * y[3] + h4.w;
       }
@@ -224,18 +270,34 @@ ln_film_act_kernel(const float* __restrict__ u, const __nv_bfloat16* __restrict_
       pk.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * N + c) = pk;
     }
+    __syncthreads();                                   // everyone is done reading this buffer
+    if (threadIdx.x == 0 && grp + 2 < ngroups) issue(grp + 2);
   }
 }
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
                         int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16) {
   const int blocks = (M + 31) / 32;
-  if (N / 4 <= 512)
-    ln_film_act_kernel<512><<<blocks, N / 4, 0, st>>>(u, u16, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M, N,
-                                                    S, film_row_dev);
-  else
-    ln_film_act_kernel<1024><<<blocks, N / 4, 0, st>>>(u, u16, stats, g, b, scale, shift, film_ld, film_bcast, act, out, M,
-                                                     N, S, film_row_dev);
+  const int threads = N / 4;
+  const bool bf = (u16 != nullptr);
+  const size_t smem = static_cast<size_t>(2 * 4 * N * (bf ? 2 : 4) + 64);
+  const void* in = bf ? static_cast<const void*>(u16) : static_cast<const void*>(u);
+#define SMD_LN_LAUNCH(MAXT, BF)                                                                                  \
+  {                                                                                                              \
+    static bool attr = false;                                                                                    \
+    if (!attr) {                                                                                                 \
+      cudaFuncSetAttribute(ln_film_act_kernel<MAXT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 * 4 + 64); \
+      attr = true;                                                                                               \
+    }                                                                                                            \
+    ln_film_act_kernel<MAXT, BF><<<blocks, threads, smem, st>>>(in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
+                                                                out, M, N, S, film_row_dev);                     \
+  }
+  if (threads <= 512) {
+    if (bf) SMD_LN_LAUNCH(512, true) else SMD_LN_LAUNCH(512, false)
+  } else {
+    if (bf) SMD_LN_LAUNCH(1024, true) else SMD_LN_LAUNCH(1024, false)
+  }
+#undef SMD_LN_LAUNCH
 }
 
 // ---------------------------------------------------------------------------------------------------
