@@ -97,10 +97,12 @@ __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_GELU_TANH) {
     const float c = 0.7978845608028654f;
-    float u = c * (v + 0.044715f * v * v * v);
-    return 0.5f * v * (1.0f + tanh_fast(u));
+    const float u = v * fmaf(v * v, 0.044715f * c, c);   // c (v + 0.044715 v^3)
+    const float h = 0.5f * v;
+    return fmaf(h, tanh_fast(u), h);
   } else if (act == ACT_SWISH) {
-    return v / (1.0f + __expf(-v));
+    const float h = 0.5f * v;
+    return fmaf(h, tanh_fast(h), h);   // v * sigmoid(v), sigmoid(v) = 0.5 + 0.5 tanh(v/2)
   }
   return v;
 }

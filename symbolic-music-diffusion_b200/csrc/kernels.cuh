@@ -20,10 +20,20 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float swishf(float v) { return v / (1.0f + __expf(-v)); }
-__device__ __forceinline__ float swish_grad(float v) {  // d/dv [v * sigmoid(v)]
-  const float s = 1.0f / (1.0f + __expf(-v));
-  return s * (1.0f + v * (1.0f - s));
+// swish(v) = v * sigmoid(v) with sigmoid(v) = 0.5 + 0.5 * tanh(v / 2): one MUFU.TANH instead of exp + IEEE divide
+// (abs error of tanh.approx ~5e-4; every consumer rounds the result to bf16 or feeds a bf16 GEMM operand)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float swishf(float v) {
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ float swish_grad(float v) {  // d/dv [v * sigmoid(v)] = s * (1 + v * (1 - s))
+  const float s = fmaf(0.5f, tanh_approx(0.5f * v), 0.5f);
+  return s * fmaf(v, 1.0f - s, 1.0f);
 }
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float c = 0.7978845608028654f;
