@@ -288,8 +288,16 @@ def run_gpu(args):
         g_ms = time_dominant_gemm(eng, m_tokens, args.cta_group)
         gflop = 2.0 * m_tokens * 2048 * 2048
         ach = gflop / (g_ms / 1e3) / 1e12
+        traffic = None      # DRAM bytes per launch from the committed `ncu --set full` capture of this same kernel/shape
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_gemm_ncu.json"))).get(str(m_tokens))
+            if cap and args.cta_group == 2:
+                traffic = cap["traffic_bytes"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                            "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst: kernel timed alone)",
+                            "traffic": traffic, "algorithmic_bytes": m_tokens * 2048 * 6 + 2048 * 2048 * 2 + m_tokens * 8 + 8192,
+                            "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst: kernel timed alone)",
                             "kernel": f"gemm_bf16_tcgen05_kernel<{args.cta_group}> [{m_tokens}x2048x2048] res-block GEMM "
                                       "+ bias + row-stat epilogue", "ms_per_launch": g_ms}
         if not args.no_cpu:

@@ -16,6 +16,15 @@ static int pick_splits(int m_rows, int n_cols, int BN, int cg, int num_kb) {
   return s;
 }
 
+// Split count for a dW GEMM that runs beside the dX chain: ~48 CTAs, leaving two thirds of the SMs to `st`.
+static int pick_splits_side(int m_rows, int n_cols, int BN, int cg, int num_kb) {
+  const int tiles = ((m_rows + 128 * cg - 1) / (128 * cg)) * ((n_cols + BN - 1) / BN);
+  int s = 48 / (tiles * cg);
+  if (s < 1) s = 1;
+  if (s > num_kb) s = num_kb;
+  return s;
+}
+
 // dW GEMM: A = X (MN-major [tokens][in]), B = G (MN-major [tokens][out]) -> out_f32 [in][out]
 static bool make_dw(GemmOp* op, const void* X, int in_f, const void* G, int g_cols, int out_f, uint64_t rows, int cg) {
   int BN = (out_f >= 256) ? 256 : ((out_f + 63) / 64 * 64);
@@ -64,15 +73,15 @@ int train_bind(smd_plan* p) {
     ts.dW2.resize(ts.L); ts.dX2.resize(ts.L); ts.dW1.resize(ts.L); ts.dX1.resize(ts.L);
     ts.dWo.resize(ts.L); ts.dXo.resize(ts.L); ts.dWqkv.resize(ts.L); ts.dXqkv.resize(ts.L);
     for (int l = 0; l < ts.L; ++l) {
-      if (!make_dw(&ts.dW2[l], ts.hidden(ws, l), Md, B16(ts.off_dh16), 128, 128, Mp, cg)) return SMD_ERR_CUDA;
-      if (!make_dx(&ts.dX2[l], B16(ts.off_dh16), 128, Wsh(LN(l) + "ffn2.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
-      if (!make_dw(&ts.dW1[l], ts.a2(ws, l), 128, B16(ts.off_g16b), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
-      if (!make_dx(&ts.dX1[l], B16(ts.off_g16b), Md, Wsh(LN(l) + "ffn1.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
-      if (!make_dw(&ts.dWo[l], ts.o(ws, l), 128, B16(ts.off_dh16), 128, 128, Mp, 1)) return SMD_ERR_CUDA;
-      if (!make_dx(&ts.dXo[l], B16(ts.off_dh16), 128, Wsh(LN(l) + "attn.out.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
-      if (!make_dw(&ts.dWqkv[l], ts.a1(ws, l), 128, B16(ts.off_dqkv16), 384, 384, Mp, 1)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dW2[l], ts.hidden(ws, l), Md, B16(ts.off_dh16a[l]), 128, 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dX2[l], B16(ts.off_dh16a[l]), 128, Wsh(LN(l) + "ffn2.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dW1[l], ts.a2(ws, l), 128, B16(ts.off_dr16[l]), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dX1[l], B16(ts.off_dr16[l]), Md, Wsh(LN(l) + "ffn1.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dWo[l], ts.o(ws, l), 128, B16(ts.off_dh16b[l]), 128, 128, Mp, 1)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dXo[l], B16(ts.off_dh16b[l]), 128, Wsh(LN(l) + "attn.out.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dw(&ts.dWqkv[l], ts.a1(ws, l), 128, B16(ts.off_dqkv16[l]), 384, 384, Mp, 1)) return SMD_ERR_CUDA;
       ts.dWqkv[l].BN = 128;
-      if (!make_dx(&ts.dXqkv[l], B16(ts.off_dqkv16), 384, Wsh(LN(l) + "attn.qkv.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
+      if (!make_dx(&ts.dXqkv[l], B16(ts.off_dqkv16[l]), 384, Wsh(LN(l) + "attn.qkv.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
     }
   } else {
     if (!make_dw(&ts.dWin, p->buf<__nv_bfloat16>("xb"), C, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
@@ -112,12 +121,19 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   auto F32 = [&](size_t off) { return ts.at<float>(ws, off); };
 
   SMD_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * p->arena, st));
+  // FiLM (scale|shift) gradients are accumulated with atomics by the two CTAs of a sample and by both uses of a pair
+  SMD_CUDA(cudaMemsetAsync(ts.at<float>(ws, ts.off_dss), 0,
+                           sizeof(float) * static_cast<size_t>(ts.K > 0 ? ts.K : 1) * c.max_batch * 2 * Md, st));
   if (Mk != M) {  // zero the reduction-tail rows of every MN-major gradient operand
     const size_t tail = static_cast<size_t>(Mk - M);
     SMD_CUDA(cudaMemsetAsync(B16(ts.off_g16a) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
     SMD_CUDA(cudaMemsetAsync(B16(ts.off_g16b) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
-    SMD_CUDA(cudaMemsetAsync(B16(ts.off_dh16) + static_cast<size_t>(M) * 128, 0, tail * 128 * 2, st));
-    SMD_CUDA(cudaMemsetAsync(B16(ts.off_dqkv16) + static_cast<size_t>(M) * 384, 0, tail * 384 * 2, st));
+    for (int l = 0; l < ts.L; ++l) {
+      SMD_CUDA(cudaMemsetAsync(B16(ts.off_dh16a[l]) + static_cast<size_t>(M) * 128, 0, tail * 128 * 2, st));
+      SMD_CUDA(cudaMemsetAsync(B16(ts.off_dh16b[l]) + static_cast<size_t>(M) * 128, 0, tail * 128 * 2, st));
+      SMD_CUDA(cudaMemsetAsync(B16(ts.off_dr16[l]) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
+      SMD_CUDA(cudaMemsetAsync(B16(ts.off_dqkv16[l]) + static_cast<size_t>(M) * 384, 0, tail * 384 * 2, st));
+    }
     SMD_CUDA(cudaMemsetAsync(B16(ts.off_dpred16) + static_cast<size_t>(M) * Cp, 0, tail * Cp * 2, st));
   }
   if (Bk != batch) {
@@ -257,7 +273,14 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   // ---------------- post dense + post LayerNorm ----------------
   float* da32 = F32(ts.off_dh2);
   float* dh32 = F32(ts.off_dh);
-  __nv_bfloat16* dh16 = B16(ts.off_dh16);
+  cudaStream_t dws = p->dw_stream;
+  // Weight-gradient GEMMs and bias column sums of the trunk are leaves of the backward graph: they run on
+  // dw_stream with a reduced CTA count while the dX chain (the critical path, mostly 32-CTA launches) keeps `st`.
+  auto fork_dw = [&]() -> cudaError_t {
+    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
+    if (e1 != cudaSuccess) return e1;
+    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
+  };
   {
     GemmEpilogue e = epi();
     e.out_f32 = G("post.kernel"); e.ld_f32 = Md;
@@ -270,7 +293,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     Ln128BwdArgs a;
     memset(&a, 0, sizeof(a));
     a.g = da32; a.h = ts.h(ws, 2 * ts.L); a.gamma = p->P(params, "post_ln.scale");
-    a.dx32 = dh32; a.dx16 = dh16;
+    a.dx32 = dh32; a.dx16 = B16(ts.off_dh16a[ts.L - 1]);
     a.dgamma = G("post_ln.scale"); a.dbeta = G("post_ln.bias");
     a.dbias = G("l" + std::to_string(ts.L - 1) + ".ffn2.bias");
     a.M = M;
@@ -280,63 +303,69 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   // ---------------- transformer trunk ----------------
   for (int l = ts.L - 1; l >= 0; --l) {
     const std::string pre = "l" + std::to_string(l) + ".";
+    __nv_bfloat16* dr16l = B16(ts.off_dr16[l]);
     // FFN: h_out = gelu(a2 W1 + b1) W2 + b2 + h_mid
     GemmEpilogue e = epi();
-    e.out_f32 = G(pre + "ffn2.kernel"); e.ld_f32 = 128;
-    int sp = pick_splits(Md, 128, ts.dW2[l].BN, ts.dW2[l].cg, nkb);
-    e.atomic_out = sp > 1;
-    SMD_CUDA(gemm_k(ts.dW2[l], Md, Mk, sp, e, st));
-    e = epi();
-    e.out_bf16 = dr16; e.ld_bf16 = Md;
+    e.out_bf16 = dr16l; e.ld_bf16 = Md;
     e.gelu_grad_of = ts.hidden_pre(ws, l); e.ld_gg = Md;
     SMD_CUDA(launch_gemm(ts.dX2[l], M, e, st));
-    launch_colsum<__nv_bfloat16>(dr16, Md, G(pre + "ffn1.bias"), M, Md, st); CNT();
+    SMD_CUDA(fork_dw());
+    e = epi();
+    e.out_f32 = G(pre + "ffn2.kernel"); e.ld_f32 = 128;
+    int sp = pick_splits_side(Md, 128, ts.dW2[l].BN, ts.dW2[l].cg, nkb);
+    e.atomic_out = sp > 1;
+    SMD_CUDA(gemm_k(ts.dW2[l], Md, Mk, sp, e, dws));
+    launch_colsum<__nv_bfloat16>(dr16l, Md, G(pre + "ffn1.bias"), M, Md, dws); CNT();
     e = epi();
     e.out_f32 = G(pre + "ffn1.kernel"); e.ld_f32 = Md;
-    sp = pick_splits(128, Md, ts.dW1[l].BN, ts.dW1[l].cg, nkb);
+    sp = pick_splits_side(128, Md, ts.dW1[l].BN, ts.dW1[l].cg, nkb);
     e.atomic_out = sp > 1;
-    SMD_CUDA(gemm_k(ts.dW1[l], 128, Mk, sp, e, st));
+    SMD_CUDA(gemm_k(ts.dW1[l], 128, Mk, sp, e, dws));
     e = epi();
     e.out_f32 = da32; e.ld_f32 = 128;
     SMD_CUDA(launch_gemm(ts.dX1[l], M, e, st));
     Ln128BwdArgs a;
     memset(&a, 0, sizeof(a));
     a.g = da32; a.h = ts.h(ws, 2 * l + 1); a.gamma = p->P(params, pre + "ln2.scale");
-    a.dres = dh32; a.dx32 = dh32; a.dx16 = dh16;
+    a.dres = dh32; a.dx32 = dh32; a.dx16 = B16(ts.off_dh16b[l]);
     a.dgamma = G(pre + "ln2.scale"); a.dbeta = G(pre + "ln2.bias");
     a.dbias = G(pre + "attn.out.bias");
     a.M = M;
     launch_ln128_bwd(a, st); CNT();
     // attention: h_mid = attn(a1) Wo + bo + h_in
+    SMD_CUDA(fork_dw());
     e = epi();
     e.out_f32 = G(pre + "attn.out.kernel"); e.ld_f32 = 128;
-    sp = pick_splits(128, 128, ts.dWo[l].BN, ts.dWo[l].cg, nkb);
+    sp = pick_splits_side(128, 128, ts.dWo[l].BN, ts.dWo[l].cg, nkb);
     e.atomic_out = sp > 1;
-    SMD_CUDA(gemm_k(ts.dWo[l], 128, Mk, sp, e, st));
+    SMD_CUDA(gemm_k(ts.dWo[l], 128, Mk, sp, e, dws));
     e = epi();
     e.out_f32 = da32; e.ld_f32 = 128;
     SMD_CUDA(launch_gemm(ts.dXo[l], M, e, st));
-    SMD_CUDA(launch_attention_bwd(ts.qkv(ws, l), ts.probs(ws, l), da32, B16(ts.off_dqkv16), G(pre + "attn.qkv.bias"),
+    SMD_CUDA(launch_attention_bwd(ts.qkv(ws, l), ts.probs(ws, l), da32, B16(ts.off_dqkv16[l]), G(pre + "attn.qkv.bias"),
                                   batch, c.num_heads, st));
     CNT();
+    SMD_CUDA(fork_dw());
     e = epi();
     e.out_f32 = G(pre + "attn.qkv.kernel"); e.ld_f32 = 384;
-    sp = pick_splits(128, 384, ts.dWqkv[l].BN, ts.dWqkv[l].cg, nkb);
+    sp = pick_splits_side(128, 384, ts.dWqkv[l].BN, ts.dWqkv[l].cg, nkb);
     e.atomic_out = sp > 1;
-    SMD_CUDA(gemm_k(ts.dWqkv[l], 128, Mk, sp, e, st));
+    SMD_CUDA(gemm_k(ts.dWqkv[l], 128, Mk, sp, e, dws));
     e = epi();
     e.out_f32 = da32; e.ld_f32 = 128;
     SMD_CUDA(launch_gemm(ts.dXqkv[l], M, e, st));
     memset(&a, 0, sizeof(a));
     a.g = da32; a.h = ts.h(ws, 2 * l); a.gamma = p->P(params, pre + "ln1.scale");
-    a.dres = dh32; a.dx32 = dh32; a.dx16 = dh16;
+    a.dres = dh32; a.dx32 = dh32; a.dx16 = (l > 0) ? B16(ts.off_dh16a[l - 1]) : nullptr;
     a.dgamma = G(pre + "ln1.scale"); a.dbeta = G(pre + "ln1.bias");
     a.dbias = (l > 0) ? G("l" + std::to_string(l - 1) + ".ffn2.bias") : G("in.bias");
     a.M = M;
     launch_ln128_bwd(a, st); CNT();
   }
+  SMD_CUDA(cudaEventRecord(p->ev_dwjoin, dws));
   // ---------------- input projection ----------------
   launch_embed_bwd(xt, dh32, G("in.kernel"), M, C, st); CNT();
+  SMD_CUDA(cudaStreamWaitEvent(st, p->ev_dwjoin, 0));
   SMD_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
   SMD_LAUNCH_CHECK("backward trunk");
   return SMD_OK;

@@ -1,6 +1,7 @@
 // SIMT kernels of the hand-written backward pass (what jax.value_and_grad derives for train_ncsn.py:282-283;
 // contract per op in SURVEY Appendix E).
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace smd {
@@ -25,13 +26,14 @@ struct LnFilmBwdArgs {
   float* dbeta;          // [N]
   float* dbias;          // [N] += column sums of the dx32 written here, or null
   float* dss;            // [nsamples][2N] gradient of [scale | shift], or null
-  int dss_accum;         // 0: overwrite, 1: add (second use of the same FiLM pair)
+  int dss_accum;         // 0: overwrite, 1: add (second use of the same FiLM pair).  The sequence fast path always
+                         // ADDS: the caller zero-fills dss once per backward pass
   int M, N, S;           // S in {1, 32}: rows per sample
 };
 
 // blockDim.x = N / 4 threads (N <= 4096): each thread owns one float4 column group; 4 rows per iteration so
 // that 8 independent 16-byte loads per thread are in flight and one block reduction serves 4 rows.
-template <int MAXT>
+template <int MAXT, bool G16, bool U16, bool RES>
 __global__ void __launch_bounds__(MAXT)
 ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
   constexpr int RPI = 4;
@@ -61,34 +63,49 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
     sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
     sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
   }
+  // Register software pipeline: the loads of row group r+RPI are issued before the math and the two block
+  // reductions of group r, so ~80 KB per SM stays in flight instead of one exposed DRAM round trip per group.
+  // Prefetched rows stay in their storage format (bf16 pairs as uint2) to keep the register budget under 128.
+  using GRaw = typename std::conditional<G16, uint2, float4>::type;
+  using URaw = typename std::conditional<U16, uint2, float4>::type;
+  GRaw gn[RPI]; URaw un[RPI]; float4 dn[RES ? RPI : 1];
+  auto unpack = [](const auto& raw) -> float4 {
+    if constexpr (sizeof(raw) == 8) {
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      return raw;
+    }
+  };
+  auto load_group = [&](int r) {
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      const int row = r0 + r + q;
+      const size_t off = static_cast<size_t>(row) * N + c;
+      if (row < a.M) {
+        if constexpr (G16) gn[q] = *reinterpret_cast<const uint2*>(a.g16 + off);
+        else gn[q] = *reinterpret_cast<const float4*>(a.g + off);
+        if constexpr (U16) un[q] = *reinterpret_cast<const uint2*>(a.u16 + off);
+        else un[q] = *reinterpret_cast<const float4*>(a.u + off);
+        if constexpr (RES) dn[q] = *reinterpret_cast<const float4*>(a.dres + off);
+      } else {
+        gn[q] = GRaw{}; un[q] = URaw{};
+        if constexpr (RES) dn[q] = make_float4(0, 0, 0, 0);
+      }
+    }
+  };
+  load_group(0);
   for (int r = 0; r < 32; r += RPI) {
     const int buf = (r / RPI) & 1;
     float dxh[RPI][4], xh[RPI][4], rstd[RPI], part[2 * RPI];
-    float4 g4[RPI], u4[RPI];
+    float4 g4[RPI], u4[RPI], d4c[RES ? RPI : 1];
 #pragma unroll
-    for (int q = 0; q < RPI; ++q) {   // issue all loads first
-      const int row = r0 + r + q;
-      if (row < a.M) {
-        if (a.g16) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(a.g16 + static_cast<size_t>(row) * N + c);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-          g4[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          g4[q] = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * N + c);
-        }
-        if (a.u16) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(a.u16 + static_cast<size_t>(row) * N + c);
-          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-          u4[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          u4[q] = *reinterpret_cast<const float4*>(a.u + static_cast<size_t>(row) * N + c);
-        }
-      } else {
-        g4[q] = make_float4(0, 0, 0, 0); u4[q] = make_float4(0, 0, 0, 0);
-      }
+    for (int q = 0; q < RPI; ++q) {
+      g4[q] = unpack(gn[q]); u4[q] = unpack(un[q]);
+      if constexpr (RES) d4c[q] = dn[q];
     }
+    if (r + RPI < 32) load_group(r + RPI);   // dres may alias dx32: rows r+RPI.. are not written before this read
 #pragma unroll
     for (int q = 0; q < RPI; ++q) {
       const int row = r0 + r + q;
@@ -158,10 +175,7 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
         float dx[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) dx[i] = rstd[q] * (dxh[q][i] - m1 - xh[q][i] * m2);
-        if (a.dres) {
-          const float4 d4 = *reinterpret_cast<const float4*>(a.dres + static_cast<size_t>(row) * N + c);
-          dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
-        }
+        if constexpr (RES) { dx[0] += d4c[q].x; dx[1] += d4c[q].y; dx[2] += d4c[q].z; dx[3] += d4c[q].w; }
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc_bias[i] += dx[i];
         if (a.dx32) *reinterpret_cast<float4*>(a.dx32 + static_cast<size_t>(row) * N + c) = make_float4(dx[0], dx[1], dx[2], dx[3]);
@@ -192,10 +206,209 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path of the same backward for the sequence model (32 rows per sample, all rows valid, bf16 incoming
+// gradient): 16 rows per CTA, two CTAs resident per SM (<= 64 registers), two rows per iteration.  The FiLM pair is
+// constant over the CTA, so per column only A1 = sum(dact) and A2 = sum(dact * xhat) are accumulated:
+//   dbeta = sc A1, dgamma = sc A2, dshift = A1, dscale = gamma A2 + beta A1.
+// Row reductions: 4 values per thread -> 6-shuffle multi-value butterfly -> [value][warp] smem -> one
+// __syncthreads -> every warp folds the 16 partials itself (no second barrier; smem is double buffered).
+// dss must be zero-initialised by the caller: the two CTAs of a sample add into it.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 unpack_bf16x4(const uint2 raw) {
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <bool U16, bool RES, bool FILM>
+__global__ void __launch_bounds__(512, 2)
+ln_film_bwd_fast_kernel(const LnFilmBwdArgs a) {
+  constexpr int RPB = 16;
+  __shared__ float red[2][4][16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int r0 = blockIdx.x * RPB;
+  const int N = a.N;
+  const int c = tid * 4;
+  const float inv_n = 1.0f / static_cast<float>(N);
+  float A[4], Bc[4], A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0}, accb[4] = {0, 0, 0, 0};
+  {
+    const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + c);
+    A[0] = g4.x; A[1] = g4.y; A[2] = g4.z; A[3] = g4.w;
+    if constexpr (FILM) {
+      const float4 b4 = *reinterpret_cast<const float4*>(a.beta + c);
+      const float* sp = a.ss + static_cast<size_t>(r0 / 32) * 2 * N;
+      const float4 s4 = *reinterpret_cast<const float4*>(sp + c);
+      const float4 h4 = *reinterpret_cast<const float4*>(sp + N + c);
+      Bc[0] = fmaf(b4.x, s4.x, h4.x); Bc[1] = fmaf(b4.y, s4.y, h4.y);
+      Bc[2] = fmaf(b4.z, s4.z, h4.z); Bc[3] = fmaf(b4.w, s4.w, h4.w);
+      A[0] *= s4.x; A[1] *= s4.y; A[2] *= s4.z; A[3] *= s4.w;     // A = gamma * scale
+    } else {
+      Bc[0] = Bc[1] = Bc[2] = Bc[3] = 0.f;
+    }
+  }
+  const bool lo16 = (lane & 16) == 0, lo8 = (lane & 8) == 0;
+  for (int r = 0; r < RPB; r += 2) {
+    const int buf = (r >> 1) & 1;
+    const size_t off0 = static_cast<size_t>(r0 + r) * N + c, off1 = off0 + N;
+    const uint2 graw0 = *reinterpret_cast<const uint2*>(a.g16 + off0);
+    const uint2 graw1 = *reinterpret_cast<const uint2*>(a.g16 + off1);
+    float4 u0, u1;
+    if constexpr (U16) {
+      u0 = unpack_bf16x4(*reinterpret_cast<const uint2*>(a.u16 + off0));
+      u1 = unpack_bf16x4(*reinterpret_cast<const uint2*>(a.u16 + off1));
+    } else {
+      u0 = *reinterpret_cast<const float4*>(a.u + off0);
+      u1 = *reinterpret_cast<const float4*>(a.u + off1);
+    }
+    const float4 st = *reinterpret_cast<const float4*>(a.stats + 2 * static_cast<size_t>(r0 + r));  // (s1, s2) x 2 rows
+    const float mean0 = st.x * inv_n, mean1 = st.z * inv_n;
+    const float rstd0 = rsqrtf(st.y * inv_n - mean0 * mean0 + 1e-6f);
+    const float rstd1 = rsqrtf(st.w * inv_n - mean1 * mean1 + 1e-6f);
+    const float4 g0 = unpack_bf16x4(graw0), g1 = unpack_bf16x4(graw1);
+    float x[2][4], d[2][4];
+    {
+      const float uu0[4] = {u0.x, u0.y, u0.z, u0.w}, uu1[4] = {u1.x, u1.y, u1.z, u1.w};
+      const float gg0[4] = {g0.x, g0.y, g0.z, g0.w}, gg1[4] = {g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[0][i] = (uu0[i] - mean0) * rstd0;
+        x[1][i] = (uu1[i] - mean1) * rstd1;
+        float da0 = gg0[i], da1 = gg1[i];
+        if constexpr (FILM) {
+          da0 *= swish_grad(fmaf(x[0][i], A[i], Bc[i]));
+          da1 *= swish_grad(fmaf(x[1][i], A[i], Bc[i]));
+        }
+        A1[i] += da0 + da1;
+        A2[i] = fmaf(da0, x[0][i], fmaf(da1, x[1][i], A2[i]));
+        d[0][i] = da0 * A[i];
+        d[1][i] = da1 * A[i];
+      }
+    }
+    float p0 = (d[0][0] + d[0][1]) + (d[0][2] + d[0][3]);
+    float p1 = fmaf(d[0][0], x[0][0], fmaf(d[0][1], x[0][1], fmaf(d[0][2], x[0][2], d[0][3] * x[0][3])));
+    float p2 = (d[1][0] + d[1][1]) + (d[1][2] + d[1][3]);
+    float p3 = fmaf(d[1][0], x[1][0], fmaf(d[1][1], x[1][1], fmaf(d[1][2], x[1][2], d[1][3] * x[1][3])));
+    {  // 4 values x 32 lanes -> lane (j * 8) holds the warp total of value j
+      const float k0 = lo16 ? p0 : p2, s0 = lo16 ? p2 : p0;
+      const float k1 = lo16 ? p1 : p3, s1 = lo16 ? p3 : p1;
+      const float q0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+      const float q1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+      const float kk = lo8 ? q0 : q1, ss = lo8 ? q1 : q0;
+      float v = kk + __shfl_xor_sync(0xffffffffu, ss, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if ((lane & 7) == 0) red[buf][lane >> 3][warp] = v;   // value index = (bit4, bit3) of the lane
+    }
+    __syncthreads();
+    float m[4];
+    {
+      const int w = lane & 15;
+      float v0 = (w < nwarps) ? red[buf][lane >> 4][w] : 0.f;        // values 0 / 1
+      float v1 = (w < nwarps) ? red[buf][2 + (lane >> 4)][w] : 0.f;  // values 2 / 3
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      m[0] = __shfl_sync(0xffffffffu, v0, 0) * inv_n;
+      m[1] = __shfl_sync(0xffffffffu, v0, 16) * inv_n;
+      m[2] = __shfl_sync(0xffffffffu, v1, 0) * inv_n;
+      m[3] = __shfl_sync(0xffffffffu, v1, 16) * inv_n;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const size_t off = q ? off1 : off0;
+      const float rs = q ? rstd1 : rstd0;
+      float dx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dx[i] = rs * (d[q][i] - m[2 * q] - x[q][i] * m[2 * q + 1]);
+      if constexpr (RES) {
+        const float4 d4 = *reinterpret_cast<const float4*>(a.dres + off);
+        dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accb[i] += dx[i];
+      if (a.dx32) *reinterpret_cast<float4*>(a.dx32 + off) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      if (a.dx16) {
+        __nv_bfloat162 q0 = __floats2bfloat162_rn(dx[0], dx[1]);
+        __nv_bfloat162 q1 = __floats2bfloat162_rn(dx[2], dx[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&q0);
+        pk.y = *reinterpret_cast<uint32_t*>(&q1);
+        *reinterpret_cast<uint2*>(a.dx16 + off) = pk;
+      }
+    }
+  }
+  // epilogue: column gradients (A currently holds gamma * scale)
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, gam[4], bet[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + c);
+    gam[0] = g4.x; gam[1] = g4.y; gam[2] = g4.z; gam[3] = g4.w;
+    if constexpr (FILM) {
+      const float4 b4 = *reinterpret_cast<const float4*>(a.beta + c);
+      const float4 s4 = *reinterpret_cast<const float4*>(a.ss + static_cast<size_t>(r0 / 32) * 2 * N + c);
+      bet[0] = b4.x; bet[1] = b4.y; bet[2] = b4.z; bet[3] = b4.w;
+      sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(a.dgamma + c + i, sc[i] * A2[i]);
+    atomicAdd(a.dbeta + c + i, sc[i] * A1[i]);
+    if (a.dbias) atomicAdd(a.dbias + c + i, accb[i]);
+  }
+  if constexpr (FILM) {
+    if (a.dss) {
+      float* dp = a.dss + static_cast<size_t>(r0 / 32) * 2 * N;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(dp + c + i, fmaf(gam[i], A2[i], bet[i] * A1[i]));
+        atomicAdd(dp + N + c + i, A1[i]);
+      }
+    }
+  }
+}
+
 inline void launch_ln_film_act_bwd(const LnFilmBwdArgs& a, cudaStream_t st) {
+  const int threads = a.N / 4;
+  const bool film = a.ss != nullptr;
+  if (a.S == 32 && a.g16 && !a.g && threads <= 512 && threads % 32 == 0 && a.M % 32 == 0 &&
+      ((film && a.act == 2) || (!film && a.act == 0))) {
+    const int fb = a.M / 16;
+    const int key = (a.u16 ? 4 : 0) | (a.dres ? 2 : 0) | (film ? 1 : 0);
+    switch (key) {
+      case 0: ln_film_bwd_fast_kernel<false, false, false><<<fb, threads, 0, st>>>(a); break;
+      case 1: ln_film_bwd_fast_kernel<false, false, true><<<fb, threads, 0, st>>>(a); break;
+      case 2: ln_film_bwd_fast_kernel<false, true, false><<<fb, threads, 0, st>>>(a); break;
+      case 3: ln_film_bwd_fast_kernel<false, true, true><<<fb, threads, 0, st>>>(a); break;
+      case 4: ln_film_bwd_fast_kernel<true, false, false><<<fb, threads, 0, st>>>(a); break;
+      case 5: ln_film_bwd_fast_kernel<true, false, true><<<fb, threads, 0, st>>>(a); break;
+      case 6: ln_film_bwd_fast_kernel<true, true, false><<<fb, threads, 0, st>>>(a); break;
+      default: ln_film_bwd_fast_kernel<true, true, true><<<fb, threads, 0, st>>>(a); break;
+    }
+    return;
+  }
   const int blocks = (a.M + 31) / 32;
-  if (a.N / 4 <= 512) ln_film_act_bwd_kernel<512><<<blocks, a.N / 4, 0, st>>>(a);
-  else ln_film_act_bwd_kernel<1024><<<blocks, a.N / 4, 0, st>>>(a);
+  auto go = [&](auto g16, auto u16, auto res) {
+    constexpr bool G = decltype(g16)::value, U = decltype(u16)::value, R = decltype(res)::value;
+    if (threads <= 512) ln_film_act_bwd_kernel<512, G, U, R><<<blocks, threads, 0, st>>>(a);
+    else ln_film_act_bwd_kernel<1024, G, U, R><<<blocks, threads, 0, st>>>(a);
+  };
+  using T = std::true_type; using F = std::false_type;
+  const int key = (a.g16 ? 4 : 0) | (a.u16 ? 2 : 0) | (a.dres ? 1 : 0);
+  switch (key) {
+    case 0: go(F{}, F{}, F{}); break;
+    case 1: go(F{}, F{}, T{}); break;
+    case 2: go(F{}, T{}, F{}); break;
+    case 3: go(F{}, T{}, T{}); break;
+    case 4: go(T{}, F{}, F{}); break;
+    case 5: go(T{}, F{}, T{}); break;
+    case 6: go(T{}, T{}, F{}); break;
+    default: go(T{}, T{}, T{}); break;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -328,7 +541,7 @@ template <int DH>
 __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                      const float* __restrict__ dO, __nv_bfloat16* __restrict__ dqkv16,
                                      float* __restrict__ dbias, int H) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* sQ = sm;                  // [32][128] scaled q
   float* sK = sQ + 32 * 128;
   float* sV = sK + 32 * 128;
@@ -361,14 +574,20 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
   }
   float dO_i[DH];
 #pragma unroll
-  for (int d = 0; d < DH; ++d) dO_i[d] = sD[lane * 128 + hc + d];
+  for (int d = 0; d < DH; d += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(&sD[lane * 128 + hc + d]);
+    dO_i[d] = t.x; dO_i[d + 1] = t.y; dO_i[d + 2] = t.z; dO_i[d + 3] = t.w;
+  }
   float dS[32];
   float rs = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) s = fmaf(dO_i[d], sV[j * 128 + hc + d], s);
+    for (int d = 0; d < DH; d += 4) {   // broadcast 16-byte reads
+      const float4 t = *reinterpret_cast<const float4*>(&sV[j * 128 + hc + d]);
+      s = fmaf(dO_i[d], t.x, fmaf(dO_i[d + 1], t.y, fmaf(dO_i[d + 2], t.z, fmaf(dO_i[d + 3], t.w, s))));
+    }
     dS[j] = s;
     rs = fmaf(s, P[j], rs);
   }
@@ -379,10 +598,15 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
   float dv[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) dv[d] = 0.f;
+#pragma unroll 4
   for (int i = 0; i < 32; ++i) {
     const float p = my[i * 33 + lane];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) dv[d] = fmaf(p, sD[i * 128 + hc + d], dv[d]);
+    for (int d = 0; d < DH; d += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(&sD[i * 128 + hc + d]);
+      dv[d] = fmaf(p, t.x, dv[d]); dv[d + 1] = fmaf(p, t.y, dv[d + 1]);
+      dv[d + 2] = fmaf(p, t.z, dv[d + 2]); dv[d + 3] = fmaf(p, t.w, dv[d + 3]);
+    }
   }
   __syncwarp();
   // dq_i = (sum_j dS[i][j] k_j) / sqrt(dh)   (lane = i)
@@ -393,7 +617,11 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
   for (int j = 0; j < 32; ++j) {
     my[lane * 33 + j] = dS[j];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) dq[d] = fmaf(dS[j], sK[j * 128 + hc + d], dq[d]);
+    for (int d = 0; d < DH; d += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(&sK[j * 128 + hc + d]);
+      dq[d] = fmaf(dS[j], t.x, dq[d]); dq[d + 1] = fmaf(dS[j], t.y, dq[d + 1]);
+      dq[d + 2] = fmaf(dS[j], t.z, dq[d + 2]); dq[d + 3] = fmaf(dS[j], t.w, dq[d + 3]);
+    }
   }
 #pragma unroll
   for (int d = 0; d < DH; ++d) dq[d] *= qs;
@@ -402,10 +630,15 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
   float dk[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) dk[d] = 0.f;
+#pragma unroll 4
   for (int i = 0; i < 32; ++i) {
     const float s = my[i * 33 + lane];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) dk[d] = fmaf(s, sQ[i * 128 + hc + d], dk[d]);
+    for (int d = 0; d < DH; d += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(&sQ[i * 128 + hc + d]);
+      dk[d] = fmaf(s, t.x, dk[d]); dk[d + 1] = fmaf(s, t.y, dk[d + 1]);
+      dk[d + 2] = fmaf(s, t.z, dk[d + 2]); dk[d + 3] = fmaf(s, t.w, dk[d + 3]);
+    }
   }
   __nv_bfloat16* orow = dqkv16 + (static_cast<size_t>(b) * 32 + lane) * 384;
 #pragma unroll
@@ -446,18 +679,52 @@ inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, co
 // ---------------------------------------------------------------------------------------------------
 // input projection backward: dW_in[c][o] += sum_m x[m][c] dh[m][o]
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// One CTA per 128 tokens; thread (o, half) accumulates 32 input channels of output column o per 64-channel
+// chunk, the x tile staged in shared memory (broadcast float4 reads), dh read once per chunk (coalesced).
+__global__ void __launch_bounds__(256)
 embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dh, float* __restrict__ dW, int M, int C) {
-  const int c = blockIdx.x, o = threadIdx.x;
-  const int per = (M + gridDim.y - 1) / gridDim.y;
-  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
-  float acc = 0.f;
-  for (int m = m0; m < m1; ++m) acc = fmaf(__ldg(x + static_cast<size_t>(m) * C + c), dh[static_cast<size_t>(m) * 128 + o], acc);
-  atomicAdd(dW + static_cast<size_t>(c) * 128 + o, acc);
+  constexpr int ROWS = 128;
+  __shared__ __align__(16) float xs[ROWS][64];
+  const int tid = threadIdx.x, o = tid & 127, half = tid >> 7;
+  const int m0 = blockIdx.x * ROWS;
+  const int rows = min(ROWS, M - m0);
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    for (int i = tid; i < ROWS * 64; i += 256) {
+      const int r = i >> 6, j = i & 63;
+      xs[r][j] = (r < rows && c0 + j < C) ? x[static_cast<size_t>(m0 + r) * C + c0 + j] : 0.f;
+    }
+    __syncthreads();
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int rb = 0; rb < rows; rb += 8) {
+      float d[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)   // 8 independent loads in flight per thread
+        d[q] = (rb + q < rows) ? dh[static_cast<size_t>(m0 + rb + q) * 128 + o] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4* xr = reinterpret_cast<const float4*>(&xs[rb + q][half * 32]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = xr[j];
+          acc[4 * j] = fmaf(v.x, d[q], acc[4 * j]);
+          acc[4 * j + 1] = fmaf(v.y, d[q], acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v.z, d[q], acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v.w, d[q], acc[4 * j + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int cc = c0 + half * 32 + j;
+      if (cc < C) atomicAdd(dW + static_cast<size_t>(cc) * 128 + o, acc[j]);
+    }
+    __syncthreads();
+  }
 }
 inline void launch_embed_bwd(const float* x, const float* dh, float* dW, int M, int C, cudaStream_t st) {
-  dim3 grid(C, 16);
-  embed_bwd_kernel<<<grid, 128, 0, st>>>(x, dh, dW, M, C);
+  embed_bwd_kernel<<<(M + 127) / 128, 256, 0, st>>>(x, dh, dW, M, C);
 }
 
 // small fp32 linear layers of the FiLM generator: weight gradient and input gradient (tiled SGEMM, kernels.cu)

@@ -222,6 +222,9 @@ int ensure_side_stream(smd_plan* p) {
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_film, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dss, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  SMD_CUDA(cudaStreamCreateWithFlags(&p->dw_stream, cudaStreamNonBlocking));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dw, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dwjoin, cudaEventDisableTiming));
   return SMD_OK;
 }
 
@@ -514,6 +517,9 @@ void smd_plan_destroy(smd_plan* plan) {
   if (plan->ev_film) cudaEventDestroy(plan->ev_film);
   if (plan->ev_dss) cudaEventDestroy(plan->ev_dss);
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  if (plan->ev_dw) cudaEventDestroy(plan->ev_dw);
+  if (plan->ev_dwjoin) cudaEventDestroy(plan->ev_dwjoin);
+  if (plan->dw_stream) cudaStreamDestroy(plan->dw_stream);
   if (plan->side_stream) cudaStreamDestroy(plan->side_stream);
   if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
   delete plan;

@@ -41,8 +41,13 @@ void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
   ts.off_g16b = add("t.g16b", M * Md * 2);
   ts.off_dh = add("t.dh", M * kEt * 4);
   ts.off_dh2 = add("t.dh2", M * kEt * 4);
-  ts.off_dh16 = add("t.dh16", M * kEt * 2);
-  ts.off_dqkv16 = add("t.dqkv16", M * 3 * kEt * 2);
+  for (int l = 0; l < ts.L; ++l) {
+    ts.off_dh16a.push_back(add(nm("dh16a", l), M * kEt * 2));
+    ts.off_dh16b.push_back(add(nm("dh16b", l), M * kEt * 2));
+    ts.off_dr16.push_back(add(nm("dr16_", l), M * Md * 2));
+    ts.off_dqkv16.push_back(add(nm("dqkv16_", l), M * 3 * kEt * 2));
+  }
+  ts.off_dh16_in = add("t.dh16_in", M * kEt * 2);
   ts.off_dqkv32 = add("t.dqkv32", M * 3 * kEt * 4);
   ts.off_dpred16 = add("t.dpred16", M * Cp * 2);
   ts.off_dpred32 = add("t.dpred32", M * c.channels * 4);

@@ -35,8 +35,13 @@ struct TrainState {
   size_t off_g32a = 0, off_g32b = 0;   // fp32 [Mp][Md] gradient ping-pong (tail) -- also used [Mp][128]-wide in the trunk
   size_t off_g16a = 0, off_g16b = 0;   // bf16 [Mp][Md]
   size_t off_dh = 0, off_dh2 = 0;      // fp32 [Mp][128]
-  size_t off_dh16 = 0;                 // bf16 [Mp][128]
-  size_t off_dqkv16 = 0;               // bf16 [Mp][384]
+  // per-layer bf16 gradient operands: the dW GEMMs that read them run on their own stream, so no buffer is
+  // rewritten within one backward pass
+  std::vector<size_t> off_dh16a;       // bf16 [Mp][128] x L: gradient entering layer l (from LN1 of l+1 / post-LN)
+  std::vector<size_t> off_dh16b;       // bf16 [Mp][128] x L: gradient at the attention output (from LN2)
+  std::vector<size_t> off_dr16;        // bf16 [Mp][Md]  x L: gradient at the FFN pre-activation
+  std::vector<size_t> off_dqkv16;      // bf16 [Mp][384] x L
+  size_t off_dh16_in = 0;              // bf16 [Mp][128]: LN1 output of layer 0 (unused operand)
   size_t off_dqkv32 = 0;               // fp32 [Mp][384]
   size_t off_dpred16 = 0;              // bf16 [Mp][Cp64]
   size_t off_dpred32 = 0;              // fp32 [Mp][C]
