@@ -36,6 +36,7 @@ struct LnFilmBwdArgs {
 template <int MAXT, bool G16, bool U16, bool RES>
 __global__ void __launch_bounds__(MAXT)
 ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
+  pdl_trigger();
   constexpr int RPI = 4;
   __shared__ float red[2][32][2 * RPI];
   __shared__ float tot[2][2 * RPI];
@@ -215,6 +216,15 @@ ln_film_act_bwd_kernel(const LnFilmBwdArgs a) {
 // __syncthreads -> every warp folds the 16 partials itself (no second barrier; smem is double buffered).
 // dss must be zero-initialised by the caller: the two CTAs of a sample add into it.
 // ---------------------------------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async_own(void* smem_dst, const void* gsrc) {   // per-thread LDGSTS, 8 or 16 bytes
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float4 unpack_bf16x4(const uint2 raw) {
   const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
   const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
@@ -224,8 +234,16 @@ __device__ __forceinline__ float4 unpack_bf16x4(const uint2 raw) {
 template <bool U16, bool RES, bool FILM>
 __global__ void __launch_bounds__(512, 2)
 ln_film_bwd_fast_kernel(const LnFilmBwdArgs a) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPB = 16;
+  constexpr int UB = U16 ? 8 : 16;                 // bytes of one thread's 4 columns of u
   __shared__ float red[2][4][16];
+  // Two-stage LDGSTS pipeline: every thread copies only its own 4 columns of the next two rows (g | u | dres)
+  // into shared memory and later reads the same bytes back, so cp.async.wait_group is the only hand-off needed.
+  extern __shared__ __align__(16) uint8_t stage_mem[];
+  const int T = blockDim.x;
+  const int stage_bytes = T * (16 + 2 * UB + (RES ? 32 : 0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;
   const int r0 = blockIdx.x * RPB;
@@ -249,20 +267,43 @@ ln_film_bwd_fast_kernel(const LnFilmBwdArgs a) {
     }
   }
   const bool lo16 = (lane & 16) == 0, lo8 = (lane & 8) == 0;
+  auto sg = [&](int stg, int q) { return stage_mem + stg * stage_bytes + (q * T + tid) * 8; };
+  auto su = [&](int stg, int q) { return stage_mem + stg * stage_bytes + 16 * T + (q * T + tid) * UB; };
+  auto sd = [&](int stg, int q) { return stage_mem + stg * stage_bytes + (16 + 2 * UB) * T + (q * T + tid) * 16; };
+  auto issue = [&](int r, int stg) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const size_t off = static_cast<size_t>(r0 + r + q) * N + c;
+      cp_async_own<8>(sg(stg, q), a.g16 + off);
+      if constexpr (U16) cp_async_own<8>(su(stg, q), a.u16 + off);
+      else cp_async_own<16>(su(stg, q), a.u + off);
+      if constexpr (RES) cp_async_own<16>(sd(stg, q), a.dres + off);
+    }
+    cp_async_commit();
+  };
+  issue(0, 0);
+  float4 st_next = *reinterpret_cast<const float4*>(a.stats + 2 * static_cast<size_t>(r0));
   for (int r = 0; r < RPB; r += 2) {
     const int buf = (r >> 1) & 1;
     const size_t off0 = static_cast<size_t>(r0 + r) * N + c, off1 = off0 + N;
-    const uint2 graw0 = *reinterpret_cast<const uint2*>(a.g16 + off0);
-    const uint2 graw1 = *reinterpret_cast<const uint2*>(a.g16 + off1);
+    const float4 st = st_next;                     // (s1, s2) x 2 rows
+    if (r + 2 < RPB) {
+      issue(r + 2, buf ^ 1);                       // dres may alias dx32: rows r+2.. are not written before this
+      st_next = *reinterpret_cast<const float4*>(a.stats + 2 * static_cast<size_t>(r0 + r + 2));
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    const uint2 graw0 = *reinterpret_cast<const uint2*>(sg(buf, 0));
+    const uint2 graw1 = *reinterpret_cast<const uint2*>(sg(buf, 1));
     float4 u0, u1;
     if constexpr (U16) {
-      u0 = unpack_bf16x4(*reinterpret_cast<const uint2*>(a.u16 + off0));
-      u1 = unpack_bf16x4(*reinterpret_cast<const uint2*>(a.u16 + off1));
+      u0 = unpack_bf16x4(*reinterpret_cast<const uint2*>(su(buf, 0)));
+      u1 = unpack_bf16x4(*reinterpret_cast<const uint2*>(su(buf, 1)));
     } else {
-      u0 = *reinterpret_cast<const float4*>(a.u + off0);
-      u1 = *reinterpret_cast<const float4*>(a.u + off1);
+      u0 = *reinterpret_cast<const float4*>(su(buf, 0));
+      u1 = *reinterpret_cast<const float4*>(su(buf, 1));
     }
-    const float4 st = *reinterpret_cast<const float4*>(a.stats + 2 * static_cast<size_t>(r0 + r));  // (s1, s2) x 2 rows
     const float mean0 = st.x * inv_n, mean1 = st.z * inv_n;
     const float rstd0 = rsqrtf(st.y * inv_n - mean0 * mean0 + 1e-6f);
     const float rstd1 = rsqrtf(st.w * inv_n - mean1 * mean1 + 1e-6f);
@@ -326,7 +367,7 @@ ln_film_bwd_fast_kernel(const LnFilmBwdArgs a) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) dx[i] = rs * (d[q][i] - m[2 * q] - x[q][i] * m[2 * q + 1]);
       if constexpr (RES) {
-        const float4 d4 = *reinterpret_cast<const float4*>(a.dres + off);
+        const float4 d4 = *reinterpret_cast<const float4*>(sd(buf, q));
         dx[0] += d4.x; dx[1] += d4.y; dx[2] += d4.z; dx[3] += d4.w;
       }
 #pragma unroll
@@ -379,16 +420,23 @@ inline void launch_ln_film_act_bwd(const LnFilmBwdArgs& a, cudaStream_t st) {
       ((film && a.act == 2) || (!film && a.act == 0))) {
     const int fb = a.M / 16;
     const int key = (a.u16 ? 4 : 0) | (a.dres ? 2 : 0) | (film ? 1 : 0);
+    const int smem = 2 * threads * (16 + 2 * (a.u16 ? 8 : 16) + (a.dres ? 32 : 0));   // <= 80 KB: two CTAs per SM
+#define SMD_LNB_FAST(U, R, F)                                                                               \
+  {                                                                                                          \
+    cudaFuncSetAttribute(ln_film_bwd_fast_kernel<U, R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    launch_pdl(ln_film_bwd_fast_kernel<U, R, F>, dim3(fb), dim3(threads), smem, st, a);                                          \
+  }
     switch (key) {
-      case 0: ln_film_bwd_fast_kernel<false, false, false><<<fb, threads, 0, st>>>(a); break;
-      case 1: ln_film_bwd_fast_kernel<false, false, true><<<fb, threads, 0, st>>>(a); break;
-      case 2: ln_film_bwd_fast_kernel<false, true, false><<<fb, threads, 0, st>>>(a); break;
-      case 3: ln_film_bwd_fast_kernel<false, true, true><<<fb, threads, 0, st>>>(a); break;
-      case 4: ln_film_bwd_fast_kernel<true, false, false><<<fb, threads, 0, st>>>(a); break;
-      case 5: ln_film_bwd_fast_kernel<true, false, true><<<fb, threads, 0, st>>>(a); break;
-      case 6: ln_film_bwd_fast_kernel<true, true, false><<<fb, threads, 0, st>>>(a); break;
-      default: ln_film_bwd_fast_kernel<true, true, true><<<fb, threads, 0, st>>>(a); break;
+      case 0: SMD_LNB_FAST(false, false, false) break;
+      case 1: SMD_LNB_FAST(false, false, true) break;
+      case 2: SMD_LNB_FAST(false, true, false) break;
+      case 3: SMD_LNB_FAST(false, true, true) break;
+      case 4: SMD_LNB_FAST(true, false, false) break;
+      case 5: SMD_LNB_FAST(true, false, true) break;
+      case 6: SMD_LNB_FAST(true, true, false) break;
+      default: SMD_LNB_FAST(true, true, true) break;
     }
+#undef SMD_LNB_FAST
     return;
   }
   const int blocks = (a.M + 31) / 32;
@@ -427,6 +475,8 @@ struct Ln128BwdArgs {
 };
 
 __global__ void __launch_bounds__(256) ln128_bwd_kernel(const Ln128BwdArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[3][8][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
@@ -489,7 +539,7 @@ __global__ void __launch_bounds__(256) ln128_bwd_kernel(const Ln128BwdArgs a) {
 inline void launch_ln128_bwd(const Ln128BwdArgs& a, cudaStream_t st) {
   int blocks = (a.M + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;
-  ln128_bwd_kernel<<<blocks, 256, 0, st>>>(a);
+  launch_pdl(ln128_bwd_kernel, dim3(blocks), dim3(256), 0, st, a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -498,6 +548,7 @@ inline void launch_ln128_bwd(const Ln128BwdArgs& a, cudaStream_t st) {
 // fp32: one column per thread; bf16: two adjacent columns per thread (4-byte loads); 64 rows per block
 template <typename T>
 __global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int M, int N) {
+  pdl_trigger();
   const int m0 = blockIdx.y * 64, m1 = min(M, m0 + 64);
   if constexpr (sizeof(T) == 2) {
     const int n = (blockIdx.x * 128 + threadIdx.x) * 2;
@@ -541,30 +592,37 @@ template <int DH>
 __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                      const float* __restrict__ dO, __nv_bfloat16* __restrict__ dqkv16,
                                      float* __restrict__ dbias, int H) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
-  float* sQ = sm;                  // [32][128] scaled q
-  float* sK = sQ + 32 * 128;
-  float* sV = sK + 32 * 128;
-  float* sD = sV + 32 * 128;       // dO
-  float* scr = sD + 32 * 128;      // [H][32][33]
+  // a CTA owns HPB = blockDim.x / 32 heads of one sample: W = HPB * DH columns of q, k, v and dO
+  const int HPB = blockDim.x >> 5, W = HPB * DH, W4 = W / 4;
+  const int hb = blockIdx.y * HPB;   // first head of this CTA
+  float* sQ = sm;                  // [32][W] scaled q
+  float* sK = sQ + 32 * W;
+  float* sV = sK + 32 * W;
+  float* sD = sV + 32 * W;         // dO
+  float* scr = sD + 32 * W;        // [HPB][32][33]
   const int b = blockIdx.x, tid = threadIdx.x;
   const float qs = rsqrtf(static_cast<float>(DH));
   const float* base = qkv + static_cast<size_t>(b) * 32 * 384;
   const float* dob = dO + static_cast<size_t>(b) * 32 * 128;
-  for (int i = tid; i < 32 * 32; i += blockDim.x) {
-    const int row = i / 32, c4 = (i % 32) * 4;
-    float4 q4 = *reinterpret_cast<const float4*>(base + row * 384 + c4);
+  for (int i = tid; i < 32 * W4; i += blockDim.x) {
+    const int row = i / W4, c4 = (i % W4) * 4, gc = hb * DH + c4;
+    float4 q4 = *reinterpret_cast<const float4*>(base + row * 384 + gc);
     q4.x *= qs; q4.y *= qs; q4.z *= qs; q4.w *= qs;
-    *reinterpret_cast<float4*>(&sQ[row * 128 + c4]) = q4;
-    *reinterpret_cast<float4*>(&sK[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 128 + c4);
-    *reinterpret_cast<float4*>(&sV[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 256 + c4);
-    *reinterpret_cast<float4*>(&sD[row * 128 + c4]) = *reinterpret_cast<const float4*>(dob + row * 128 + c4);
+    *reinterpret_cast<float4*>(&sQ[row * W + c4]) = q4;
+    *reinterpret_cast<float4*>(&sK[row * W + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 128 + gc);
+    *reinterpret_cast<float4*>(&sV[row * W + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 256 + gc);
+    *reinterpret_cast<float4*>(&sD[row * W + c4]) = *reinterpret_cast<const float4*>(dob + row * 128 + gc);
   }
   __syncthreads();
-  const int h = tid >> 5, lane = tid & 31;
+  const int hl = tid >> 5, lane = tid & 31;
+  const int h = hb + hl;
   if (h >= H) return;
-  float* my = scr + h * 32 * 33;
-  const int hc = h * DH;
+  float* my = scr + hl * 32 * 33;
+  const int hc = hl * DH;      // column offset inside the staged tiles
+  const int gh = h * DH;       // column offset in global memory
   float P[32];
   const float* pr = probs + ((static_cast<size_t>(b) * H + h) * 32 + lane) * 32;
 #pragma unroll
@@ -575,7 +633,7 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
   float dO_i[DH];
 #pragma unroll
   for (int d = 0; d < DH; d += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(&sD[lane * 128 + hc + d]);
+    const float4 t = *reinterpret_cast<const float4*>(&sD[lane * W + hc + d]);
     dO_i[d] = t.x; dO_i[d + 1] = t.y; dO_i[d + 2] = t.z; dO_i[d + 3] = t.w;
   }
   float dS[32];
@@ -585,7 +643,7 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < DH; d += 4) {   // broadcast 16-byte reads
-      const float4 t = *reinterpret_cast<const float4*>(&sV[j * 128 + hc + d]);
+      const float4 t = *reinterpret_cast<const float4*>(&sV[j * W + hc + d]);
       s = fmaf(dO_i[d], t.x, fmaf(dO_i[d + 1], t.y, fmaf(dO_i[d + 2], t.z, fmaf(dO_i[d + 3], t.w, s))));
     }
     dS[j] = s;
@@ -603,7 +661,7 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
     const float p = my[i * 33 + lane];
 #pragma unroll
     for (int d = 0; d < DH; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(&sD[i * 128 + hc + d]);
+      const float4 t = *reinterpret_cast<const float4*>(&sD[i * W + hc + d]);
       dv[d] = fmaf(p, t.x, dv[d]); dv[d + 1] = fmaf(p, t.y, dv[d + 1]);
       dv[d + 2] = fmaf(p, t.z, dv[d + 2]); dv[d + 3] = fmaf(p, t.w, dv[d + 3]);
     }
@@ -618,7 +676,7 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
     my[lane * 33 + j] = dS[j];
 #pragma unroll
     for (int d = 0; d < DH; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(&sK[j * 128 + hc + d]);
+      const float4 t = *reinterpret_cast<const float4*>(&sK[j * W + hc + d]);
       dq[d] = fmaf(dS[j], t.x, dq[d]); dq[d + 1] = fmaf(dS[j], t.y, dq[d + 1]);
       dq[d + 2] = fmaf(dS[j], t.z, dq[d + 2]); dq[d + 3] = fmaf(dS[j], t.w, dq[d + 3]);
     }
@@ -635,7 +693,7 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
     const float s = my[i * 33 + lane];
 #pragma unroll
     for (int d = 0; d < DH; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(&sQ[i * 128 + hc + d]);
+      const float4 t = *reinterpret_cast<const float4*>(&sQ[i * W + hc + d]);
       dk[d] = fmaf(s, t.x, dk[d]); dk[d + 1] = fmaf(s, t.y, dk[d + 1]);
       dk[d + 2] = fmaf(s, t.z, dk[d + 2]); dk[d + 3] = fmaf(s, t.w, dk[d + 3]);
     }
@@ -643,30 +701,33 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
   __nv_bfloat16* orow = dqkv16 + (static_cast<size_t>(b) * 32 + lane) * 384;
 #pragma unroll
   for (int d = 0; d < DH; d += 2) {
-    *reinterpret_cast<__nv_bfloat162*>(orow + hc + d) = __floats2bfloat162_rn(dq[d], dq[d + 1]);
-    *reinterpret_cast<__nv_bfloat162*>(orow + 128 + hc + d) = __floats2bfloat162_rn(dk[d], dk[d + 1]);
-    *reinterpret_cast<__nv_bfloat162*>(orow + 256 + hc + d) = __floats2bfloat162_rn(dv[d], dv[d + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(orow + gh + d) = __floats2bfloat162_rn(dq[d], dq[d + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(orow + 128 + gh + d) = __floats2bfloat162_rn(dk[d], dk[d + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(orow + 256 + gh + d) = __floats2bfloat162_rn(dv[d], dv[d + 1]);
   }
 #pragma unroll
   for (int d = 0; d < DH; ++d) {
     const float a = warp_sum(dq[d]), bsum = warp_sum(dk[d]), c = warp_sum(dv[d]);
     if (lane == 0) {
-      atomicAdd(dbias + hc + d, a);
-      atomicAdd(dbias + 128 + hc + d, bsum);
-      atomicAdd(dbias + 256 + hc + d, c);
+      atomicAdd(dbias + gh + d, a);
+      atomicAdd(dbias + 128 + gh + d, bsum);
+      atomicAdd(dbias + 256 + gh + d, c);
     }
   }
 }
 inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, const float* dO, __nv_bfloat16* dqkv16,
                                         float* dbias, int B, int H, cudaStream_t st) {
   const int dh = 128 / H;
-  const size_t smem = (4 * 32 * 128 + static_cast<size_t>(H) * 32 * 33) * sizeof(float);
+  int hpb = H;                       // heads per CTA: <= 4 so that several CTAs are resident per SM
+  while (hpb > 4 && hpb % 2 == 0) hpb /= 2;
+  const size_t smem = (4 * 32 * static_cast<size_t>(hpb) * dh + static_cast<size_t>(hpb) * 32 * 33) * sizeof(float);
+  const dim3 grid(B, H / hpb);
 #define SMD_ATT_BWD(DHV)                                                                                       \
   {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          static_cast<int>(smem));                                              \
     if (e != cudaSuccess) return e;                                                                            \
-    attention_bwd_kernel<DHV><<<B, H * 32, smem, st>>>(qkv, probs, dO, dqkv16, dbias, H);                       \
+    launch_pdl(attention_bwd_kernel<DHV>, dim3(grid), dim3(hpb * 32), smem, st, qkv, probs, dO, dqkv16, dbias, H);                       \
   }
   if (dh == 16) SMD_ATT_BWD(16)
   else if (dh == 8) SMD_ATT_BWD(8)
@@ -683,6 +744,8 @@ inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, co
 // chunk, the x tile staged in shared memory (broadcast float4 reads), dh read once per chunk (coalesced).
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dh, float* __restrict__ dW, int M, int C) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int ROWS = 128;
   __shared__ __align__(16) float xs[ROWS][64];
   const int tid = threadIdx.x, o = tid & 127, half = tid >> 7;
@@ -724,7 +787,7 @@ embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dh, floa
   }
 }
 inline void launch_embed_bwd(const float* x, const float* dh, float* dW, int M, int C, cudaStream_t st) {
-  embed_bwd_kernel<<<(M + 127) / 128, 256, 0, st>>>(x, dh, dW, M, C);
+  launch_pdl(embed_bwd_kernel, dim3((M + 127) / 128), dim3(256), 0, st, x, dh, dW, M, C);
 }
 
 // small fp32 linear layers of the FiLM generator: weight gradient and input gradient (tiled SGEMM, kernels.cu)
@@ -743,6 +806,7 @@ __global__ void __launch_bounds__(256)
 ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
                      float* __restrict__ loss_sum, float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16,
                      float gscale, int S, int C, int Cp) {
+  pdl_trigger();
   const int b = blockIdx.x;
   const int per = S * C;
   const size_t base = static_cast<size_t>(b) * per;

@@ -1,12 +1,14 @@
 // Host side of the tcgen05 GEMM: tensor-map construction (cuTensorMapEncodeTiled through the runtime's
 // driver-entry-point lookup, so libsmd.so has no link-time dependency on libcuda) and the launcher.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 #include <atomic>
 #include <string>
 #include "gemm_tcgen05.cuh"
+#include "pdl_launch.cuh"
 
 namespace smd {
 
@@ -137,13 +139,15 @@ inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue&
   cfg.blockDim = dim3(SM::kThreads);
   cfg.dynamicSmemBytes = SM::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kCG;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCG, kF, kEW>, op.tmA, op.tmB, sh, ep);
 }

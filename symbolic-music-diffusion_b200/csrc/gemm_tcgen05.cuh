@@ -140,6 +140,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_groups = gridDim.x / kCG;
   const int b_rows = BN / kCG;  // B rows staged by this CTA
 
+  pdl_trigger();   // the next kernel of the stream may start its own prologue now
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -163,6 +164,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data: under
+  // programmatic dependent launch it overlaps the tail of the previous kernel.  From here on operands are read.
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================

@@ -9,6 +9,8 @@ namespace smd {
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ eps,
                                 const float* __restrict__ ua, float* __restrict__ xt, float* __restrict__ cond, int B,
                                 int per_sample) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = static_cast<size_t>(B) * per_sample;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -24,7 +26,7 @@ void launch_q_sample(const float* x0, const float* eps, const float* used_alpha,
   const size_t total = static_cast<size_t>(B) * per_sample;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  q_sample_kernel<<<blocks, 256, 0, st>>>(x0, eps, used_alpha, xt, cond, B, per_sample);
+  launch_pdl(q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -34,6 +36,8 @@ __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
              const float* __restrict__ posenc, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
              float* __restrict__ h, __nv_bfloat16* __restrict__ a, int M, int C, int S) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -73,7 +77,7 @@ embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const flo
 void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
                   const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st) {
   const int blocks = (M + 7) / 8;
-  embed_kernel<<<blocks, 256, 0, st>>>(x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S);
+  launch_pdl(embed_kernel, dim3(blocks), dim3(256), 0, st, x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -82,18 +86,25 @@ void launch_embed(const float* x, const float* W_in, const float* b_in, const fl
 template <int DH>
 __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
                                  float* __restrict__ probs, int B, int H) {
-  __shared__ float sK[32 * 128];
-  __shared__ float sV[32 * 128];
+  pdl_trigger();
+  pdl_wait();
+  // a CTA owns HPB = blockDim.x / 32 heads of one sample (W = HPB * DH columns of k and v): small CTAs, several
+  // resident per SM, so one CTA's global->shared fill overlaps another's math
+  __shared__ __align__(16) float sK[32 * 128];
+  __shared__ __align__(16) float sV[32 * 128];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
+  const int HPB = blockDim.x >> 5, W = HPB * DH, W4 = W / 4;
+  const int hb = blockIdx.y * HPB;
   const float* base = qkv + static_cast<size_t>(b) * 32 * 384;
-  for (int i = tid; i < 32 * 128 / 4; i += blockDim.x) {
-    const int row = i / 32, c4 = (i % 32) * 4;
-    *reinterpret_cast<float4*>(&sK[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 128 + c4);
-    *reinterpret_cast<float4*>(&sV[row * 128 + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 256 + c4);
+  for (int i = tid; i < 32 * W4; i += blockDim.x) {
+    const int row = i / W4, c4 = (i % W4) * 4, gc = hb * DH + c4;
+    *reinterpret_cast<float4*>(&sK[row * W + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 128 + gc);
+    *reinterpret_cast<float4*>(&sV[row * W + c4]) = *reinterpret_cast<const float4*>(base + row * 384 + 256 + gc);
   }
   __syncthreads();
-  const int h = tid >> 5, lane = tid & 31;
+  const int hl = tid >> 5, lane = tid & 31;
+  const int h = hb + hl;
   if (h >= H) return;
   float q[DH];
   const float qs = rsqrtf(static_cast<float>(DH));
@@ -105,7 +116,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float s = 0.f;
-    const float4* kr = reinterpret_cast<const float4*>(&sK[j * 128 + h * DH]);
+    const float4* kr = reinterpret_cast<const float4*>(&sK[j * W + hl * DH]);
 #pragma unroll
     for (int d4 = 0; d4 < DH / 4; ++d4) {
       const float4 k4 = kr[d4];   // one 16-byte broadcast read per 4 MACs
@@ -126,7 +137,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
   for (int j = 0; j < 32; ++j) {
     const float p = sc[j] * inv;
     sc[j] = p;
-    const float4* vr = reinterpret_cast<const float4*>(&sV[j * 128 + h * DH]);
+    const float4* vr = reinterpret_cast<const float4*>(&sV[j * W + hl * DH]);
 #pragma unroll
     for (int d4 = 0; d4 < DH / 4; ++d4) {
       const float4 v4 = vr[d4];
@@ -147,10 +158,14 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
 }
 void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st) {
   const int dh = 128 / H;
-  if (dh == 16) attention_kernel<16><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
-  else if (dh == 8) attention_kernel<8><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
-  else if (dh == 32) attention_kernel<32><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
-  else if (dh == 4) attention_kernel<4><<<B, H * 32, 0, st>>>(qkv, o, probs_or_null, B, H);
+  int hpb = H;
+  while (hpb > 4 && hpb % 2 == 0) hpb /= 2;
+  const dim3 grid(B, H / hpb);
+  const int threads = hpb * 32;
+  if (dh == 16) launch_pdl(attention_kernel<16>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  else if (dh == 8) launch_pdl(attention_kernel<8>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  else if (dh == 32) launch_pdl(attention_kernel<32>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  else if (dh == 4) launch_pdl(attention_kernel<4>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -192,6 +207,8 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
                    int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
                    const int* __restrict__ film_row_dev) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t lsm[];
   constexpr int RPG = 4;                                   // rows per copy group
   constexpr int ES = IN_BF16 ? 2 : 4;
@@ -289,7 +306,7 @@ void launch_ln_film_act(const float* u, const float* stats, const float* g, cons
       cudaFuncSetAttribute(ln_film_act_kernel<MAXT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 * 4 + 64); \
       attr = true;                                                                                               \
     }                                                                                                            \
-    ln_film_act_kernel<MAXT, BF><<<blocks, threads, smem, st>>>(in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
+    launch_pdl(ln_film_act_kernel<MAXT, BF>, dim3(blocks), dim3(threads), smem, st, in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
                                                                 out, M, N, S, film_row_dev);                     \
   }
   if (threads <= 512) {
@@ -305,6 +322,7 @@ void launch_ln_film_act(const float* u, const float* stats, const float* g, cons
 // ---------------------------------------------------------------------------------------------------
 __global__ void noise_encoding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
                                       float* __restrict__ enc, int R) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 64) return;
   const int r = i / 64, j = i % 64;
@@ -485,6 +503,8 @@ void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 reverse_step_kernel(const ReverseStepArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int t = a.t_ptr ? *a.t_ptr : a.t;
   const float* cf = a.coef + 8 * t;
   const float sqrt_recip = cf[0], sqrt_m1 = cf[1], mu1 = cf[2], mu2 = cf[3], sigma = cf[4], sqrt_ap = cf[5],
@@ -544,16 +564,18 @@ reverse_step_kernel(const ReverseStepArgs a) {
 }
 void launch_reverse_step(const ReverseStepArgs& a, cudaStream_t st) {
   const int NC = a.N * a.C;
-  reverse_step_kernel<<<(NC + 255) / 256, 256, 0, st>>>(a);
+  launch_pdl(reverse_step_kernel, dim3((NC + 255) / 256), dim3(256), 0, st, a);
 }
 __global__ void step_advance_kernel(int* t_ptr) { *t_ptr -= 1; }
 void launch_step_advance(int* t_ptr, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(t_ptr); }
 __global__ void fill_cond_kernel(const float* coef, const int* t_ptr, float* cond, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) cond[i] = coef[8 * (*t_ptr) + 5];
 }
 void launch_fill_cond(const float* coef, const int* t_ptr, float* cond, int n, cudaStream_t st) {
-  fill_cond_kernel<<<(n + 255) / 256, 256, 0, st>>>(coef, t_ptr, cond, n);
+  launch_pdl(fill_cond_kernel, dim3((n + 255) / 256), dim3(256), 0, st, coef, t_ptr, cond, n);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -562,6 +584,8 @@ void launch_fill_cond(const float* coef, const int* t_ptr, float* cond, int n, c
 __global__ void __launch_bounds__(256)
 ddpm_loss_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
                  float* __restrict__ dpred, float gscale, int per_sample) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const size_t base = static_cast<size_t>(b) * per_sample;
   float s = 0.f;
@@ -582,7 +606,7 @@ ddpm_loss_kernel(const float* __restrict__ eps, const float* __restrict__ pred, 
 }
 void launch_ddpm_loss(const float* eps, const float* pred, float* loss_per_example, float* dpred_or_null,
                       float gscale, int B, int per_sample, cudaStream_t st) {
-  ddpm_loss_kernel<<<B, 256, 0, st>>>(eps, pred, loss_per_example, dpred_or_null, gscale, per_sample);
+  launch_pdl(ddpm_loss_kernel, dim3(B), dim3(256), 0, st, eps, pred, loss_per_example, dpred_or_null, gscale, per_sample);
 }
 
 }  // namespace smd

@@ -4,8 +4,12 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
+#include "ptx.cuh"
+#include "pdl_launch.cuh"
 
 namespace smd {
+
 
 // ---------------------------------------------------------------------------------------------------
 // helpers

@@ -250,4 +250,11 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   return d;
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its in-stream predecessor is still running;
+// pdl_wait() blocks until that predecessor has completed and its writes are visible (no-op otherwise), and
+// pdl_trigger() lets the NEXT kernel in the stream begin launching once every CTA of this grid has called it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace smd
