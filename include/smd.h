@@ -7,7 +7,7 @@
  *   smd_forward            <- model(inputs, t)               models/ncsn.py:141-179 (TransformerDDPM.apply),
  *                                                            models/ncsn.py:125-135 (DenseDDPM.apply)
  *   smd_ddpm_loss          <- diffusion_loss(...)            utils/losses.py:250-308   (eval_step, train_ncsn.py:206-221)
- *   smd_ddpm_train_step    <- train_step(...)                train_ncsn.py:260-288 (value_and_grad + clip + Adam)
+ *   smd_ddpm_grads + smd_clip_adam <- train_step(...)      train_ncsn.py:260-288 (value_and_grad, then clip + Adam)
  *   smd_ema_update         <- EMAHelper.update               utils/train_utils.py:73-78
  *   smd_ddpm_reverse_step  <- body of sample_with_beta       utils/ebm_utils.py:327-397
  *   smd_ddpm_sample        <- diffusion_dynamics(...)        utils/ebm_utils.py:274-405 (lax.scan over T steps)
@@ -50,7 +50,7 @@ typedef struct smd_config {
   int channels;        /* C: data_shape[-1] after --slice_ckpt (42 / 146 / 512) */
   int max_batch;       /* largest number of examples one call may pass */
   int cta_group;       /* 1 or 2: tcgen05 cta_group used by the GEMMs (2 = CTA pairs, M=256 tiles) */
-  int training;        /* 1: reserve the saved-activation / gradient buffers of smd_ddpm_train_step */
+  int training;        /* 1: reserve the saved-activation / gradient buffers of smd_ddpm_grads */
   int sampler_T;       /* > 0: reserve a (K, sampler_T, 2*mlp_dims) FiLM table so the sampler evaluates the FiLM
                           generator once per schedule instead of once per step (all samples share t) */
 } smd_config;
