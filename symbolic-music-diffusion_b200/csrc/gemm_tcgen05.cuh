@@ -115,7 +115,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   static_assert(SM::kStages >= 3, "pipeline too shallow");
   static_assert(!((kF & F_LN) && !(kF & F_RAGGED)) || kEW == 8, "the paired LayerNorm epilogue needs 8 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KiB alignment by OFFSET from the __shared__ symbol (not by integer-casting the pointer): the compiler keeps the
+  // shared address space, so the epilogue's staging accesses are LDS/STS instead of generic LD/ST.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kStages * SM::kStageBytes);
   uint64_t* full_bar = bars;                         // [kStages]
   uint64_t* empty_bar = bars + SM::kStages;          // [kStages]
@@ -459,9 +461,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
           }
+          const int col0 = n0 + c0;
+          // the chunk's 32 bias values are fetched while the TMEM load is in flight
+          float4 bq[H_BIAS ? 8 : 1];
+          if constexpr (H_BIAS) {
+            if (has_bias && first_split && chunk_fast(c0)) {
+              const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bq[i] = __ldg(b4 + i);
+            }
+          }
           tmem_ld_wait();
           const int ncols = half ? 16 : 32;
-          const int col0 = n0 + c0;
           float v[32];
           if constexpr (H_SCALE) {
 #pragma unroll
@@ -493,10 +504,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             } else {
               if constexpr (H_BIAS) {
                 if (has_bias && first_split) {
-                  const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    const float4 b = __ldg(b4 + i);
+                    const float4 b = bq[i];
                     v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                   }
                 }
