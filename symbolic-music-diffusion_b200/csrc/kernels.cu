@@ -1,4 +1,5 @@
 // SIMT kernels of the DDPM hot path (see kernels.cuh for the contract of each launcher).
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace smd {
@@ -156,12 +157,174 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(pr + j) = make_float4(sc[j], sc[j + 1], sc[j + 2], sc[j + 3]);
   }
 }
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core variant (DH % 8 == 0): same CTA / warp mapping, but Q K^T and P V run on mma.sync m16n8k8 tf32
+// (a 32x32x16 problem per head is far below a tcgen05 tile; ~350 instructions per warp instead of ~2000).
+// q, k, v are rounded to tf32 once while the CTA stages them in shared memory (row pitch = W + 4 words, so every
+// fragment read is bank-conflict free); scores, softmax and the P V accumulation stay fp32.  The softmax output is
+// fed to the second MMA straight from the accumulator registers: within each block of 8 keys, k-slot t holds key 2t
+// and k-slot t+4 holds key 2t+1, and the V fragment is read with the same permutation (a sum over keys does not
+// care about their order), so no shuffles are needed between the two products.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ o, float* __restrict__ probs, int B, int H) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint32_t att_sm[];
+  const int tid = threadIdx.x;
+  const int HPB = blockDim.x >> 5, W = HPB * DH, W4 = W / 4, P = W + 4;
+  uint32_t* sQ = att_sm;
+  uint32_t* sK = sQ + 32 * P;
+  uint32_t* sV = sK + 32 * P;
+  const int b = blockIdx.x, hb = blockIdx.y * HPB;
+  const float qs = rsqrtf(static_cast<float>(DH));   // flax: query / sqrt(depth) before the dot
+  const float* base = qkv + static_cast<size_t>(b) * 32 * 384;
+  for (int i = tid; i < 32 * W4; i += blockDim.x) {
+    const int row = i / W4, c4 = (i % W4) * 4, gc = hb * DH + c4;
+    const float4 q4 = *reinterpret_cast<const float4*>(base + row * 384 + gc);
+    const float4 k4 = *reinterpret_cast<const float4*>(base + row * 384 + 128 + gc);
+    const float4 v4 = *reinterpret_cast<const float4*>(base + row * 384 + 256 + gc);
+    *reinterpret_cast<uint4*>(&sQ[row * P + c4]) = make_uint4(to_tf32(q4.x * qs), to_tf32(q4.y * qs), to_tf32(q4.z * qs), to_tf32(q4.w * qs));
+    *reinterpret_cast<uint4*>(&sK[row * P + c4]) = make_uint4(to_tf32(k4.x), to_tf32(k4.y), to_tf32(k4.z), to_tf32(k4.w));
+    *reinterpret_cast<uint4*>(&sV[row * P + c4]) = make_uint4(to_tf32(v4.x), to_tf32(v4.y), to_tf32(v4.z), to_tf32(v4.w));
+  }
+  __syncthreads();
+  const int hl = tid >> 5, lane = tid & 31;
+  const int h = hb + hl;
+  if (h >= H) return;
+  const int g = lane >> 2, t = lane & 3;
+  const int hc = hl * DH;
+  // ---- S = (Q / sqrt(dh)) K^T : 2 m-tiles x 4 n-tiles, DH / 8 k-steps
+  float sc[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < DH / 8; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t* q0 = sQ + (16 * mt + g) * P + hc + 8 * ks + t;
+      a[mt][0] = q0[0]; a[mt][1] = q0[8 * P]; a[mt][2] = q0[4]; a[mt][3] = q0[8 * P + 4];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint32_t* k0 = sK + (8 * nt + g) * P + hc + 8 * ks + t;
+      const uint32_t b0 = k0[0], b1 = k0[4];
+      mma_tf32_16x8x8(sc[0][nt], a[0], b0, b1);
+      mma_tf32_16x8x8(sc[1][nt], a[1], b0, b1);
+    }
+  }
+  // ---- row softmax: a row lives in the 4 lanes of a quad (t = 0..3), 8 values per lane
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {   // hr = 0: row 16 mt + g (c0, c1); hr = 1: row 16 mt + g + 8 (c2, c3)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(sc[mt][nt][2 * hr], sc[mt][nt][2 * hr + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float e0 = expf(sc[mt][nt][2 * hr] - mx), e1 = expf(sc[mt][nt][2 * hr + 1] - mx);
+        sc[mt][nt][2 * hr] = e0; sc[mt][nt][2 * hr + 1] = e1;
+        sum += e0 + e1;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { sc[mt][nt][2 * hr] *= inv; sc[mt][nt][2 * hr + 1] *= inv; }
+    }
+  }
+  if (probs != nullptr) {
+    float* pr = probs + (static_cast<size_t>(b) * H + h) * 32 * 32;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<float2*>(pr + (16 * mt + g) * 32 + 8 * nt + 2 * t) = make_float2(sc[mt][nt][0], sc[mt][nt][1]);
+        *reinterpret_cast<float2*>(pr + (16 * mt + g + 8) * 32 + 8 * nt + 2 * t) = make_float2(sc[mt][nt][2], sc[mt][nt][3]);
+      }
+  }
+  // ---- O = P V : 2 m-tiles x DH / 8 n-tiles, 4 k-steps (one per block of 8 keys, permuted as described above)
+  float acc[2][DH / 8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n2 = 0; n2 < DH / 8; ++n2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][n2][i] = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      a[mt][0] = to_tf32(sc[mt][kb][0]);   // (row g,     slot t)     = key 2t
+      a[mt][1] = to_tf32(sc[mt][kb][2]);   // (row g + 8, slot t)
+      a[mt][2] = to_tf32(sc[mt][kb][1]);   // (row g,     slot t + 4) = key 2t + 1
+      a[mt][3] = to_tf32(sc[mt][kb][3]);   // (row g + 8, slot t + 4)
+    }
+#pragma unroll
+    for (int n2 = 0; n2 < DH / 8; ++n2) {
+      const uint32_t* v0 = sV + (8 * kb + 2 * t) * P + hc + 8 * n2 + g;
+      const uint32_t b0 = v0[0], b1 = v0[P];
+      mma_tf32_16x8x8(acc[0][n2], a[0], b0, b1);
+      mma_tf32_16x8x8(acc[1][n2], a[1], b0, b1);
+    }
+  }
+  __nv_bfloat16* ob = o + static_cast<size_t>(b) * 32 * 128 + h * DH;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n2 = 0; n2 < DH / 8; ++n2) {
+      *reinterpret_cast<__nv_bfloat162*>(ob + (16 * mt + g) * 128 + 8 * n2 + 2 * t) = __floats2bfloat162_rn(acc[mt][n2][0], acc[mt][n2][1]);
+      *reinterpret_cast<__nv_bfloat162*>(ob + (16 * mt + g + 8) * 128 + 8 * n2 + 2 * t) = __floats2bfloat162_rn(acc[mt][n2][2], acc[mt][n2][3]);
+    }
+}
+
 void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st) {
   const int dh = 128 / H;
   int hpb = H;
   while (hpb > 4 && hpb % 2 == 0) hpb /= 2;
   const dim3 grid(B, H / hpb);
   const int threads = hpb * 32;
+  static const bool simt = [] { const char* v = getenv("SMD_ATTENTION_SIMT"); return v && v[0] == '1'; }();
+  if (!simt && dh % 8 == 0 && dh <= 32) {
+    const size_t smem = 3 * 32 * static_cast<size_t>(hpb * dh + 4) * sizeof(uint32_t);
+#define SMD_ATT_MMA(DHV)                                                                                          \
+  {                                                                                                               \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      cudaFuncSetAttribute(attention_mma_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 132 * 4); \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    launch_pdl(attention_mma_kernel<DHV>, grid, dim3(threads), smem, st, qkv, o, probs_or_null, B, H);            \
+  }
+    if (dh == 16) SMD_ATT_MMA(16)
+    else if (dh == 8) SMD_ATT_MMA(8)
+    else SMD_ATT_MMA(32)
+#undef SMD_ATT_MMA
+    return;
+  }
   if (dh == 16) launch_pdl(attention_kernel<16>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
   else if (dh == 8) launch_pdl(attention_kernel<8>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
   else if (dh == 32) launch_pdl(attention_kernel<32>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
