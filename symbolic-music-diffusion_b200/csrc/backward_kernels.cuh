@@ -1,6 +1,7 @@
 // SIMT kernels of the hand-written backward pass (what jax.value_and_grad derives for train_ncsn.py:282-283;
 // contract per op in SURVEY Appendix E).
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 #include "kernels.cuh"
 
@@ -715,6 +716,208 @@ __global__ void attention_bwd_kernel(const float* __restrict__ qkv, const float*
     }
   }
 }
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core attention backward (DH % 8 == 0): the four 32x32x16-class products per head on mma.sync m16n8k8 tf32.
+//   dP = dO V^T, dS = P (dP - rowsum(dP P)), dV = P^T dO, dQ = dS K / sqrt(dh), dK = dS^T Q~
+// P and dS live in accumulator-layout registers; the products that need them as the A operand in the same
+// orientation (dQ) take them straight from registers with the key permutation of the forward kernel, the transposed
+// uses (dV, dK) go through a per-warp 32x36 shared tile read back as the transposed fragment (bank-conflict free
+// with the same within-8 permutation applied to the B operand rows).
+// ---------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attention_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ probs, const float* __restrict__ dO,
+                         __nv_bfloat16* __restrict__ dqkv16, float* __restrict__ dbias, int H) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint32_t attb_sm[];
+  constexpr int NT2 = DH / 8;
+  const int tid = threadIdx.x;
+  const int HPB = blockDim.x >> 5, W = HPB * DH, W4 = W / 4, PT = W + 4;
+  uint32_t* sQ = attb_sm;             // [32][PT] tf32, q / sqrt(dh)
+  uint32_t* sK = sQ + 32 * PT;
+  uint32_t* sV = sK + 32 * PT;
+  uint32_t* sD = sV + 32 * PT;        // dO
+  uint32_t* sTall = sD + 32 * PT;     // [HPB][32][36]
+  const int b = blockIdx.x, hb = blockIdx.y * HPB;
+  const float qs = rsqrtf(static_cast<float>(DH));
+  const float* base = qkv + static_cast<size_t>(b) * 32 * 384;
+  const float* dob = dO + static_cast<size_t>(b) * 32 * 128;
+  for (int i = tid; i < 32 * W4; i += blockDim.x) {
+    const int row = i / W4, c4 = (i % W4) * 4, gc = hb * DH + c4;
+    const float4 q4 = *reinterpret_cast<const float4*>(base + row * 384 + gc);
+    const float4 k4 = *reinterpret_cast<const float4*>(base + row * 384 + 128 + gc);
+    const float4 v4 = *reinterpret_cast<const float4*>(base + row * 384 + 256 + gc);
+    const float4 d4 = *reinterpret_cast<const float4*>(dob + row * 128 + gc);
+    *reinterpret_cast<uint4*>(&sQ[row * PT + c4]) = make_uint4(to_tf32(q4.x * qs), to_tf32(q4.y * qs), to_tf32(q4.z * qs), to_tf32(q4.w * qs));
+    *reinterpret_cast<uint4*>(&sK[row * PT + c4]) = make_uint4(to_tf32(k4.x), to_tf32(k4.y), to_tf32(k4.z), to_tf32(k4.w));
+    *reinterpret_cast<uint4*>(&sV[row * PT + c4]) = make_uint4(to_tf32(v4.x), to_tf32(v4.y), to_tf32(v4.z), to_tf32(v4.w));
+    *reinterpret_cast<uint4*>(&sD[row * PT + c4]) = make_uint4(to_tf32(d4.x), to_tf32(d4.y), to_tf32(d4.z), to_tf32(d4.w));
+  }
+  __syncthreads();
+  const int hl = tid >> 5, lane = tid & 31;
+  const int h = hb + hl;
+  if (h >= H) return;
+  const int g = lane >> 2, t = lane & 3;
+  const int hc = hl * DH, gh = h * DH;
+  uint32_t* sT = sTall + hl * 32 * 36;
+
+  // P in accumulator layout: [mt][nt] -> rows 16 mt + g (+8), keys 8 nt + 2t (+1)
+  float pc[2][4][4];
+  {
+    const float* pr = probs + (static_cast<size_t>(b) * H + h) * 32 * 32;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 lo = *reinterpret_cast<const float2*>(pr + (16 * mt + g) * 32 + 8 * nt + 2 * t);
+        const float2 hi = *reinterpret_cast<const float2*>(pr + (16 * mt + g + 8) * 32 + 8 * nt + 2 * t);
+        pc[mt][nt][0] = lo.x; pc[mt][nt][1] = lo.y; pc[mt][nt][2] = hi.x; pc[mt][nt][3] = hi.y;
+      }
+  }
+  // ---- dP = dO V^T
+  float ds[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ds[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT2; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t* d0 = sD + (16 * mt + g) * PT + hc + 8 * ks + t;
+      a[mt][0] = d0[0]; a[mt][1] = d0[8 * PT]; a[mt][2] = d0[4]; a[mt][3] = d0[8 * PT + 4];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint32_t* v0 = sV + (8 * nt + g) * PT + hc + 8 * ks + t;
+      const uint32_t b0 = v0[0], b1 = v0[4];
+      mma_tf32_16x8x8(ds[0][nt], a[0], b0, b1);
+      mma_tf32_16x8x8(ds[1][nt], a[1], b0, b1);
+    }
+  }
+  // ---- dS = P (dP - sum_j dP P)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      float rs = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        rs = fmaf(ds[mt][nt][2 * hr], pc[mt][nt][2 * hr], fmaf(ds[mt][nt][2 * hr + 1], pc[mt][nt][2 * hr + 1], rs));
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        ds[mt][nt][2 * hr] = pc[mt][nt][2 * hr] * (ds[mt][nt][2 * hr] - rs);
+        ds[mt][nt][2 * hr + 1] = pc[mt][nt][2 * hr + 1] * (ds[mt][nt][2 * hr + 1] - rs);
+      }
+    }
+  // stage an accumulator-layout [query][key] matrix in the warp's tile (tf32)
+  auto stage = [&](const float (&m)[2][4][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<uint2*>(&sT[(16 * mt + g) * 36 + 8 * nt + 2 * t]) = make_uint2(to_tf32(m[mt][nt][0]), to_tf32(m[mt][nt][1]));
+        *reinterpret_cast<uint2*>(&sT[(16 * mt + g + 8) * 36 + 8 * nt + 2 * t]) = make_uint2(to_tf32(m[mt][nt][2]), to_tf32(m[mt][nt][3]));
+      }
+  };
+  // out[key][dim] = sum_query T[query][key] * Bm[query][dim]; query slots of each 8-block permuted (t -> 2t, t+4 -> 2t+1)
+  auto mma_transposed = [&](float (&out)[2][NT2][4], const uint32_t* Bm) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n2 = 0; n2 < NT2; ++n2)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[mt][n2][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[2][4];
+      const uint32_t* r0 = sT + (8 * ks + 2 * t) * 36;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        a[mt][0] = r0[16 * mt + g];        // (key g,     query 2t)
+        a[mt][1] = r0[16 * mt + g + 8];    // (key g + 8, query 2t)
+        a[mt][2] = r0[36 + 16 * mt + g];   // (key g,     query 2t + 1)
+        a[mt][3] = r0[36 + 16 * mt + g + 8];
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < NT2; ++n2) {
+        const uint32_t* b0p = Bm + (8 * ks + 2 * t) * PT + hc + 8 * n2 + g;
+        const uint32_t b0 = b0p[0], b1 = b0p[PT];
+        mma_tf32_16x8x8(out[0][n2], a[0], b0, b1);
+        mma_tf32_16x8x8(out[1][n2], a[1], b0, b1);
+      }
+    }
+  };
+  // ---- dV = P^T dO
+  float dv[2][NT2][4];
+  stage(pc);
+  __syncwarp();
+  mma_transposed(dv, sD);
+  __syncwarp();
+  // ---- dQ = dS K / sqrt(dh)  (A straight from registers, keys permuted as in the forward P V product)
+  float dq[2][NT2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n2 = 0; n2 < NT2; ++n2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dq[mt][n2][i] = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      a[mt][0] = to_tf32(ds[mt][kb][0]); a[mt][1] = to_tf32(ds[mt][kb][2]);
+      a[mt][2] = to_tf32(ds[mt][kb][1]); a[mt][3] = to_tf32(ds[mt][kb][3]);
+    }
+#pragma unroll
+    for (int n2 = 0; n2 < NT2; ++n2) {
+      const uint32_t* k0 = sK + (8 * kb + 2 * t) * PT + hc + 8 * n2 + g;
+      const uint32_t b0 = k0[0], b1 = k0[PT];
+      mma_tf32_16x8x8(dq[0][n2], a[0], b0, b1);
+      mma_tf32_16x8x8(dq[1][n2], a[1], b0, b1);
+    }
+  }
+  // ---- dK = dS^T Q~
+  float dk[2][NT2][4];
+  stage(ds);
+  __syncwarp();
+  mma_transposed(dk, sQ);
+  // ---- outputs (bf16 GEMM operand) and bias gradients (column sums over the 32 rows)
+  __nv_bfloat16* ob = dqkv16 + static_cast<size_t>(b) * 32 * 384 + gh;
+  auto emit = [&](const float (&m)[2][NT2][4], int col_off, float scale) {
+#pragma unroll
+    for (int n2 = 0; n2 < NT2; ++n2) {
+      float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float v0 = m[mt][n2][0] * scale, v1 = m[mt][n2][1] * scale, v2 = m[mt][n2][2] * scale, v3 = m[mt][n2][3] * scale;
+        *reinterpret_cast<__nv_bfloat162*>(ob + (16 * mt + g) * 384 + col_off + 8 * n2 + 2 * t) = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<__nv_bfloat162*>(ob + (16 * mt + g + 8) * 384 + col_off + 8 * n2 + 2 * t) = __floats2bfloat162_rn(v2, v3);
+        c0 += v0 + v2; c1 += v1 + v3;
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      }
+      if (g == 0) {
+        atomicAdd(dbias + col_off + gh + 8 * n2 + 2 * t, c0);
+        atomicAdd(dbias + col_off + gh + 8 * n2 + 2 * t + 1, c1);
+      }
+    }
+  };
+  emit(dq, 0, qs);
+  emit(dk, 128, 1.0f);
+  emit(dv, 256, 1.0f);
+}
+
 inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, const float* dO, __nv_bfloat16* dqkv16,
                                         float* dbias, int B, int H, cudaStream_t st) {
   const int dh = 128 / H;
@@ -722,6 +925,21 @@ inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, co
   while (hpb > 4 && hpb % 2 == 0) hpb /= 2;
   const size_t smem = (4 * 32 * static_cast<size_t>(hpb) * dh + static_cast<size_t>(hpb) * 32 * 33) * sizeof(float);
   const dim3 grid(B, H / hpb);
+  static const bool simt = [] { const char* v = getenv("SMD_ATTENTION_SIMT"); return v && v[0] == '1'; }();
+  if (!simt && dh % 8 == 0 && dh <= 32) {
+    const size_t sm2 = (4 * 32 * static_cast<size_t>(hpb * dh + 4) + static_cast<size_t>(hpb) * 32 * 36) * sizeof(uint32_t);
+#define SMD_ATT_BWD_MMA(DHV)                                                                                        \
+  {                                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         static_cast<int>(sm2));                                                    \
+    if (e != cudaSuccess) return e;                                                                                 \
+    return launch_pdl(attention_bwd_mma_kernel<DHV>, grid, dim3(hpb * 32), sm2, st, qkv, probs, dO, dqkv16, dbias, H); \
+  }
+    if (dh == 16) SMD_ATT_BWD_MMA(16)
+    else if (dh == 8) SMD_ATT_BWD_MMA(8)
+    else SMD_ATT_BWD_MMA(32)
+#undef SMD_ATT_BWD_MMA
+  }
 #define SMD_ATT_BWD(DHV)                                                                                       \
   {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -39,6 +39,19 @@ __device__ __forceinline__ float swish_grad(float v) {  // d/dv [v * sigmoid(v)]
   const float s = fmaf(0.5f, tanh_approx(0.5f * v), 0.5f);
   return s * fmaf(v, 1.0f - s, 1.0f);
 }
+// tf32 mma.sync helpers (attention forward / backward)
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float c = 0.7978845608028654f;
   const float u = c * (x + 0.044715f * x * x * x);
