@@ -8,6 +8,7 @@
 #include <atomic>
 #include <string>
 #include "gemm_tcgen05.cuh"
+#include "ffn_fused.cuh"
 #include "pdl_launch.cuh"
 
 namespace smd {
@@ -172,6 +173,57 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
 
 inline cudaError_t launch_gemm(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
   return op.cg == 2 ? launch_gemm_cg<2>(op, M, ep, st) : launch_gemm_cg<1>(op, M, ep, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// fused FFN (ffn_fused.cuh)
+// ---------------------------------------------------------------------------------------------------
+struct FfnOp {
+  CUtensorMap tmA, tmW1, tmW2;
+  bool ok = false;
+};
+// A: bf16 [rows][128] K-major; W1: bf16 (128, Md) row-major; W2: bf16 (Md, 128) row-major (both MN-major B operands)
+inline bool make_ffn_op(FfnOp* op, const void* A, uint64_t rows, const void* W1, const void* W2, int Md) {
+  op->ok = make_tmap_bf16(&op->tmA, A, rows, 128, 128) && make_tmap_bf16(&op->tmW1, W1, 128, static_cast<uint64_t>(Md), 64) &&
+           make_tmap_bf16(&op->tmW2, W2, static_cast<uint64_t>(Md), 128, 64);
+  return op->ok;
+}
+inline bool ffn_fused_enabled() {
+  static const bool on = [] { const char* v = getenv("SMD_FFN_FUSED"); return !(v && v[0] == '0'); }();
+  return on;
+}
+// SMD_FFN_FUSED=2: use the fused kernel at every size and in training too (tests)
+inline bool ffn_fused_forced() {
+  static const bool on = [] { const char* v = getenv("SMD_FFN_FUSED"); return v && v[0] == '2'; }();
+  return on;
+}
+inline cudaError_t launch_ffn_fused(const FfnOp& op, const FfnFusedArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = (a.M + 255) / 256;
+  int pairs = device_sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+  cfg.blockDim = dim3(FfnSmem::kThreads);
+  cfg.dynamicSmemBytes = FfnSmem::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (a.hidden_pre != nullptr || a.hidden != nullptr) return cudaLaunchKernelEx(&cfg, ffn_fused_kernel<true>, op.tmA, op.tmW1, op.tmW2, a);
+  return cudaLaunchKernelEx(&cfg, ffn_fused_kernel<false>, op.tmA, op.tmW1, op.tmW2, a);
 }
 
 }  // namespace smd

@@ -70,6 +70,7 @@ struct smd_plan {
   int pack_tiles = 0;
   // ---- GEMM ops ----
   std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b;
+  std::vector<FfnOp> op_ffn;   // fused FFN (cta_group 2, mlp_dims % 128 == 0)
   GemmOp op_post, op_out, op_in;
   // sampler
   int T = 0;

@@ -168,12 +168,15 @@ static int build_ops(smd_plan* p) {
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
     p->op_qkv.resize(c.num_layers); p->op_o.resize(c.num_layers);
     p->op_ffn1.resize(c.num_layers); p->op_ffn2.resize(c.num_layers);
+    p->op_ffn.resize(c.num_layers);
     for (int l = 0; l < c.num_layers; ++l) {
       const std::string pre = "l" + std::to_string(l) + ".";
       if (!fwd(&p->op_qkv[l], "a", pre + "attn.qkv.kernel", kE, 3 * kE, 128)) return SMD_ERR_CUDA;
       if (!fwd(&p->op_o[l], "o", pre + "attn.out.kernel", kE, kE, 128)) return SMD_ERR_CUDA;
       if (!fwd(&p->op_ffn1[l], "a", pre + "ffn1.kernel", kE, Md, 256)) return SMD_ERR_CUDA;
       if (!fwd(&p->op_ffn2[l], "hidden", pre + "ffn2.kernel", Md, kE, 128)) return SMD_ERR_CUDA;
+      if (cg == 2 && Md % 128 == 0 &&
+          !make_ffn_op(&p->op_ffn[l], A("a"), Mp, Wsh(pre + "ffn1.kernel"), Wsh(pre + "ffn2.kernel"), Md)) return SMD_ERR_CUDA;
     }
     if (!fwd(&p->op_post, "a", "post.kernel", kE, Md, 256)) return SMD_ERR_CUDA;
   } else {
@@ -357,6 +360,23 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
       e.out_bf16 = a2; e.ld_bf16 = kE;
       e.ln_gamma = p->P(params, pre + "ln2.scale"); e.ln_beta = p->P(params, pre + "ln2.bias");
       SMD_CUDA(launch_gemm(oo, M, e, st));
+      const std::string nl = (l + 1 < c.num_layers) ? ("l" + std::to_string(l + 1) + ".ln1.") : std::string("post_ln.");
+      // worth it once the token count fills the machine (one CTA pair per 256 tokens); training keeps the two-GEMM
+      // path: it has to write the hidden activations anyway and at batch 128 only 16 pairs would be busy
+      if (p->op_ffn[l].ok && ffn_fused_enabled() && (ffn_fused_forced() || (!save && M >= 32 * 256))) {
+        // FFN up + GELU + FFN down + residual + next LayerNorm in one launch; the hidden activation stays on chip
+        FfnOp fo = p->op_ffn[l];
+        if (save && !make_tmap_bf16(&fo.tmA, a2, p->Mp, 128, 128)) return SMD_ERR_CUDA;
+        FfnFusedArgs fa;
+        fa.b1 = p->P(params, pre + "ffn1.bias"); fa.b2 = p->P(params, pre + "ffn2.bias");
+        fa.residual = h_mid; fa.out_f32 = h_out;
+        fa.ln_gamma = p->P(params, nl + "scale"); fa.ln_beta = p->P(params, nl + "bias");
+        fa.out_bf16 = a_next;
+        fa.hidden_pre = hid_pre; fa.hidden = save ? hidden : nullptr;
+        fa.M = M; fa.Md = Md;
+        SMD_CUDA(launch_ffn_fused(fo, fa, st));
+        continue;
+      }
       e = epi();
       e.bias = p->P(params, pre + "ffn1.bias");
       e.out_bf16 = hidden; e.ld_bf16 = Md; e.act = ACT_GELU_TANH;
@@ -367,7 +387,6 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
       e.residual = h_mid; e.ld_res = kE;
       e.out_f32 = h_out; e.ld_f32 = kE;
       e.out_bf16 = a_next; e.ld_bf16 = kE;
-      const std::string nl = (l + 1 < c.num_layers) ? ("l" + std::to_string(l + 1) + ".ln1.") : std::string("post_ln.");
       e.ln_gamma = p->P(params, nl + "scale"); e.ln_beta = p->P(params, nl + "bias");
       SMD_CUDA(launch_gemm(o2, M, e, st));
     }

@@ -99,3 +99,15 @@ def test_ddpm_loss_parity(lib):
     assert rel_l2(pred, ref_pred) < 3e-2
     # |d loss| <= 2e-2 * loss (stated tolerance on ddpm_loss for bf16 operands)
     np.testing.assert_allclose(loss.cpu().numpy(), ref.numpy(), rtol=2e-2)
+
+
+def test_fused_ffn_kernel(lib):
+    """The fused FFN kernel (csrc/ffn_fused.cuh) only engages on its own at >= 8192 tokens; SMD_FFN_FUSED=2 forces
+    it everywhere (training included) in a worker process -- the switch is read once per process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SMD_FFN_FUSED="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fused_ffn_worker.py")], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fused-ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
