@@ -90,45 +90,116 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_train_step_rate(sample_batch: int, min_seconds: float, max_steps: int, threads: int):
+def host_threads() -> int:
+    """Threads the CPU arm may use: the scheduler affinity mask, clipped by a cgroup CPU quota if there is one and by
+    32 (a batch-16 sample of this model stops scaling -- and with an over-reported core count collapses -- beyond)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))
+
+
+class CpuTrainStep:
     """Oracle (torch CPU fp32 restatement of train_ncsn.py:260-288) on a bounded sample of the train workload."""
-    from oracle import ddpm_oracle as O
-    from smd_b200 import Engine
-    torch.set_num_threads(threads)
-    cfg = model_config("train")
-    eng = Engine(cfg, max_batch=sample_batch)     # layout only; never touches the GPU
-    flat = eng.init_params(seed=1)
-    p = {k: torch.from_numpy(v) for k, v in eng.flat_to_dict(flat).items()}
-    m = {k: torch.zeros_like(v) for k, v in p.items()}
-    v = {k: torch.zeros_like(t) for k, t in p.items()}
-    x0 = torch.from_numpy(synthetic_batch(sample_batch, 0))
-    rng = np.random.default_rng(2)
-    eps = torch.from_numpy(rng.standard_normal(tuple(x0.shape)).astype(np.float32))
-    ap = O.alphas_prod_with_one(O.create_noise_schedule(1e-6, 0.01, 1000, "linear"))
-    used = torch.from_numpy(ap[rng.integers(1, 1001, sample_batch) - 1])
-    kw = dict(num_layers=6, num_heads=8, num_mlp_layers=2, mlp_dims=2048)
-    (p, m, v), _, _, _ = O.train_step("TransformerDDPM", p, m, v, 0, x0, used, eps, 1e-3, model_kw=kw)  # warm-up
+
+    def __init__(self, sample_batch: int, threads: int):
+        from oracle import ddpm_oracle as O
+        from smd_b200 import Engine
+        self.O = O
+        torch.set_num_threads(threads)
+        cfg = model_config("train")
+        eng = Engine(cfg, max_batch=sample_batch)     # layout only; never touches the GPU
+        flat = eng.init_params(seed=1)
+        self.p = {k: torch.from_numpy(v) for k, v in eng.flat_to_dict(flat).items()}
+        self.m = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        self.v = {k: torch.zeros_like(t) for k, t in self.p.items()}
+        self.kw = dict(num_layers=6, num_heads=8, num_mlp_layers=2, mlp_dims=2048)
+        self.n = 0
+        self.set_batch(sample_batch)
+
+    def set_batch(self, sample_batch: int):
+        O = self.O
+        self.batch = sample_batch
+        self.x0 = torch.from_numpy(synthetic_batch(sample_batch, 0))
+        rng = np.random.default_rng(2)
+        self.eps = torch.from_numpy(rng.standard_normal(tuple(self.x0.shape)).astype(np.float32))
+        ap = O.alphas_prod_with_one(O.create_noise_schedule(1e-6, 0.01, 1000, "linear"))
+        self.used = torch.from_numpy(ap[rng.integers(1, 1001, sample_batch) - 1])
+
+    def step(self) -> float:
+        t0 = time.perf_counter()
+        (self.p, self.m, self.v), _, _, _ = self.O.train_step("TransformerDDPM", self.p, self.m, self.v, self.n, self.x0,
+                                                              self.used, self.eps, 1e-3, model_kw=self.kw)
+        self.n += 1
+        return time.perf_counter() - t0
+
+
+def cpu_train_step_rate(sample_batch: int, min_seconds: float, max_steps: int, threads: int):
+    """(sample-steps/s, steps, seconds) of the CPU restatement: one untimed warm-up step, then steps until
+    `min_seconds` have passed (at most `max_steps`); if the warm-up shows a step would blow the budget the sample
+    shrinks (batch 16 -> 4 -> 1)."""
+    job = CpuTrainStep(sample_batch, threads)
+    w = job.step()
+    while w > max(3.0, min_seconds) and job.batch > 1:
+        job.set_batch(max(1, job.batch // 4))
+        w = job.step()
     t0 = time.perf_counter()
     n = 0
     while n < max_steps and (n == 0 or time.perf_counter() - t0 < min_seconds):
-        (p, m, v), _, _, _ = O.train_step("TransformerDDPM", p, m, v, n + 1, x0, used, eps, 1e-3, model_kw=kw)
+        job.step()
         n += 1
     dt = time.perf_counter() - t0
-    return sample_batch * n / dt, n, dt
+    return job.batch * n / dt, n, dt, job.batch
+
+
+def cpu_sample_step_rate(n_samples: int, min_seconds: float, max_steps: int, threads: int):
+    """Oracle reverse-diffusion steps (ebm_utils.py:327-397) on a bounded sample of the sampling workload."""
+    from oracle import ddpm_oracle as O
+    from smd_b200 import Engine
+    torch.set_num_threads(threads)
+    cfg = model_config("sample")
+    eng = Engine(cfg, max_batch=n_samples)     # layout only; never touches the GPU
+    p = {k: torch.from_numpy(v) for k, v in eng.flat_to_dict(eng.init_params(seed=1)).items()}
+    kw = dict(num_layers=6, num_heads=8, num_mlp_layers=2, mlp_dims=2048)
+    coef = O.reverse_coefficients(O.create_noise_schedule(1e-6, 0.01, 1000, "linear"))
+    rng = np.random.default_rng(3)
+    state = torch.from_numpy(rng.standard_normal((n_samples, 32, 42)).astype(np.float32))
+    z = torch.from_numpy(rng.standard_normal((n_samples, 32, 42)).astype(np.float32))
+    apply_fn = lambda a, c: O.transformer_ddpm(p, a, c.reshape(-1), **kw)
+    with torch.no_grad():
+        state = O.reverse_step(apply_fn, state, 999, coef, z)[0]      # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while n < max_steps and (n == 0 or time.perf_counter() - t0 < min_seconds):
+            state = O.reverse_step(apply_fn, state, 998 - n, coef, z)[0]
+            n += 1
+    dt = time.perf_counter() - t0
+    return n_samples * n / dt, n, dt, n_samples
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample_batch = 16
-    times = []
-    # W warm-up + K timed "steps", each a bounded sample (batch 16 instead of 128) of the train workload
-    for i in range(args.warmup + args.steps):
-        rate, n, dt = cpu_train_step_rate(sample_batch, 0.0, 1, threads)
-        if i >= args.warmup:
-            times.append(dt)
+    threads = host_threads()
+    budget = 150.0                      # seconds for the W + K steps: each step is a bounded sample of the workload
+    job = CpuTrainStep(16, threads)
+    w = job.step()                      # sizing probe (also pays the first-call costs); not reported
+    per_step = budget / max(1, args.warmup + args.steps)
+    while w > per_step and job.batch > 1:
+        job.set_batch(max(1, job.batch // 2))
+        w = job.step()
+    for _ in range(args.warmup):
+        job.step()
+    times = [job.step() for _ in range(args.steps)]
+    sample_batch = job.batch
     ms = 1e3 * float(np.mean(times))
     value = sample_batch / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -136,9 +207,10 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "train ddpm-mel-32seq-512.cfg (TransformerDDPM L6 H8 K2 M2048 C42)",
                        "global_batch": sample_batch, "note": "CPU restatement of the reference path (JAX 0.2.8/flax "
-                       "0.3.0 not installable); each step is a batch-16 sample of the batch-128 train step"},
+                       f"0.3.0 not installable); each step is a batch-{sample_batch} sample of the batch-128 train step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"batch {sample_batch} optimizer steps (fwd+bwd+clip+Adam), torch CPU fp32"},
+                             "sample": f"batch {sample_batch} optimizer steps (fwd+bwd+clip+Adam), torch CPU fp32, "
+                                       f"{threads} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -301,10 +373,16 @@ def run_gpu(args):
                             "kernel": f"gemm_bf16_tcgen05_kernel<{args.cta_group}> [{m_tokens}x2048x2048] res-block GEMM "
                                       "+ bias + row-stat epilogue", "ms_per_launch": g_ms}
         if not args.no_cpu:
-            rate, n, dt = cpu_train_step_rate(16, 10.0, 8, os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"{n} optimizer steps at batch 16 (of the batch-128 train step) in {dt:.1f}s, "
-                                              "torch CPU fp32 restatement of the reference path (JAX unavailable)"}
+            threads = host_threads()
+            if wl == "train":
+                rate, n, dt, sb = cpu_train_step_rate(16, 10.0, 8, threads)
+                what = f"{n} optimizer steps at batch {sb} (of the batch-128 train step)"
+            else:
+                rate, n, dt, sb = cpu_sample_step_rate(32, 10.0, 8, threads)
+                what = f"{n} reverse-diffusion steps over {sb} samples (of the 1000-sample step)"
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{what} in {dt:.1f}s, torch CPU fp32 restatement of the reference path "
+                                              f"(JAX unavailable), {threads} threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
