@@ -95,7 +95,16 @@ int smd_ddpm_loss(smd_plan* plan, const float* params, const float* x0, const fl
  * smd_clip_adam applies global-norm clipping (jax clip_grads), Adam (flax.optim.Adam) and optional EMA. */
 int smd_ddpm_grads(smd_plan* plan, const float* params, const float* x0, const float* used_alpha, const float* eps,
                    int batch, int global_batch, float* grads, float* loss_sum, smd_stream_t stream);
-/* scratch: >= 1024 floats of zero-initialised-by-callee scratch; grad_norm_out[0] = post-clip global L2 norm.
+/* Overlapping the data-parallel exchange with the backward pass (what jax.lax.pmean over the gradient pytree does at
+ * train_ncsn.py:283-284, where XLA is free to schedule the collective early): the gradients of the FiLM'd residual
+ * tail and the output layer -- the contiguous arena slice [*first_float, *first_float + *num_floats), ~85% of all
+ * parameters -- are final long before the transformer trunk's.  After smd_ddpm_grads has been enqueued,
+ * smd_wait_tail_grads makes `stream` (the caller's communication stream) wait until that slice is complete, so its
+ * all-reduce runs under the trunk backward; the rest of the arena is reduced after smd_ddpm_grads' own stream. */
+int smd_grads_tail_range(const smd_plan* plan, long long* first_float, long long* num_floats);
+int smd_wait_tail_grads(smd_plan* plan, smd_stream_t stream);
+/* scratch: >= 1024 floats (per-block partial sums of squares, combined in a fixed order so that all data-parallel
+ * ranks compute bit-identical clip factors); grad_norm_out[0] = post-clip global L2 norm.
  * bf16_shadow_or_null: the plan's bf16 shadow arena (smd_shadow_arena): the updated parameters are also written
  * there in the same pass, after which smd_pack_weights_after_adam (not smd_pack_weights) completes the refresh. */
 int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, float* ema_or_null,

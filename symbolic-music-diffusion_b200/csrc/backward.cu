@@ -258,6 +258,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     launch_small_linear_bwd_w(enc, de1, G(pre + "film.d1.kernel"), batch, 128, 512, side); CNT();
   }
   SMD_CUDA(cudaEventRecord(p->ev_join, side));
+  SMD_CUDA(cudaEventRecord(p->ev_tail, st));   // every k*. / out_ln / out gradient is final (smd_wait_tail_grads)
   SMD_LAUNCH_CHECK("backward tail");
 
   if (ts.L == 0) {

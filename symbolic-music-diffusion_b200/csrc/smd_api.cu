@@ -228,6 +228,7 @@ int ensure_side_stream(smd_plan* p) {
   SMD_CUDA(cudaStreamCreateWithFlags(&p->dw_stream, cudaStreamNonBlocking));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dw, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dwjoin, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming));
   return SMD_OK;
 }
 
@@ -538,6 +539,7 @@ void smd_plan_destroy(smd_plan* plan) {
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
   if (plan->ev_dw) cudaEventDestroy(plan->ev_dw);
   if (plan->ev_dwjoin) cudaEventDestroy(plan->ev_dwjoin);
+  if (plan->ev_tail) cudaEventDestroy(plan->ev_tail);
   if (plan->dw_stream) cudaStreamDestroy(plan->dw_stream);
   if (plan->side_stream) cudaStreamDestroy(plan->side_stream);
   if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
@@ -606,6 +608,23 @@ int smd_pack_weights_after_adam(smd_plan* plan, const float* params, smd_stream_
 }
 
 void* smd_shadow_arena(smd_plan* plan) { return plan->ws ? plan->buf<void>("wshadow") : nullptr; }
+
+int smd_grads_tail_range(const smd_plan* plan, long long* first_float, long long* num_floats) {
+  if (!plan || !first_float || !num_floats) { set_error("null argument"); return SMD_ERR_INVALID; }
+  auto it = plan->off.find("k0.film.d1.kernel");   // first tensor of the FiLM'd tail; out_ln / out follow it
+  if (it == plan->off.end()) { set_error("plan has no FiLM'd residual tail"); return SMD_ERR_STATE; }
+  *first_float = static_cast<long long>(it->second);
+  *num_floats = static_cast<long long>(plan->arena) - *first_float;
+  return SMD_OK;
+}
+
+int smd_wait_tail_grads(smd_plan* plan, smd_stream_t stream) {
+  if (!plan || !plan->ev_tail || !plan->ev_join) { set_error("no smd_ddpm_grads call has been enqueued on this plan"); return SMD_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_tail, 0));   // tail + output-layer gradients (caller's stream)
+  SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));   // FiLM generator gradients (side stream)
+  return SMD_OK;
+}
 
 int smd_forward(smd_plan* plan, const float* params, const float* x, const float* t, int t_broadcast, int batch,
                 float* y, smd_stream_t stream) {

@@ -81,15 +81,28 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x == 0) {
     float v = 0.f;
     for (int j = 0; j < 8; ++j) v += red[j];
-    atomicAdd(out, v);
-  }
+    out[1 + blockIdx.x] = v;   // per-block partial, no atomics: the total is summed in a fixed order by clip_adam_kernel,
+  }                            // so every data-parallel rank derives bit-identical clip factors from identical gradients
 }
+static constexpr int kSumsqBlocks = 1023;   // partials live in scratch[1 .. 1023]; scratch[0] receives the total
 
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  float* __restrict__ ema, __nv_bfloat16* __restrict__ shadow, long long n, float lr, float max_norm, float b1, float b2, float eps,
-                 float bc1, float bc2, float mu, const float* __restrict__ sumsq, float* __restrict__ gnorm_out) {
-  const float norm = sqrtf(*sumsq);
+                 float bc1, float bc2, float mu, float* __restrict__ sumsq, float* __restrict__ gnorm_out) {
+  __shared__ float nred[8];
+  {
+    float part = 0.f;
+    for (int j = threadIdx.x; j < kSumsqBlocks; j += 256) part += sumsq[1 + j];   // fixed order in every block
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) nred[threadIdx.x >> 5] = part;
+    __syncthreads();
+  }
+  float total = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) total += nred[j];
+  if (blockIdx.x == 0 && threadIdx.x == 0) sumsq[0] = total;
+  const float norm = sqrtf(total);
   // jax.experimental.optimizers.clip_grads: g if norm < max else g * (max / norm)
   const float factor = (norm < max_norm) ? 1.0f : (max_norm / norm);
   if (blockIdx.x == 0 && threadIdx.x == 0 && gnorm_out) *gnorm_out = norm * factor;  // post-clip norm (train_ncsn.py:285)
@@ -124,9 +137,8 @@ int smd_clip_adam(float* params, float* grads, float* adam_m, float* adam_v, flo
                   float beta2, float eps, float ema_mu, float* scratch, float* grad_norm_out, smd_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n <= 0 || !scratch) { set_error("bad arguments"); return SMD_ERR_INVALID; }
-  if (cudaMemsetAsync(scratch, 0, sizeof(float), st) != cudaSuccess) { set_error("memset failed"); return SMD_ERR_CUDA; }
   const int blocks = 148 * 8;
-  sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, scratch);
+  sumsq_kernel<<<kSumsqBlocks, 256, 0, st>>>(grads, n, scratch);
   g_launches.fetch_add(1);
   const double t = static_cast<double>(step) + 1.0;
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));

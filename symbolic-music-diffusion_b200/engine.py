@@ -6,6 +6,7 @@ PyTorch is used only as the device-memory / stream provider; all compute goes th
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, asdict
 from typing import Dict, List, Optional, Tuple
 
@@ -66,6 +67,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.lib.smd_plan_create(C.byref(c), C.byref(h)))
         self._plan = h
+        self._comm_stream = None
         self.seq_len = cfg.seq_len if ARCHS[cfg.arch] == 0 else 1
         self.training = bool(training)
         self.layout: List[Tuple[str, int, Tuple[int, ...]]] = []
@@ -243,6 +245,38 @@ class Engine:
         self.loss_sum.zero_()
         self.ddpm_grads(x0, used_alpha, eps, self.grads, self.loss_sum, global_batch)
 
+    def reduce_grads(self, world_size: int, process_group=None) -> None:
+        """SUM all-reduce of the gradient arena and the loss scalar over the data-parallel ranks (call right after
+        compute_grads; the current stream ends up waiting for the reduced gradients)."""
+        if world_size <= 1:
+            return
+        import torch.distributed as dist
+        overlap = self.grads.is_cuda and dist.get_backend(process_group) == "nccl" and \
+            os.environ.get("SMD_DP_OVERLAP", "1") != "0"
+        if overlap:
+            # the tail / output-layer gradients (~85% of the arena) are final before the trunk backward starts:
+            # their all-reduce runs on a communication stream underneath it (include/smd.h: smd_wait_tail_grads)
+            first, count = self.grads_tail_range()
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            with torch.cuda.stream(self._comm_stream):
+                _lib.check(self.lib.smd_wait_tail_grads(self._plan, C.c_void_p(self._comm_stream.cuda_stream)))
+                w_tail = dist.all_reduce(self.grads[first:first + count], op=dist.ReduceOp.SUM, group=process_group,
+                                         async_op=True)
+            w_head = dist.all_reduce(self.grads[:first], op=dist.ReduceOp.SUM, group=process_group, async_op=True)
+            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=process_group)
+            w_head.wait()
+            w_tail.wait()      # the current stream now waits for both reductions
+        else:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=process_group)
+            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=process_group)
+
+    def grads_tail_range(self):
+        """(first_float, num_floats) of the gradient-arena slice that is final after the tail backward."""
+        first, count = C.c_longlong(0), C.c_longlong(0)
+        _lib.check(self.lib.smd_grads_tail_range(self._plan, C.byref(first), C.byref(count)))
+        return int(first.value), int(count.value)
+
     def apply_grads(self, lr: float, grad_clip: float = 1.0, mu: float = 0.999) -> None:
         self.clip_adam(self.grads, self.adam_m, self.adam_v, lr, self.opt_step, grad_clip, self._scratch,
                        self.grad_norm, ema=self.ema_params, mu=mu)
@@ -257,10 +291,7 @@ class Engine:
         Returns (mean loss over the global batch, post-clip grad norm) as device tensors (no host sync)."""
         batch = x0.shape[0]
         self.compute_grads(x0, used_alpha, eps, global_batch=batch * world_size)
-        if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=process_group)
-            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=process_group)
+        self.reduce_grads(world_size, process_group)
         self.apply_grads(lr, grad_clip)
         return self.loss_sum / float(batch * world_size), self.grad_norm
 

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "smd_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "smd_ddpm_loss": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "smd_ddpm_grads": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "smd_grads_tail_range": (C.c_int, [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "smd_wait_tail_grads": (C.c_int, [_P, _P]),
     "smd_pack_weights_after_adam": (C.c_int, [_P, _P, _P]),
     "smd_shadow_arena": (_P, [_P]),
     "smd_clip_adam": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_longlong, C.c_float, C.c_int, C.c_float, C.c_float,

@@ -144,8 +144,7 @@ def train_step(objective, batch, optimizer, sigmas, rng, learning_rate, ema=None
     key = random.split(rng, world)[rank] if world > 1 else rng   # independent noise per shard
     used, eps = eng.draws((int(key[0]), int(key[1])), local)
     eng.compute_grads(x0, used, eps, global_batch=local * world)
-    parallel.all_reduce_sum_(eng.grads)
-    parallel.all_reduce_sum_(eng.loss_sum)
+    eng.reduce_grads(parallel.world_size())     # tail gradients are reduced underneath the trunk backward
     optimizer.apply_gradient(eng.grads, learning_rate=learning_rate, max_norm=FLAGS.grad_clip,
                              ema=None if ema is None else ema.params.flat, mu=FLAGS.mu)
     metrics = {"loss": eng.loss_sum / float(local * world), "grad": optimizer.grad_norm, "lr": learning_rate}
