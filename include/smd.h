@@ -140,6 +140,9 @@ int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int st
 
 /* ---- jax.random (threefry2x32) on device ------------------------------------------------------------------ */
 int smd_threefry_normal(const uint32_t host_key[2], float* out, long long n, smd_stream_t stream);
+/* jax.random.uniform(key, (n,), float32, minval, maxval) as of jax 0.2.8 (sample_ncsn.py:230: the infill initial state) */
+int smd_threefry_uniform(const uint32_t host_key[2], float* out, long long n, float minval, float maxval,
+                         smd_stream_t stream);
 /* host-side split: out_keys = jax.random.split(key, num) (num x 2 uint32) */
 int smd_threefry_split(const uint32_t host_key[2], int num, uint32_t* host_out_keys);
 

@@ -461,6 +461,15 @@ __global__ void ddpm_draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint
   used[i] = fmaxf(minv, __fadd_rn(__fmul_rn(u01, __fsub_rn(maxv, minv)), minv));
 }
 
+// jax.random.uniform (0.2.8): f = bitcast((bits >> 9) | 0x3F800000) - 1; max(minval, f * (maxval - minval) + minval)
+__global__ void threefry_uniform_kernel(uint32_t k0, uint32_t k1, float* out, uint32_t n, float minv, float maxv) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t bits = jax_random_bits(k0, k1, i, n);
+    const float u01 = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+    out[i] = fmaxf(minv, __fadd_rn(__fmul_rn(u01, __fsub_rn(maxv, minv)), minv));
+  }
+}
+
 __global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, i, n));
@@ -902,6 +911,18 @@ int smd_threefry_normal(const uint32_t host_key[2], float* out, long long n, smd
                                                                                 static_cast<uint32_t>(n));
   CNT();
   SMD_LAUNCH_CHECK("threefry_normal");
+  return SMD_OK;
+}
+int smd_threefry_uniform(const uint32_t host_key[2], float* out, long long n, float minval, float maxval,
+                         smd_stream_t stream) {
+  if (n < 0 || n > 0xFFFFFFFFll) { set_error("n out of range"); return SMD_ERR_INVALID; }
+  if (n == 0) return SMD_OK;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  threefry_uniform_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(host_key[0], host_key[1], out,
+                                                                                 static_cast<uint32_t>(n), minval, maxval);
+  CNT();
+  SMD_LAUNCH_CHECK("threefry_uniform");
   return SMD_OK;
 }
 int smd_threefry_split(const uint32_t host_key[2], int num, uint32_t* host_out_keys) {

@@ -1,7 +1,7 @@
 """jax.random (0.2.8, threefry2x32) subset used by the hot path, host side backed by libsmd.
 
 Keys are numpy uint32[2] arrays exactly like ``jax.random.PRNGKey``; ``split`` runs the C++ host threefry in
-libsmd (smd_threefry_split); ``normal`` generates on the GPU (smd_threefry_normal)."""
+libsmd (smd_threefry_split); ``normal`` / ``uniform`` generate on the GPU (smd_threefry_normal / _uniform)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -31,4 +31,14 @@ def normal(key, shape, device=None) -> torch.Tensor:
     out = torch.empty(tuple(shape), dtype=torch.float32, device=device or "cuda")
     k = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
     _lib.check(lib.smd_threefry_normal(k, out.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def uniform(key, shape, minval: float = 0.0, maxval: float = 1.0, device=None) -> torch.Tensor:
+    lib = _lib.load_library()
+    n = int(np.prod(shape))
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=device or "cuda")
+    k = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
+    _lib.check(lib.smd_threefry_uniform(k, out.data_ptr(), n, C.c_float(minval), C.c_float(maxval),
+                                        torch.cuda.current_stream().cuda_stream))
     return out

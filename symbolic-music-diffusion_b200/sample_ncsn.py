@@ -28,8 +28,8 @@ flags.DEFINE_bool("compute_metrics", False, "Compute evaluation metrics (out of 
 flags.DEFINE_bool("compute_final_only", False, "Metrics on the final samples only.")
 flags.DEFINE_bool("flush", True, "Write pickles.")
 flags.DEFINE_bool("animate", False, "Write sampling animations (out of scope).")
-flags.DEFINE_bool("infill", False, "Infill the second half of real examples.")
-flags.DEFINE_bool("interpolate", False, "Interpolation mode (next scope row, SURVEY 8(f3)).")
+flags.DEFINE_bool("infill", False, "Infill the middle 16 latents of real examples (sample_ncsn.py:408-427).")
+flags.DEFINE_bool("interpolate", False, "Interpolate between real examples in the diffusion latent space.")
 
 
 def _restore(model_dir, shape, batch_size=1):
@@ -70,11 +70,45 @@ def infill_samples(samples, masks, rng_seed=1):
     rng, optimizer = _restore(FLAGS.model_dir, samples.shape[1:])
     sigmas = ebm_utils.create_noise_schedule(FLAGS.sigma_begin, FLAGS.sigma_end, FLAGS.num_sigmas, FLAGS.schedule_type)
     init_rng, ld_rng = random.split(rng)
-    init = random.normal(init_rng, samples.shape)
+    init = random.uniform(init_rng, samples.shape)      # upstream initialises the infill chain with uniform noise
     generated, collection, ld_metrics = ebm_utils.diffusion_dynamics(ld_rng, optimizer.target, sigmas, init,
                                                                      FLAGS.ld_epsilon, FLAGS.ld_steps, FLAGS.denoise,
                                                                      True, samples, masks)
     return generated.cpu().numpy(), collection.cpu().numpy(), ebm_utils.collate_sampling_metrics(ld_metrics)
+
+
+def diffusion_stochastic_encoder(samples, rng_seed=1):
+    """sample_ncsn.py:245-265: z ~ q(x_T | x_0).  Upstream indexes ``alphas_prod[T]`` (one past the end), which jax
+    clamps to the last element; the first output of ``split(rng)`` is the noise key."""
+    assert FLAGS.sampling == "ddpm"
+    rng = random.PRNGKey(rng_seed)
+    betas = ebm_utils.create_noise_schedule(FLAGS.sigma_begin, FLAGS.sigma_end, FLAGS.num_sigmas, FLAGS.schedule_type)
+    alphas_prod = np.cumprod((np.float32(1.0) - betas).astype(np.float32), dtype=np.float32)
+    rng, _ = random.split(rng)
+    x = torch.as_tensor(np.ascontiguousarray(samples, np.float32), device="cuda")
+    noise = random.normal(rng, x.shape)
+    last = alphas_prod[-1]                        # alphas_prod[T] clamped
+    return float(np.sqrt(last)) * x + float(np.sqrt(np.float32(1.0) - last)) * noise
+
+
+def diffusion_decoder(z_list, rng_seed=1):
+    """sample_ncsn.py:268-310: one reverse chain per latent, all with the same sampling key."""
+    assert FLAGS.sampling == "ddpm"
+    rng = random.PRNGKey(rng_seed)
+    rng, ld_rng, model_rng = random.split(rng, 3)
+    del model_rng
+    betas = ebm_utils.create_noise_schedule(FLAGS.sigma_begin, FLAGS.sigma_end, FLAGS.num_sigmas, FLAGS.schedule_type)
+    _, optimizer = _restore(FLAGS.model_dir, tuple(z_list[0].shape[1:]))
+    gen, collects, metrics = [], [], []
+    for i, z in enumerate(z_list):
+        generated, collection, ld_metrics = ebm_utils.diffusion_dynamics(ld_rng, optimizer.target, betas, z,
+                                                                         FLAGS.ld_epsilon, FLAGS.ld_steps, FLAGS.denoise,
+                                                                         False)
+        gen.append(generated.cpu().numpy())
+        collects.append(collection.cpu().numpy())
+        metrics.append(ebm_utils.collate_sampling_metrics(ld_metrics))
+        logging.info("Generated samples %i out of %i", i, len(z_list))
+    return gen, collects, metrics
 
 
 def _save(obj, path):
@@ -87,8 +121,6 @@ def _save(obj, path):
 def main(argv):
     del argv
     parallel.init_from_env()
-    if FLAGS.interpolate:
-        raise ValueError("--interpolate is the next scope row (SURVEY 8(f3)); not built yet")
     if FLAGS.compute_metrics or FLAGS.animate:
         raise ValueError("--compute_metrics / --animate depend on note_seq / matplotlib code that is out of scope")
     _, eval_ds = input_pipeline.get_dataset(
@@ -103,10 +135,23 @@ def main(argv):
             break
     real = np.concatenate(real)[:FLAGS.sample_size]
     shape = real.shape[1:]
-    if FLAGS.infill:
-        masks = np.zeros_like(real)
-        masks[:, : real.shape[1] // 2] = 1.0
-        generated, collection, _ = infill_samples(real, masks, FLAGS.sample_seed)
+    if FLAGS.infill:                                       # sample_ncsn.py:408-427 (sequence branch)
+        if real.ndim != 3 or real.shape[1] != 32:
+            raise ValueError("--infill needs (N, 32, C) latent sequences")
+        samples = np.copy(real)
+        samples[:, 8:-8, :] = 0                            # the middle 16 latents are regenerated
+        masks = np.zeros(samples.shape, np.float32)
+        masks[:, :8, :] = 1
+        masks[:, -8:, :] = 1                               # first and last 8 are held fixed
+        generated, collection, _ = infill_samples(samples, masks, FLAGS.sample_seed)
+    elif FLAGS.interpolate:                                # sample_ncsn.py:429-438
+        starts = real
+        goals = np.roll(starts, shift=1, axis=0)
+        starts_z = diffusion_stochastic_encoder(starts, FLAGS.sample_seed)
+        goals_z = diffusion_stochastic_encoder(goals, FLAGS.sample_seed)
+        interp_zs = [float(1 - alpha) * starts_z + float(alpha) * goals_z for alpha in np.linspace(0.0, 1.0, 9)]
+        gen, coll, _ = diffusion_decoder(interp_zs, FLAGS.sample_seed)
+        generated, collection = np.stack(gen), np.stack(coll)
     else:
         generated, collection, _ = generate_samples(shape, len(real), FLAGS.sample_seed)
     if FLAGS.flush and parallel.rank() == 0:

@@ -88,3 +88,26 @@ def test_train_and_sample_cli_synthetic(tmp_path):
     real = pickle.load(open(out / "real.pkl", "rb"))
     assert gen.shape == (16, 32, 42) and real.shape == (16, 32, 42) and coll.shape == (41, 16, 32, 42)
     assert np.isfinite(gen).all()
+    # --infill (sample_ncsn.py:408-427): the first and last 8 latents of every sequence are held fixed
+    r = subprocess.run([sys.executable, "-m", "smd_b200.sample_ncsn", f"--flagfile={cfg}", "--sample_size=8", "--infill",
+                        "--sampling_dir=infill"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = tmp_path / "run" / "infill" / "ncsn"
+    gen = pickle.load(open(out / "generated.pkl", "rb"))
+    real = pickle.load(open(out / "real.pkl", "rb"))
+    assert gen.shape == (8, 32, 42) and np.isfinite(gen).all()
+    np.testing.assert_allclose(gen[:, :8], real[:, :8], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(gen[:, -8:], real[:, -8:], rtol=0, atol=1e-5)
+    assert np.abs(gen[:, 8:-8] - real[:, 8:-8]).max() > 1e-3
+    # --interpolate (sample_ncsn.py:429-438): 9 latent mixtures between each example and its neighbour
+    r = subprocess.run([sys.executable, "-m", "smd_b200.sample_ncsn", f"--flagfile={cfg}", "--sample_size=4",
+                        "--interpolate", "--sampling_dir=interp"], capture_output=True, text=True, timeout=600, env=env,
+                       cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = tmp_path / "run" / "interp" / "ncsn"
+    gen = pickle.load(open(out / "generated.pkl", "rb"))
+    coll = pickle.load(open(out / "collection.pkl", "rb"))
+    assert gen.shape == (9, 4, 32, 42) and coll.shape == (9, 41, 4, 32, 42) and np.isfinite(gen).all()
+    assert np.abs(gen[0] - gen[8]).max() > 1e-3          # the two end points decode different latents
+    # neighbouring mixtures stay closer to each other than the end points do (same sampling key for every chain)
+    assert np.abs(gen[4] - gen[5]).mean() < np.abs(gen[0] - gen[8]).mean()

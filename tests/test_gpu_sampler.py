@@ -108,3 +108,14 @@ def test_short_chain_with_device_rng(lib, use_graph):
     for i, t in enumerate(range(999, 993, -1)):
         if slots[t] >= 0:
             assert rel_l2(coll[slots[t]], ref_coll[slots[t]]) < 1e-2
+
+
+@pytest.mark.parametrize("n,lo,hi", [(7, 0.0, 1.0), (4096, -1.0, 1.0), (1000 * 32 * 42 + 1, 0.25, 0.75)])
+def test_device_threefry_uniform_matches_jax_restatement(lib, n, lo, hi):
+    """jax.random.uniform (0.2.8) -- the infill chain's initial state (sample_ncsn.py:230) -- bit-exact."""
+    from oracle import threefry as T
+    from smd_b200 import jrandom
+    key = jrandom.PRNGKey(11)
+    got = jrandom.uniform(key, (n,), lo, hi).cpu().numpy()
+    ref = T.uniform(np.asarray(key, np.uint32), (n,), lo, hi)
+    assert got.dtype == np.float32 and np.array_equal(got, ref)
