@@ -231,13 +231,15 @@ class Engine:
             raise _lib.SmdError("set_params() first")
         dev = self.params.device
         n = self.arena_floats
-        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        # the loss accumulator sits right behind the gradient arena so that one collective reduces both
+        self._grads_buf = torch.zeros(n + 8, dtype=torch.float32, device=dev)
+        self.grads = self._grads_buf[:n]
         self.adam_m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.adam_v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.ema_params = self.params.clone() if ema else None
         self._scratch = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_sum = self._grads_buf[n:n + 1]
         self.opt_step = 0
 
     def compute_grads(self, x0, used_alpha, eps, global_batch: Optional[int] = None) -> None:
@@ -261,15 +263,14 @@ class Engine:
                 self._comm_stream = torch.cuda.Stream()
             with torch.cuda.stream(self._comm_stream):
                 _lib.check(self.lib.smd_wait_tail_grads(self._plan, C.c_void_p(self._comm_stream.cuda_stream)))
-                w_tail = dist.all_reduce(self.grads[first:first + count], op=dist.ReduceOp.SUM, group=process_group,
-                                         async_op=True)
+                # + 1: the loss sum stored behind the arena rides along (it is final long before the tail gradients)
+                w_tail = dist.all_reduce(self._grads_buf[first:first + count + 1], op=dist.ReduceOp.SUM,
+                                         group=process_group, async_op=True)
             w_head = dist.all_reduce(self.grads[:first], op=dist.ReduceOp.SUM, group=process_group, async_op=True)
-            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=process_group)
             w_head.wait()
             w_tail.wait()      # the current stream now waits for both reductions
         else:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=process_group)
-            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=process_group)
+            dist.all_reduce(self._grads_buf[:self.grads.numel() + 1], op=dist.ReduceOp.SUM, group=process_group)
 
     def grads_tail_range(self):
         """(first_float, num_floats) of the gradient-arena slice that is final after the tail backward."""
