@@ -374,7 +374,7 @@ def run_gpu(args):
                                       "+ bias + row-stat epilogue", "ms_per_launch": g_ms}
         if not args.no_cpu:
             threads = host_threads()
-            if wl == "train":
+            if args.workload == "train":
                 rate, n, dt, sb = cpu_train_step_rate(16, 10.0, 8, threads)
                 what = f"{n} optimizer steps at batch {sb} (of the batch-128 train step)"
             else:
