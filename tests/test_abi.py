@@ -63,3 +63,16 @@ def test_host_threefry_split_matches_oracle(lib):
     out = (ctypes.c_uint32 * 6)()
     assert lib.smd_threefry_split(key, 3, out) == 0
     np.testing.assert_array_equal(np.array(list(out), np.uint32).reshape(3, 2), tf.split(tf.prng_key(0), 3))
+
+
+def test_tail_gradient_slice_is_the_film_tail_and_output_layer(lib):
+    """smd_grads_tail_range: the contiguous arena slice that is final after the tail backward (data-parallel overlap)."""
+    for cfg in (ModelConfig(channels=42), ModelConfig(arch="DenseDDPM", num_layers=3, channels=512)):
+        eng = Engine(cfg, max_batch=4, training=True)
+        first, count = eng.grads_tail_range()
+        offs = {n: off for n, off, _ in eng.layout}
+        assert first == offs["k0.film.d1.kernel"] and first + count == eng.arena_floats
+        inside = [n for n, off, _ in eng.layout if off >= first]
+        assert all(n.startswith(("k", "out_ln.", "out.")) for n in inside) and "out.bias" in inside
+        assert not any(n.startswith(("k", "out")) for n, off, _ in eng.layout if off < first)
+        assert count > 0.8 * eng.arena_floats           # ~85% of the parameters live in the FiLM'd tail

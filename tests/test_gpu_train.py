@@ -148,3 +148,28 @@ def test_device_draws_match_jax_restatement(lib):
         np.testing.assert_array_equal(labels.cpu().numpy(), rl)
         np.testing.assert_array_equal(used.cpu().numpy(), ru)           # == abar[l-1]
         np.testing.assert_allclose(eps.cpu().numpy(), re, rtol=2e-5, atol=2e-6)
+
+
+def test_tail_gradients_are_final_at_the_tail_event(lib):
+    """smd_wait_tail_grads: a second stream that waits on it sees the final tail slice while the trunk backward is
+    still in flight on the main stream (what the overlapped all-reduce relies on)."""
+    import ctypes as C
+    from smd_b200 import Engine, ModelConfig
+    from smd_b200 import lib as L
+    kw, arch, batch = CASES["base2"]
+    eng = Engine(ModelConfig(arch=arch, **kw), max_batch=batch, cta_group=2, training=True)
+    eng.set_params(eng.init_params(seed=2, perturb=0.05))
+    eng.init_train_state()
+    shape = (32, kw["channels"])
+    x0, used, eps = _draws(batch, shape)
+    first, count = eng.grads_tail_range()
+    side = torch.cuda.Stream()
+    snap = torch.empty(count, dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        eng.compute_grads(torch.from_numpy(x0).cuda(), torch.from_numpy(used).cuda(), torch.from_numpy(eps).cuda())
+        with torch.cuda.stream(side):
+            L.check(eng.lib.smd_wait_tail_grads(eng._plan, C.c_void_p(side.cuda_stream)))
+            snap.copy_(eng.grads[first:first + count], non_blocking=True)
+        torch.cuda.synchronize()
+        assert torch.equal(snap, eng.grads[first:first + count])
+        assert float(eng.grads[:first].abs().sum()) > 0
