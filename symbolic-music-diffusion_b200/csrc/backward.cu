@@ -54,10 +54,10 @@ int train_bind(smd_plan* p) {
   ts.dWss.resize(ts.K); ts.dXss.resize(ts.K);
   const uint64_t Bp = (static_cast<uint64_t>(c.max_batch) + 127) / 128 * 128;
   for (int k = 0; k < ts.K; ++k) {
-    if (!make_dw(&ts.dWb[k], ts.act_b(ws, k), Md, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXb[k], B16(ts.off_g16a), Md, Wsh(KN(k) + "res.b.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
-    if (!make_dw(&ts.dWa[k], ts.act_a(ws, k), Md, B16(ts.off_g16b), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXa[k], B16(ts.off_g16b), Md, Wsh(KN(k) + "res.a.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dw(&ts.dWb[k], ts.act_b(ws, k), Md, B16(ts.off_du16[k + 1]), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXb[k], B16(ts.off_du16[k + 1]), Md, Wsh(KN(k) + "res.b.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dw(&ts.dWa[k], ts.act_a(ws, k), Md, B16(ts.off_dr16t[k]), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXa[k], B16(ts.off_dr16t[k]), Md, Wsh(KN(k) + "res.a.kernel"), Md, Mp, cg)) return SMD_ERR_CUDA;
     if (!make_dw(&ts.dWss[k], B16(ts.off_e2_16), 512, B16(ts.off_dss16), 2 * Md, 2 * Md, Bp, 1)) return SMD_ERR_CUDA;
     if (!make_dx(&ts.dXss[k], B16(ts.off_dss16), 2 * Md, Wsh(KN(k) + "film.ss.kernel"), 512, Bp, 1)) return SMD_ERR_CUDA;
   }
@@ -68,8 +68,8 @@ int train_bind(smd_plan* p) {
   if (!make_gemm_op(&ts.dXout, B16(ts.off_dpred16), Mp, p->buf<__nv_bfloat16>("w.out_pad"), static_cast<uint64_t>(Md), Md, Cp,
                     choose_bn(Md, cg), cg, 0, 0)) return SMD_ERR_CUDA;
   if (ts.L > 0) {
-    if (!make_dw(&ts.dWpost, ts.a_post(ws), 128, B16(ts.off_g16a), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
-    if (!make_dx(&ts.dXpost, B16(ts.off_g16a), Md, Wsh("post.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dw(&ts.dWpost, ts.a_post(ws), 128, B16(ts.off_du16[0]), Md, Md, Mp, 1)) return SMD_ERR_CUDA;
+    if (!make_dx(&ts.dXpost, B16(ts.off_du16[0]), Md, Wsh("post.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
     ts.dW2.resize(ts.L); ts.dX2.resize(ts.L); ts.dW1.resize(ts.L); ts.dX1.resize(ts.L);
     ts.dWo.resize(ts.L); ts.dXo.resize(ts.L); ts.dWqkv.resize(ts.L); ts.dXqkv.resize(ts.L);
     for (int l = 0; l < ts.L; ++l) {
@@ -84,7 +84,7 @@ int train_bind(smd_plan* p) {
       if (!make_dx(&ts.dXqkv[l], B16(ts.off_dqkv16[l]), 384, Wsh(LN(l) + "attn.qkv.kernel"), 128, Mp, cg)) return SMD_ERR_CUDA;
     }
   } else {
-    if (!make_dw(&ts.dWin, p->buf<__nv_bfloat16>("xb"), C, B16(ts.off_g16a), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
+    if (!make_dw(&ts.dWin, p->buf<__nv_bfloat16>("xb"), C, B16(ts.off_du16[0]), Md, Md, Mp, cg)) return SMD_ERR_CUDA;
   }
   return SMD_OK;
 }
@@ -126,8 +126,8 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
                            sizeof(float) * static_cast<size_t>(ts.K > 0 ? ts.K : 1) * c.max_batch * 2 * Md, st));
   if (Mk != M) {  // zero the reduction-tail rows of every MN-major gradient operand
     const size_t tail = static_cast<size_t>(Mk - M);
-    SMD_CUDA(cudaMemsetAsync(B16(ts.off_g16a) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
-    SMD_CUDA(cudaMemsetAsync(B16(ts.off_g16b) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
+    for (size_t off : ts.off_du16) SMD_CUDA(cudaMemsetAsync(B16(off) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
+    for (size_t off : ts.off_dr16t) SMD_CUDA(cudaMemsetAsync(B16(off) + static_cast<size_t>(M) * Md, 0, tail * Md * 2, st));
     for (int l = 0; l < ts.L; ++l) {
       SMD_CUDA(cudaMemsetAsync(B16(ts.off_dh16a[l]) + static_cast<size_t>(M) * 128, 0, tail * 128 * 2, st));
       SMD_CUDA(cudaMemsetAsync(B16(ts.off_dh16b[l]) + static_cast<size_t>(M) * 128, 0, tail * 128 * 2, st));
@@ -162,8 +162,6 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   // dX GEMM outputs (gradient wrt a bf16 activation), stored as bf16: half the epilogue / LayerNorm-backward bytes
   __nv_bfloat16* g16 = B16(ts.off_g32a);
   float* du32 = F32(ts.off_g32b);   // gradient of the fp32 residual stream u
-  __nv_bfloat16* du16 = B16(ts.off_g16a);
-  __nv_bfloat16* dr16 = B16(ts.off_g16b);
   float* stats = p->buf<float>("stats");
   const size_t sstride = static_cast<size_t>(p->Mp) * 2;
   const int nkb = Mk / 64;
@@ -182,7 +180,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     memset(&a, 0, sizeof(a));
     a.g16 = g16; a.u = ts.u(ws, ts.K); a.stats = stats + (2 * ts.K) * sstride;
     a.gamma = p->P(params, "out_ln.scale"); a.beta = p->P(params, "out_ln.bias");
-    a.dx32 = du32; a.dx16 = du16;
+    a.dx32 = du32; a.dx16 = B16(ts.off_du16[ts.K]);
     a.dgamma = G("out_ln.scale"); a.dbeta = G("out_ln.bias");
     a.dbias = G("k" + std::to_string(ts.K - 1) + ".res.b.bias");
     a.M = M; a.N = Md; a.S = S;
@@ -194,13 +192,22 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   float* dss_all = F32(ts.off_dss);
   { int rcs = ensure_side_stream(p); if (rcs) return rcs; }
   cudaStream_t side = p->side_stream;
+  cudaStream_t dws = p->dw_stream;
+  // Weight-gradient GEMMs are leaves of the backward graph: they run on dw_stream next to the dX chain; every gradient
+  // operand they read has its own buffer, so nothing they read is rewritten within this backward pass.
+  auto fork_dw = [&]() -> cudaError_t {
+    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
+    if (e1 != cudaSuccess) return e1;
+    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
+  };
   for (int k = ts.K - 1; k >= 0; --k) {
     const std::string pre = "k" + std::to_string(k) + ".";
     const float* ss_k = ssbuf + static_cast<size_t>(k) * c.max_batch * 2 * Md;
     float* dss = dss_all + static_cast<size_t>(k) * c.max_batch * 2 * Md;
+    SMD_CUDA(fork_dw());
     GemmEpilogue e = epi();
     e.out_f32 = G(pre + "res.b.kernel"); e.ld_f32 = Md;
-    SMD_CUDA(gemm_k(ts.dWb[k], Md, Mk, 1, e, st));
+    SMD_CUDA(gemm_k(ts.dWb[k], Md, Mk, 1, e, dws));
     e = epi();
     e.out_bf16 = g16; e.ld_bf16 = Md;
     SMD_CUDA(launch_gemm(ts.dXb[k], M, e, st));
@@ -209,15 +216,16 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     a.g16 = g16; a.u16 = reinterpret_cast<const __nv_bfloat16*>(ts.r1(ws, k)); a.stats = stats + (2 * k + 1) * sstride;
     a.gamma = p->P(params, pre + "res.ln_b.scale"); a.beta = p->P(params, pre + "res.ln_b.bias");
     a.ss = ss_k; a.act = 2;
-    a.dx32 = nullptr; a.dx16 = dr16;   // dr1 is only consumed as a bf16 GEMM operand (and its column sums)
+    a.dx32 = nullptr; a.dx16 = B16(ts.off_dr16t[k]);   // dr1 is only consumed as a bf16 GEMM operand
     a.dgamma = G(pre + "res.ln_b.scale"); a.dbeta = G(pre + "res.ln_b.bias");
     a.dbias = G(pre + "res.a.bias");
     a.dss = dss; a.dss_accum = 0;
     a.M = M; a.N = Md; a.S = S;
     launch_ln_film_act_bwd(a, st); CNT();
+    SMD_CUDA(fork_dw());
     e = epi();
     e.out_f32 = G(pre + "res.a.kernel"); e.ld_f32 = Md;
-    SMD_CUDA(gemm_k(ts.dWa[k], Md, Mk, 1, e, st));
+    SMD_CUDA(gemm_k(ts.dWa[k], Md, Mk, 1, e, dws));
     e = epi();
     e.out_bf16 = g16; e.ld_bf16 = Md;
     SMD_CUDA(launch_gemm(ts.dXa[k], M, e, st));
@@ -225,7 +233,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     a.g16 = g16; a.u = ts.u(ws, k); a.stats = stats + (2 * k) * sstride;
     a.gamma = p->P(params, pre + "res.ln_a.scale"); a.beta = p->P(params, pre + "res.ln_a.bias");
     a.ss = ss_k; a.act = 2;
-    a.dres = du32; a.dx32 = du32; a.dx16 = du16;
+    a.dres = du32; a.dx32 = du32; a.dx16 = B16(ts.off_du16[k]);
     a.dgamma = G(pre + "res.ln_a.scale"); a.dbeta = G(pre + "res.ln_a.bias");
     a.dbias = (k > 0) ? G("k" + std::to_string(k - 1) + ".res.b.bias") : G(ts.L ? "post.bias" : "in.bias");
     a.dss = dss; a.dss_accum = 1;
@@ -259,6 +267,7 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   }
   SMD_CUDA(cudaEventRecord(p->ev_join, side));
   SMD_CUDA(cudaEventRecord(p->ev_tail, st));   // every k*. / out_ln / out gradient is final (smd_wait_tail_grads)
+  SMD_CUDA(cudaEventRecord(p->ev_dwtail, dws));
   SMD_LAUNCH_CHECK("backward tail");
 
   if (ts.L == 0) {
@@ -266,6 +275,8 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     GemmEpilogue e = epi();
     e.out_f32 = G("in.kernel"); e.ld_f32 = Md;
     SMD_CUDA(gemm_k(ts.dWin, C, Mk, 1, e, st));
+    SMD_CUDA(cudaEventRecord(p->ev_dwjoin, dws));
+    SMD_CUDA(cudaStreamWaitEvent(st, p->ev_dwjoin, 0));
     SMD_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     SMD_LAUNCH_CHECK("backward dense");
     return SMD_OK;
@@ -274,14 +285,8 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   // ---------------- post dense + post LayerNorm ----------------
   float* da32 = F32(ts.off_dh2);
   float* dh32 = F32(ts.off_dh);
-  cudaStream_t dws = p->dw_stream;
-  // Weight-gradient GEMMs and bias column sums of the trunk are leaves of the backward graph: they run on
-  // dw_stream with a reduced CTA count while the dX chain (the critical path, mostly 32-CTA launches) keeps `st`.
-  auto fork_dw = [&]() -> cudaError_t {
-    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
-    if (e1 != cudaSuccess) return e1;
-    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
-  };
+  // (the trunk's weight-gradient GEMMs and bias column sums go to dw_stream as well, with a reduced CTA count, while
+  // the dX chain -- the critical path, mostly 32-CTA launches -- keeps `st`)
   {
     GemmEpilogue e = epi();
     e.out_f32 = G("post.kernel"); e.ld_f32 = Md;

@@ -96,7 +96,7 @@ struct smd_plan {
   // training: the FiLM generator (forward and backward) runs on a side stream, concurrently with the trunk
   cudaStream_t side_stream = nullptr;   // FiLM generator forward / backward
   cudaStream_t dw_stream = nullptr;     // trunk weight-gradient GEMMs (leaves of the backward graph)
-  cudaEvent_t ev_fork = nullptr, ev_film = nullptr, ev_dss = nullptr, ev_join = nullptr, ev_dw = nullptr, ev_dwjoin = nullptr, ev_tail = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_film = nullptr, ev_dss = nullptr, ev_join = nullptr, ev_dw = nullptr, ev_dwjoin = nullptr, ev_tail = nullptr, ev_dwtail = nullptr;
   smd::TrainState train;
 
   template <typename Tp>

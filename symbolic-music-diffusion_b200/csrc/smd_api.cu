@@ -229,6 +229,7 @@ int ensure_side_stream(smd_plan* p) {
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dw, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dwjoin, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dwtail, cudaEventDisableTiming));
   return SMD_OK;
 }
 
@@ -549,6 +550,7 @@ void smd_plan_destroy(smd_plan* plan) {
   if (plan->ev_dw) cudaEventDestroy(plan->ev_dw);
   if (plan->ev_dwjoin) cudaEventDestroy(plan->ev_dwjoin);
   if (plan->ev_tail) cudaEventDestroy(plan->ev_tail);
+  if (plan->ev_dwtail) cudaEventDestroy(plan->ev_dwtail);
   if (plan->dw_stream) cudaStreamDestroy(plan->dw_stream);
   if (plan->side_stream) cudaStreamDestroy(plan->side_stream);
   if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
@@ -632,6 +634,7 @@ int smd_wait_tail_grads(smd_plan* plan, smd_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_tail, 0));   // tail + output-layer gradients (caller's stream)
   SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));   // FiLM generator gradients (side stream)
+  SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_dwtail, 0)); // res-block weight gradients (weight-gradient stream)
   return SMD_OK;
 }
 

@@ -37,8 +37,8 @@ void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
   ts.off_act_out = add("t.act_out", M * Md * 2);
   ts.off_g32a = add("t.g32a", M * Md * 4);
   ts.off_g32b = add("t.g32b", M * Md * 4);
-  ts.off_g16a = add("t.g16a", M * Md * 2);
-  ts.off_g16b = add("t.g16b", M * Md * 2);
+  for (int k = 0; k < K + 1; ++k) ts.off_du16.push_back(add(nm("du16_", k), M * Md * 2));
+  for (int k = 0; k < K; ++k) ts.off_dr16t.push_back(add(nm("dr16t_", k), M * Md * 2));
   ts.off_dh = add("t.dh", M * kEt * 4);
   ts.off_dh2 = add("t.dh2", M * kEt * 4);
   for (int l = 0; l < ts.L; ++l) {

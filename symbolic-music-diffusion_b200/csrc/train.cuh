@@ -33,7 +33,9 @@ struct TrainState {
   std::vector<size_t> off_e1pre, off_e1, off_e2;  // fp32 [B][512] x K
   // backward scratch
   size_t off_g32a = 0, off_g32b = 0;   // fp32 [Mp][Md] gradient ping-pong (tail) -- also used [Mp][128]-wide in the trunk
-  size_t off_g16a = 0, off_g16b = 0;   // bf16 [Mp][Md]
+  // bf16 gradient operands of the tail, one buffer per use (their dW GEMMs run on the weight-gradient stream):
+  std::vector<size_t> off_du16;        // bf16 [Mp][Md] x (K+1): gradient wrt the residual stream u_j entering block j
+  std::vector<size_t> off_dr16t;       // bf16 [Mp][Md] x K: gradient wrt r1 (after LayerNorm-b backward)
   size_t off_dh = 0, off_dh2 = 0;      // fp32 [Mp][128]
   // per-layer bf16 gradient operands: the dW GEMMs that read them run on their own stream, so no buffer is
   // rewritten within one backward pass
