@@ -425,7 +425,7 @@ inline void launch_ln_film_act_bwd(const LnFilmBwdArgs& a, cudaStream_t st) {
 #define SMD_LNB_FAST(U, R, F)                                                                               \
   {                                                                                                          \
     cudaFuncSetAttribute(ln_film_bwd_fast_kernel<U, R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    launch_pdl(ln_film_bwd_fast_kernel<U, R, F>, dim3(fb), dim3(threads), smem, st, a);                                          \
+    launch_pdl_g(kPdlLnFilmBwd, ln_film_bwd_fast_kernel<U, R, F>, dim3(fb), dim3(threads), smem, st, a);                                          \
   }
     switch (key) {
       case 0: SMD_LNB_FAST(false, false, false) break;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) ln128_bwd_kernel(const Ln128BwdArgs a) {
 inline void launch_ln128_bwd(const Ln128BwdArgs& a, cudaStream_t st) {
   int blocks = (a.M + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;
-  launch_pdl(ln128_bwd_kernel, dim3(blocks), dim3(256), 0, st, a);
+  launch_pdl_g(kPdlLn128, ln128_bwd_kernel, dim3(blocks), dim3(256), 0, st, a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -933,7 +933,7 @@ inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, co
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                          static_cast<int>(sm2));                                                    \
     if (e != cudaSuccess) return e;                                                                                 \
-    return launch_pdl(attention_bwd_mma_kernel<DHV>, grid, dim3(hpb * 32), sm2, st, qkv, probs, dO, dqkv16, dbias, H); \
+    return launch_pdl_g(kPdlAttention, attention_bwd_mma_kernel<DHV>, grid, dim3(hpb * 32), sm2, st, qkv, probs, dO, dqkv16, dbias, H); \
   }
     if (dh == 16) SMD_ATT_BWD_MMA(16)
     else if (dh == 8) SMD_ATT_BWD_MMA(8)
@@ -945,7 +945,7 @@ inline cudaError_t launch_attention_bwd(const float* qkv, const float* probs, co
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          static_cast<int>(smem));                                              \
     if (e != cudaSuccess) return e;                                                                            \
-    launch_pdl(attention_bwd_kernel<DHV>, dim3(grid), dim3(hpb * 32), smem, st, qkv, probs, dO, dqkv16, dbias, H);                       \
+    launch_pdl_g(kPdlAttention, attention_bwd_kernel<DHV>, dim3(grid), dim3(hpb * 32), smem, st, qkv, probs, dO, dqkv16, dbias, H);                       \
   }
   if (dh == 16) SMD_ATT_BWD(16)
   else if (dh == 8) SMD_ATT_BWD(8)
@@ -1005,7 +1005,7 @@ embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dh, floa
   }
 }
 inline void launch_embed_bwd(const float* x, const float* dh, float* dW, int M, int C, cudaStream_t st) {
-  launch_pdl(embed_bwd_kernel, dim3((M + 127) / 128), dim3(256), 0, st, x, dh, dW, M, C);
+  launch_pdl_g(kPdlMisc, embed_bwd_kernel, dim3((M + 127) / 128), dim3(256), 0, st, x, dh, dW, M, C);
 }
 
 // small fp32 linear layers of the FiLM generator: weight gradient and input gradient (tiled SGEMM, kernels.cu)

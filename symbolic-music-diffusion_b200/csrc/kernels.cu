@@ -27,7 +27,7 @@ void launch_q_sample(const float* x0, const float* eps, const float* used_alpha,
   const size_t total = static_cast<size_t>(B) * per_sample;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl(q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample);
+  launch_pdl_g(kPdlMisc, q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -78,7 +78,7 @@ embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const flo
 void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
                   const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st) {
   const int blocks = (M + 7) / 8;
-  launch_pdl(embed_kernel, dim3(blocks), dim3(256), 0, st, x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S);
+  launch_pdl_g(kPdlMisc, embed_kernel, dim3(blocks), dim3(256), 0, st, x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -305,7 +305,7 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
       cudaFuncSetAttribute(attention_mma_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 132 * 4); \
       attr = true;                                                                                                \
     }                                                                                                             \
-    launch_pdl(attention_mma_kernel<DHV>, grid, dim3(threads), smem, st, qkv, o, probs_or_null, B, H);            \
+    launch_pdl_g(kPdlAttention, attention_mma_kernel<DHV>, grid, dim3(threads), smem, st, qkv, o, probs_or_null, B, H);            \
   }
     if (dh == 16) SMD_ATT_MMA(16)
     else if (dh == 8) SMD_ATT_MMA(8)
@@ -313,10 +313,10 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 #undef SMD_ATT_MMA
     return;
   }
-  if (dh == 16) launch_pdl(attention_kernel<16>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
-  else if (dh == 8) launch_pdl(attention_kernel<8>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
-  else if (dh == 32) launch_pdl(attention_kernel<32>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
-  else if (dh == 4) launch_pdl(attention_kernel<4>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  if (dh == 16) launch_pdl_g(kPdlAttention, attention_kernel<16>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  else if (dh == 8) launch_pdl_g(kPdlAttention, attention_kernel<8>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  else if (dh == 32) launch_pdl_g(kPdlAttention, attention_kernel<32>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  else if (dh == 4) launch_pdl_g(kPdlAttention, attention_kernel<4>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -457,7 +457,7 @@ void launch_ln_film_act(const float* u, const float* stats, const float* g, cons
       cudaFuncSetAttribute(ln_film_act_kernel<MAXT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 * 4 + 64); \
       attr = true;                                                                                               \
     }                                                                                                            \
-    launch_pdl(ln_film_act_kernel<MAXT, BF>, dim3(blocks), dim3(threads), smem, st, in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
+    launch_pdl_g(kPdlLnFilmFwd, ln_film_act_kernel<MAXT, BF>, dim3(blocks), dim3(threads), smem, st, in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
                                                                 out, M, N, S, film_row_dev);                     \
   }
   if (threads <= 512) {
@@ -715,7 +715,7 @@ reverse_step_kernel(const ReverseStepArgs a) {
 }
 void launch_reverse_step(const ReverseStepArgs& a, cudaStream_t st) {
   const int NC = a.N * a.C;
-  launch_pdl(reverse_step_kernel, dim3((NC + 255) / 256), dim3(256), 0, st, a);
+  launch_pdl_g(kPdlMisc, reverse_step_kernel, dim3((NC + 255) / 256), dim3(256), 0, st, a);
 }
 __global__ void step_advance_kernel(int* t_ptr) { *t_ptr -= 1; }
 void launch_step_advance(int* t_ptr, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(t_ptr); }
@@ -726,7 +726,7 @@ __global__ void fill_cond_kernel(const float* coef, const int* t_ptr, float* con
   if (i < n) cond[i] = coef[8 * (*t_ptr) + 5];
 }
 void launch_fill_cond(const float* coef, const int* t_ptr, float* cond, int n, cudaStream_t st) {
-  launch_pdl(fill_cond_kernel, dim3((n + 255) / 256), dim3(256), 0, st, coef, t_ptr, cond, n);
+  launch_pdl_g(kPdlMisc, fill_cond_kernel, dim3((n + 255) / 256), dim3(256), 0, st, coef, t_ptr, cond, n);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -757,7 +757,7 @@ ddpm_loss_kernel(const float* __restrict__ eps, const float* __restrict__ pred, 
 }
 void launch_ddpm_loss(const float* eps, const float* pred, float* loss_per_example, float* dpred_or_null,
                       float gscale, int B, int per_sample, cudaStream_t st) {
-  launch_pdl(ddpm_loss_kernel, dim3(B), dim3(256), 0, st, eps, pred, loss_per_example, dpred_or_null, gscale, per_sample);
+  launch_pdl_g(kPdlMisc, ddpm_loss_kernel, dim3(B), dim3(256), 0, st, eps, pred, loss_per_example, dpred_or_null, gscale, per_sample);
 }
 
 }  // namespace smd
