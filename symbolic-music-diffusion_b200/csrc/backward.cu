@@ -7,15 +7,6 @@
 
 namespace smd {
 
-static int pick_splits(int m_rows, int n_cols, int BN, int cg, int num_kb) {
-  const int tiles = ((m_rows + 128 * cg - 1) / (128 * cg)) * ((n_cols + BN - 1) / BN);
-  if (tiles >= 64) return 1;
-  int s = 148 / (tiles * cg);
-  if (s < 1) s = 1;
-  if (s > num_kb) s = num_kb;
-  return s;
-}
-
 // Split count for a dW GEMM that runs beside the dX chain: ~48 CTAs, leaving two thirds of the SMs to `st`.
 static int pick_splits_side(int m_rows, int n_cols, int BN, int cg, int num_kb) {
   const int tiles = ((m_rows + 128 * cg - 1) / (128 * cg)) * ((n_cols + BN - 1) / BN);
@@ -155,9 +146,20 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   const float gscale = 1.0f / (static_cast<float>(global_batch) * static_cast<float>(per));
   float* dpred32 = F32(ts.off_dpred32);
   __nv_bfloat16* dpred16 = B16(ts.off_dpred16);
+  { int rcs = ensure_side_stream(p); if (rcs) return rcs; }
+  cudaStream_t side = p->side_stream;
+  cudaStream_t dws = p->dw_stream;
+  // Weight-gradient GEMMs are leaves of the backward graph: they run on dw_stream next to the dX chain; every gradient
+  // operand they read has its own buffer, so nothing they read is rewritten within this backward pass.
+  auto fork_dw = [&]() -> cudaError_t {
+    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
+    if (e1 != cudaSuccess) return e1;
+    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
+  };
   ddpm_loss_bwd_kernel<<<batch, 256, 0, st>>>(eps, pred, F32(ts.off_loss), loss_sum, dpred32, dpred16, gscale, S, C, Cp);
   CNT();
-  launch_colsum<float>(dpred32, C, G("out.bias"), M, C, st); CNT();
+  SMD_CUDA(fork_dw());
+  launch_colsum<float>(dpred32, C, G("out.bias"), M, C, dws); CNT();
 
   // dX GEMM outputs (gradient wrt a bf16 activation), stored as bf16: half the epilogue / LayerNorm-backward bytes
   __nv_bfloat16* g16 = B16(ts.off_g32a);
@@ -170,9 +172,9 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   {
     GemmEpilogue e = epi();
     e.out_f32 = G("out.kernel"); e.ld_f32 = C;
-    const int sp = pick_splits(Md, C, ts.dWout.BN, ts.dWout.cg, nkb);
+    const int sp = pick_splits_side(Md, C, ts.dWout.BN, ts.dWout.cg, nkb);
     e.atomic_out = sp > 1;
-    SMD_CUDA(gemm_k(ts.dWout, Md, Mk, sp, e, st));
+    SMD_CUDA(gemm_k(ts.dWout, Md, Mk, sp, e, dws));
     e = epi();
     e.out_bf16 = g16; e.ld_bf16 = Md;
     SMD_CUDA(launch_gemm(ts.dXout, M, e, st));
@@ -190,16 +192,6 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   // ---------------- FiLM'd residual blocks ----------------
   float* ssbuf = p->buf<float>("ss");
   float* dss_all = F32(ts.off_dss);
-  { int rcs = ensure_side_stream(p); if (rcs) return rcs; }
-  cudaStream_t side = p->side_stream;
-  cudaStream_t dws = p->dw_stream;
-  // Weight-gradient GEMMs are leaves of the backward graph: they run on dw_stream next to the dX chain; every gradient
-  // operand they read has its own buffer, so nothing they read is rewritten within this backward pass.
-  auto fork_dw = [&]() -> cudaError_t {
-    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
-    if (e1 != cudaSuccess) return e1;
-    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
-  };
   for (int k = ts.K - 1; k >= 0; --k) {
     const std::string pre = "k" + std::to_string(k) + ".";
     const float* ss_k = ssbuf + static_cast<size_t>(k) * c.max_batch * 2 * Md;
@@ -290,9 +282,10 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   {
     GemmEpilogue e = epi();
     e.out_f32 = G("post.kernel"); e.ld_f32 = Md;
-    const int sp = pick_splits(128, Md, ts.dWpost.BN, ts.dWpost.cg, nkb);
+    const int sp = pick_splits_side(128, Md, ts.dWpost.BN, ts.dWpost.cg, nkb);
     e.atomic_out = sp > 1;
-    SMD_CUDA(gemm_k(ts.dWpost, 128, Mk, sp, e, st));
+    SMD_CUDA(fork_dw());
+    SMD_CUDA(gemm_k(ts.dWpost, 128, Mk, sp, e, dws));
     e = epi();
     e.out_f32 = da32; e.ld_f32 = 128;
     SMD_CUDA(launch_gemm(ts.dXpost, M, e, st));
