@@ -16,6 +16,8 @@ CASES = {
     "base2": (dict(num_layers=2, num_heads=8, num_mlp_layers=2, channels=42), "TransformerDDPM", 6),
     "large_h16": (dict(num_layers=2, num_heads=16, num_mlp_layers=3, channels=146), "TransformerDDPM", 3),
     "dense": (dict(num_layers=2, channels=512), "DenseDDPM", 8),
+    "heads4": (dict(num_layers=1, num_heads=4, num_mlp_layers=1, channels=42), "TransformerDDPM", 3),
+    "heads32": (dict(num_layers=1, num_heads=32, num_mlp_layers=1, channels=42), "TransformerDDPM", 3),
 }
 
 

@@ -13,6 +13,8 @@ TRANSFORMER_CASES = {
     "base_c146": (dict(num_layers=6, num_heads=8, num_mlp_layers=2, channels=146), 3),
     "base_c512": (dict(num_layers=2, num_heads=8, num_mlp_layers=2, channels=512), 5),
     "large_c42": (dict(num_layers=8, num_heads=16, num_mlp_layers=3, channels=42), 4),
+    "heads4": (dict(num_layers=2, num_heads=4, num_mlp_layers=1, channels=42), 3),     # head dim 32 (mma k-steps = 4)
+    "heads32": (dict(num_layers=1, num_heads=32, num_mlp_layers=1, channels=42), 3),   # head dim 4 (SIMT attention)
 }
 
 
