@@ -3,9 +3,11 @@ sample_ncsn.py:341-342): save_checkpoint(dir, (optimizer, ema, early_stop), step
 ``checkpoint_<step>`` atomically and prunes to the newest `keep`; restore_checkpoint(dir, target) loads the
 latest into the template objects.
 
-Format: msgpack of a state dict {'0': optimizer, '1': ema, '2': early_stop} with ndarray leaves encoded as
-{'__nd__': True, 'dtype', 'shape', 'data'}.  (Byte-compatibility with flax 0.3.0's own msgpack ext encoding is
-the next scope row; the tree shape -- tuple -> dict keyed '0','1','2' -- already matches.)"""
+Default format: msgpack of a state dict {'0': optimizer, '1': ema, '2': early_stop} with the flat arenas as ndarray
+leaves encoded as {'__nd__': True, 'dtype', 'shape', 'data'} plus the arena layout (self-describing).
+With SMD_CHECKPOINT_FORMAT=flax (or save_checkpoint(..., fmt="flax")) the file is written in flax 0.3.0's own wire
+format -- nested pre-Linen parameter tree, msgpack ext-type ndarrays (flax_compat.py; restated from memory, not
+verifiable here); restore_checkpoint detects either format."""
 from __future__ import annotations
 
 import os
@@ -48,12 +50,20 @@ def list_checkpoints(ckpt_dir: str, prefix: str = PREFIX):
     return sorted(names, key=_natural_key)
 
 
-def save_checkpoint(ckpt_dir: str, target, step: int, prefix: str = PREFIX, keep: int = 1) -> str:
+def save_checkpoint(ckpt_dir: str, target, step: int, prefix: str = PREFIX, keep: int = 1, fmt: str = None) -> str:
     os.makedirs(ckpt_dir, exist_ok=True)
     path = os.path.join(ckpt_dir, f"{prefix}{step}")
     tmp = path + ".tmp"
+    fmt = fmt or os.environ.get("SMD_CHECKPOINT_FORMAT", "native")
+    if fmt not in ("native", "flax"):
+        raise ValueError(f"unknown checkpoint format {fmt!r}")
+    if fmt == "flax":
+        from . import flax_compat
+        blob = flax_compat.msgpack_serialize(flax_compat.to_flax_state(target))
+    else:
+        blob = msgpack.packb(_state(target), use_bin_type=True)
     with open(tmp, "wb") as f:
-        f.write(msgpack.packb(_state(target), use_bin_type=True))
+        f.write(blob)
     os.replace(tmp, path)
     names = list_checkpoints(ckpt_dir, prefix)
     for old in names[:-keep] if keep > 0 else []:
@@ -69,8 +79,11 @@ def restore_checkpoint(ckpt_dir: str, target, step: int = None, prefix: str = PR
         names = [n for n in names if n == f"{prefix}{step}"]
     if not names:
         return target
+    from . import flax_compat
     with open(os.path.join(ckpt_dir, names[-1]), "rb") as f:
-        st = msgpack.unpackb(f.read(), raw=False, strict_map_key=False)
+        st = flax_compat.msgpack_restore(f.read())       # plain msgpack plus flax's ndarray ext types
+    if flax_compat.is_flax_state(st):
+        return flax_compat.load_flax_state(st, target)
     optimizer, ema, early_stop = target
     o = st["0"]
     flat = _un_nd(o["target"]["params"])
