@@ -76,3 +76,20 @@ def test_tail_gradient_slice_is_the_film_tail_and_output_layer(lib):
         assert all(n.startswith(("k", "out_ln.", "out.")) for n in inside) and "out.bias" in inside
         assert not any(n.startswith(("k", "out")) for n, off, _ in eng.layout if off < first)
         assert count > 0.8 * eng.arena_floats           # ~85% of the parameters live in the FiLM'd tail
+
+
+def test_plain_c_client(lib, tmp_path):
+    """include/smd.h compiles as C11 and a C program drives the plan / layout entry points of libsmd.so."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    exe = tmp_path / "abi_client"
+    libdir = os.path.dirname(L.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_client", "abi_client.c"), "-o", str(exe),
+                        "-L", libdir, "-l:libsmd.so", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "params=25579946" in r.stdout and "tensors=" in r.stdout
