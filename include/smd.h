@@ -90,7 +90,9 @@ int smd_ddpm_loss(smd_plan* plan, const float* params, const float* x0, const fl
 
 /* One optimizer step of train_ncsn.py:260-288 on this rank's shard:
  *   grads <- d mean_{global batch}(loss) / d params   (scaled by 1/global_batch so a SUM all-reduce over ranks
- *   gives the gradient of the global mean);  loss_sum[0] += sum of this shard's per-example losses.
+ *   gives the gradient of the global mean);  loss_sum[0] = sum of this shard's per-example losses and
+ *   loss_sum[1] = loss_sum[0] / global_batch (two floats, overwritten; summed in example order by the kernel's last
+ *   block, so the reported loss is bit-reproducible; a SUM all-reduce of loss_sum[1] gives the global mean loss).
  * smd_ddpm_grads only produces grads (so the caller can all-reduce them with NCCL);
  * smd_clip_adam applies global-norm clipping (jax clip_grads), Adam (flax.optim.Adam) and optional EMA. */
 int smd_ddpm_grads(smd_plan* plan, const float* params, const float* x0, const float* used_alpha, const float* eps,
@@ -119,12 +121,24 @@ int smd_ema_update(float* ema, const float* params, long long n, float mu, smd_s
 int smd_objective_setup(smd_plan* plan, const float* host_betas, int T, smd_stream_t stream);
 int smd_ddpm_draws(smd_plan* plan, const uint32_t host_key[2], int batch, float* used_alpha, float* eps,
                    int* labels_or_null, smd_stream_t stream);
+/* The same draws for rows [first_row, first_row + batch) of a GLOBAL batch of global_batch examples (threefry is
+ * counter based): a data-parallel rank consumes exactly its slice of the single-process stream, so a run on N GPUs
+ * with seed s sees the noise of the 1-GPU run with seed s.  continuous_noise == 0 follows the
+ * reference's int(continuous_noise) label range (utils/losses.py:272-275): labels in [0, T), and for label 0 the
+ * lower bound alphas_prod[-1] wraps to the last entry as jnp indexing does. */
+int smd_ddpm_draws_sharded(smd_plan* plan, const uint32_t host_key[2], int global_batch, int first_row, int batch,
+                           int continuous_noise, float* used_alpha, float* eps, int* labels_or_null,
+                           smd_stream_t stream);
 
 /* ---- sampler ---------------------------------------------------------------------------------------------- */
 /* host_betas: HOST pointer, T floats.  Builds the per-step coefficient / key / slot tables in the workspace.
  * key = jax PRNG key (2 x uint32) that diffusion_dynamics receives as `rng`. */
 int smd_sampler_setup(smd_plan* plan, const float* host_betas, int T, const uint32_t host_key[2],
                       smd_stream_t stream);
+/* Sharded sampling (sample_size split over data-parallel ranks): this plan's calls hold samples
+ * [first_row, first_row + n) of a global batch of total_rows samples and draw exactly that slice of the chain's
+ * threefry noise streams, so the gathered result equals the single-process chain.  total_rows = 0 switches it off. */
+int smd_sampler_set_shard(smd_plan* plan, long long first_row, long long total_rows);
 /* One reverse step at index t (T-1 .. 0) on state x (n,S,C), in place allowed (x_next == x).
  * z / infill_z: supplied N(0,1) tensors or NULL -> in-kernel threefry with the tables of smd_sampler_setup.
  * metrics: device (4, T) fp32 or NULL (column T-1-t accumulated: grad_norm, step_norm, alpha_prod, noise_norm).
@@ -140,6 +154,9 @@ int smd_ddpm_sample(smd_plan* plan, const float* params, float* x, int n, int st
 
 /* ---- jax.random (threefry2x32) on device ------------------------------------------------------------------ */
 int smd_threefry_normal(const uint32_t host_key[2], float* out, long long n, smd_stream_t stream);
+/* elements [first, first + n) of jax.random.normal(key, (total,)) (a rank's rows of the global initial state) */
+int smd_threefry_normal_slice(const uint32_t host_key[2], float* out, long long n, long long first, long long total,
+                              smd_stream_t stream);
 /* jax.random.uniform(key, (n,), float32, minval, maxval) as of jax 0.2.8 (sample_ncsn.py:230: the infill initial state) */
 int smd_threefry_uniform(const uint32_t host_key[2], float* out, long long n, float minval, float maxval,
                          smd_stream_t stream);

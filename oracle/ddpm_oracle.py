@@ -393,11 +393,10 @@ def diffusion_dynamics(apply_fn, betas: np.ndarray, init: Tensor, noise_fn, infi
     T = len(betas)
     coef = reverse_coefficients(betas)
     slots = collection_slots(T)
-    state = init
-    if infill:
-        state = init * (1 - infill_masks) + infill_samples * infill_masks
+    state = init           # ebm_utils.py:398: the scan starts from the raw init ...
     collection = torch.zeros((41,) + tuple(init.shape), dtype=init.dtype)
-    collection[0] = state
+    # ... and the merged start only goes to collection[0] (ebm_utils.py:321-323)
+    collection[0] = init * (1 - infill_masks) + infill_samples * infill_masks if infill else init
     mets = torch.zeros((4, T, 1), dtype=init.dtype)
     n = T if steps is None else steps
     for i, t in enumerate(range(T - 1, T - 1 - n, -1)):

@@ -156,7 +156,8 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     if (e1 != cudaSuccess) return e1;
     return cudaStreamWaitEvent(dws, p->ev_dw, 0);
   };
-  ddpm_loss_bwd_kernel<<<batch, 256, 0, st>>>(eps, pred, F32(ts.off_loss), loss_sum, dpred32, dpred16, gscale, S, C, Cp);
+  ddpm_loss_bwd_kernel<<<batch, 256, 0, st>>>(eps, pred, F32(ts.off_loss), loss_sum, ts.at<unsigned int>(ws, ts.off_loss_ctr),
+                                              1.0f / static_cast<float>(global_batch), dpred32, dpred16, gscale, S, C, Cp);
   CNT();
   SMD_CUDA(fork_dw());
   launch_colsum<float>(dpred32, C, G("out.bias"), M, C, dws); CNT();

@@ -1022,8 +1022,8 @@ inline void launch_small_linear_bwd_x(const float* g, const float* W, const floa
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
-                     float* __restrict__ loss_sum, float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16,
-                     float gscale, int S, int C, int Cp) {
+                     float* __restrict__ loss_sum, unsigned int* __restrict__ done_counter, float inv_global_batch,
+                     float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16, float gscale, int S, int C, int Cp) {
   pdl_trigger();
   const int b = blockIdx.x;
   const int per = S * C;
@@ -1038,6 +1038,7 @@ ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pr
     dpred16[(static_cast<size_t>(b) * S + row) * Cp + c] = __float2bfloat16_rn(gval);
   }
   __shared__ float red[8];
+  __shared__ bool last;
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -1046,7 +1047,22 @@ ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pr
     for (int j = 0; j < 8; ++j) v += red[j];
     v /= static_cast<float>(per);
     loss[b] = v;
-    if (loss_sum) atomicAdd(loss_sum, v);
+    last = false;
+    if (loss_sum) {
+      // the block that finishes last adds the per-example losses in index order: the reported loss is bit-reproducible
+      // (an atomicAdd per block would make its summation order depend on block scheduling)
+      __threadfence();
+      last = atomicInc(done_counter, gridDim.x - 1) == gridDim.x - 1;   // wraps back to 0 for the next launch
+    }
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    float acc = 0.f;
+    // fixed association: lane-strided partials, then the butterfly
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) acc += __ldcg(loss + i);
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) { loss_sum[0] = acc; loss_sum[1] = acc * inv_global_batch; }
   }
 }
 

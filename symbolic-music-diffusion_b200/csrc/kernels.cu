@@ -664,6 +664,7 @@ reverse_step_kernel(const ReverseStepArgs a) {
   if (a.key_tab) { k0 = a.key_tab[4 * t]; k1 = a.key_tab[4 * t + 1]; ik0 = a.key_tab[4 * t + 2]; ik1 = a.key_tab[4 * t + 3]; }
   const int NC = a.N * a.C;
   const uint32_t total = static_cast<uint32_t>(a.N) * a.S * a.C;
+  const uint32_t rtotal = a.rng_total ? a.rng_total : total, rfirst = a.rng_total ? a.rng_first : 0u;
   const int slot = (a.slot_tab && a.collection) ? a.slot_tab[t] : -1;
   float m_eps = 0.f, m_step = 0.f, m_noise = 0.f;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,7 +676,7 @@ reverse_step_kernel(const ReverseStepArgs a) {
       const float x = a.x[idx];
       const float eh = a.eps_hat[idx];
       float z = 0.f;
-      if (t > 0) z = a.z ? a.z[idx] : jax_normal_from_bits(jax_random_bits(k0, k1, idx, total));
+      if (t > 0) z = a.z ? a.z[idx] : jax_normal_from_bits(jax_random_bits(k0, k1, rfirst + idx, rtotal));
       const float noise = z * sigma;
       float recon = __fsub_rn(__fmul_rn(sqrt_recip, x), __fmul_rn(sqrt_m1, eh));
       recon = fminf(fmaxf(recon, -1.0f), 1.0f);
@@ -685,7 +686,7 @@ reverse_step_kernel(const ReverseStepArgs a) {
         const float ix = a.infill_x[idx];
         float y = ix;
         if (t > 0) {
-          const float iz = a.infill_z ? a.infill_z[idx] : jax_normal_from_bits(jax_random_bits(ik0, ik1, idx, total));
+          const float iz = a.infill_z ? a.infill_z[idx] : jax_normal_from_bits(jax_random_bits(ik0, ik1, rfirst + idx, rtotal));
           y = sqrt_ap * ix + sqrt_1m * iz;
         }
         nx = nx * (1.0f - mk) + y * mk;

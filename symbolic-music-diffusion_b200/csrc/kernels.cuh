@@ -190,6 +190,9 @@ struct ReverseStepArgs {
   float* collection;       // (41, N, S, C) or null
   float* metrics;          // device [4][T] accumulators (grad_norm, step_norm, alpha_prod, noise_norm); slot = T-1-t
   int N, S, C, T;
+  // sharded sampling: this call holds samples [rng_first / (S*C), ...) of a global batch of rng_total / (S*C) samples
+  // and draws exactly that slice of the global threefry streams (0 / 0: the local batch is the whole batch)
+  uint32_t rng_first, rng_total;
 };
 // One body of the reverse-diffusion scan after the network call (utils/ebm_utils.py:332-394)
 void launch_reverse_step(const ReverseStepArgs& a, cudaStream_t st);

@@ -82,6 +82,7 @@ struct smd_plan {
   const int* film_row_dev = nullptr;
   const float* film_tab_params = nullptr;
   bool sampler_ready = false;
+  long long shard_first_row = 0, shard_total_rows = 0;   // smd_sampler_set_shard
   cudaGraphExec_t graph_exec = nullptr;
   int graph_n = -1;
   const float* graph_params = nullptr;

@@ -438,11 +438,16 @@ static void h_split(const uint32_t key[2], int num, uint32_t* out) {
   memcpy(out, flat.data(), sizeof(uint32_t) * 2 * num);
 }
 
-// labels = jax.random.randint(label_key, (B,), 1, T+1); used = max(lo, u*(hi-lo)+lo) with lo=abar[l-1], hi=abar[l]
+// labels = jax.random.randint(label_key, (B,), minlabel, T + minlabel); used = max(lo, u*(hi-lo)+lo) with
+// lo = abar[l-1], hi = abar[l]   (utils/losses.py:272-286; minlabel = int(continuous_noise), and for label 0 the
+// index -1 wraps to the last entry exactly as jnp indexing does).  Rows [first, first + n) of a GLOBAL batch of B
+// examples: threefry is counter based, so a data-parallel rank generates exactly its slice of the global stream.
 __global__ void ddpm_draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint32_t nk1, const float* __restrict__ abar,
-                                  int T, int B, float* __restrict__ used, int* __restrict__ labels) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
+                                  int T, int B, int first, int n, int minlabel, float* __restrict__ used,
+                                  int* __restrict__ labels) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int i = first + j;
   // randint: k1,k2 = split(key); hi,lo bits; span = T; mult = (2^16 % span)^2 % span
   uint32_t a0 = 0, b0 = 2, a1 = 1, b1 = 3;
   threefry2x32(lk0, lk1, a0, b0);
@@ -454,12 +459,12 @@ __global__ void ddpm_draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint
   uint32_t mult = 65536u % span;
   mult = static_cast<uint32_t>((static_cast<uint64_t>(mult) * mult) % span);
   const uint32_t off = static_cast<uint32_t>((static_cast<uint64_t>(hi % span) * mult + (lo % span)) % span);
-  const int label = 1 + static_cast<int>(off);
-  if (labels) labels[i] = label;
-  const float minv = abar[label - 1], maxv = abar[label];
+  const int label = minlabel + static_cast<int>(off);
+  if (labels) labels[j] = label;
+  const float minv = abar[label > 0 ? label - 1 : T], maxv = abar[label];
   const uint32_t bits = jax_random_bits(nk0, nk1, i, B);
   const float u01 = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
-  used[i] = fmaxf(minv, __fadd_rn(__fmul_rn(u01, __fsub_rn(maxv, minv)), minv));
+  used[j] = fmaxf(minv, __fadd_rn(__fmul_rn(u01, __fsub_rn(maxv, minv)), minv));
 }
 
 // jax.random.uniform (0.2.8): f = bitcast((bits >> 9) | 0x3F800000) - 1; max(minval, f * (maxval - minval) + minval)
@@ -471,9 +476,10 @@ __global__ void threefry_uniform_kernel(uint32_t k0, uint32_t k1, float* out, ui
   }
 }
 
-__global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uint32_t n) {
+// out[j] = element (first + j) of jax.random.normal(key, (total,))
+__global__ void threefry_normal_kernel(uint32_t k0, uint32_t k1, float* out, uint32_t n, uint32_t first, uint32_t total) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, i, n));
+    out[i] = jax_normal_from_bits(jax_random_bits(k0, k1, first + i, total));
 }
 
 void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld) {
@@ -674,25 +680,36 @@ int smd_objective_setup(smd_plan* plan, const float* host_betas, int T, smd_stre
   return SMD_OK;
 }
 
-int smd_ddpm_draws(smd_plan* plan, const uint32_t host_key[2], int batch, float* used_alpha, float* eps,
-                   int* labels_or_null, smd_stream_t stream) {
+int smd_ddpm_draws_sharded(smd_plan* plan, const uint32_t host_key[2], int global_batch, int first_row, int batch,
+                           int continuous_noise, float* used_alpha, float* eps, int* labels_or_null,
+                           smd_stream_t stream) {
   if (plan->T_obj <= 0) { set_error("smd_objective_setup has not been called"); return SMD_ERR_STATE; }
-  if (batch < 1) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  if (batch < 1 || first_row < 0 || global_batch < first_row + batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  const long long per = static_cast<long long>(plan->cfg.seq_len) * plan->cfg.channels;
+  if (static_cast<long long>(global_batch) * per > 0xFFFFFFFFll) { set_error("global batch too large"); return SMD_ERR_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint32_t k3[6], k2[4];
   h_split(host_key, 3, k3);               // rng, label_rng, sample_rng
   const uint32_t rng[2] = {k3[0], k3[1]};
   h_split(rng, 2, k2);                    // rng, noise_rng
   ddpm_draws_kernel<<<(batch + 127) / 128, 128, 0, st>>>(k3[2], k3[3], k2[2], k2[3], plan->buf<float>("abar"),
-                                                         plan->T_obj, batch, used_alpha, labels_or_null);
+                                                         plan->T_obj, global_batch, first_row, batch,
+                                                         continuous_noise ? 1 : 0, used_alpha, labels_or_null);
   CNT();
-  const long long n = static_cast<long long>(batch) * plan->cfg.seq_len * plan->cfg.channels;
+  const long long n = static_cast<long long>(batch) * per;
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  threefry_normal_kernel<<<blocks, 256, 0, st>>>(k3[4], k3[5], eps, static_cast<uint32_t>(n));
+  threefry_normal_kernel<<<blocks, 256, 0, st>>>(k3[4], k3[5], eps, static_cast<uint32_t>(n),
+                                                 static_cast<uint32_t>(first_row * per),
+                                                 static_cast<uint32_t>(global_batch * per));
   CNT();
   SMD_LAUNCH_CHECK("ddpm_draws");
   return SMD_OK;
+}
+
+int smd_ddpm_draws(smd_plan* plan, const uint32_t host_key[2], int batch, float* used_alpha, float* eps,
+                   int* labels_or_null, smd_stream_t stream) {
+  return smd_ddpm_draws_sharded(plan, host_key, batch, 0, batch, 1, used_alpha, eps, labels_or_null, stream);
 }
 
 int smd_sampler_setup(smd_plan* plan, const float* host_betas, int T, const uint32_t host_key[2],
@@ -823,8 +840,23 @@ static int reverse_step_impl(smd_plan* plan, const float* params, const float* x
   a.infill_x = infill_x; a.infill_mask = infill_mask; a.infill_z = infill_z;
   a.x_next = x_next; a.collection = collection; a.metrics = metrics;
   a.N = n; a.S = plan->cfg.seq_len; a.C = plan->cfg.channels; a.T = plan->T;
+  if (plan->shard_total_rows > 0) {
+    const long long per = static_cast<long long>(a.S) * a.C;
+    a.rng_first = static_cast<uint32_t>(plan->shard_first_row * per);
+    a.rng_total = static_cast<uint32_t>(plan->shard_total_rows * per);
+  }
   launch_reverse_step(a, st); CNT();
   SMD_LAUNCH_CHECK("reverse_step");
+  return SMD_OK;
+}
+
+int smd_sampler_set_shard(smd_plan* plan, long long first_row, long long total_rows) {
+  if (!plan) { set_error("null plan"); return SMD_ERR_INVALID; }
+  if (total_rows < 0 || first_row < 0 || (total_rows > 0 && first_row >= total_rows) ||
+      total_rows * plan->cfg.seq_len * plan->cfg.channels > 0xFFFFFFFFll) { set_error("bad shard"); return SMD_ERR_INVALID; }
+  plan->shard_first_row = first_row;
+  plan->shard_total_rows = total_rows;
+  if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }  // kernel args changed
   return SMD_OK;
 }
 
@@ -911,9 +943,24 @@ int smd_threefry_normal(const uint32_t host_key[2], float* out, long long n, smd
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   threefry_normal_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(host_key[0], host_key[1], out,
+                                                                                static_cast<uint32_t>(n), 0u,
                                                                                 static_cast<uint32_t>(n));
   CNT();
   SMD_LAUNCH_CHECK("threefry_normal");
+  return SMD_OK;
+}
+int smd_threefry_normal_slice(const uint32_t host_key[2], float* out, long long n, long long first, long long total,
+                              smd_stream_t stream) {
+  if (n < 0 || first < 0 || first + n > total || total > 0xFFFFFFFFll) { set_error("slice out of range"); return SMD_ERR_INVALID; }
+  if (n == 0) return SMD_OK;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  threefry_normal_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(host_key[0], host_key[1], out,
+                                                                                static_cast<uint32_t>(n),
+                                                                                static_cast<uint32_t>(first),
+                                                                                static_cast<uint32_t>(total));
+  CNT();
+  SMD_LAUNCH_CHECK("threefry_normal_slice");
   return SMD_OK;
 }
 int smd_threefry_uniform(const uint32_t host_key[2], float* out, long long n, float minval, float maxval,

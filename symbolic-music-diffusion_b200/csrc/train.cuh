@@ -50,6 +50,7 @@ struct TrainState {
   size_t off_dss = 0;                  // fp32 [B][2Md]
   size_t off_de = 0, off_de2 = 0;      // fp32 [B][512] x2
   size_t off_loss = 0;                 // fp32 [B]
+  size_t off_loss_ctr = 0;             // u32: blocks of the loss kernel that have finished
   size_t off_wplain = 0;               // bf16 plain (in,out) copies of every GEMM weight (dX operands)
   std::vector<size_t> off_w_qkv, off_w_o, off_w_ffn1, off_w_ffn2, off_w_a, off_w_b;
   size_t off_w_post = 0, off_w_out = 0, off_w_in = 0;

@@ -29,7 +29,7 @@ def create_noise_schedule(sigma_begin=1, sigma_end=1e-2, L=10, schedule="geometr
 
 
 def diffusion_dynamics(rng, model, betas, init, epsilon, T, denoise, infill=False, infill_samples=None,
-                       infill_masks=None):
+                       infill_masks=None, shard=None):
     """utils/ebm_utils.py:274-405.  Returns (state, collection (41, N, *shape), ld_metrics (4, len(betas), 1)).
 
     epsilon / T / denoise are null parameters upstream too.  The whole chain runs on the GPU (CUDA-graph replay of
@@ -41,15 +41,30 @@ def diffusion_dynamics(rng, model, betas, init, epsilon, T, denoise, infill=Fals
     eng = model.engine(n)
     betas = np.asarray(betas, np.float32)
     eng.sampler_setup(betas, key=(int(rng[0]), int(rng[1])))
+    # shard = (first_row, total_rows): `init` holds this rank's rows of a global batch; the per-step noise is the same
+    # slice of the global threefry stream and the batch-mean metrics are reduced over ranks below
+    eng.set_sampler_shard(*(shard if shard is not None else (0, 0)))
     ix = im = None
+    collection = torch.zeros((41,) + tuple(x.shape), dtype=torch.float32, device=x.device)
     if infill:
         ix = _as_device_f32(infill_samples)
         im = _as_device_f32(infill_masks)
-        x = x * (1 - im) + ix * im
-    collection = torch.zeros((41,) + tuple(x.shape), dtype=torch.float32, device=x.device)
-    collection[0] = x
+        # utils/ebm_utils.py:321-323,398: the merged start only goes to collection[0]; the scan itself starts from the
+        # raw `init` (the first step's blend overwrites the masked entries anyway)
+        collection[0] = x * (1 - im) + ix * im
+    else:
+        collection[0] = x
     metrics = torch.zeros((4, len(betas)), dtype=torch.float32, device=x.device)
     eng.sample(x, steps=len(betas), infill_x=ix, infill_mask=im, collection=collection, metrics=metrics, use_graph=True)
+    if shard is not None:
+        # utils/ebm_utils.py:380-384: the metrics are means over the batch -> one weighted (4, T) all-reduce at the end
+        from . import parallel
+        if parallel.world_size() > 1:
+            w = float(n) / float(shard[1])
+            alpha_row = metrics[2].clone()              # alpha_prod is not a batch mean
+            metrics.mul_(w)
+            parallel.all_reduce_sum_(metrics)
+            metrics[2] = alpha_row
     return x, collection, metrics.unsqueeze(2)
 
 

@@ -36,7 +36,7 @@ class ModelConfig:
             L, K = self.num_layers, self.num_mlp_layers
             mac_tok = C * E + L * (4 * E * E + 2 * S * E + 2 * E * M) + E * M + K * 2 * M * M + M * C
         else:
-            K = self.num_layers
+            K, S = self.num_layers, 1      # DenseDDPM: one (B, C) vector per example
             mac_tok = C * M + K * 2 * M * M + M * C
         mac_film = K * (128 * 512 + 512 * 512 + 2 * 512 * M)
         return 2.0 * (S * mac_tok + mac_film)
@@ -210,16 +210,21 @@ class Engine:
         _lib.check(self.lib.smd_objective_setup(self._plan, b.ctypes.data_as(C.POINTER(C.c_float)), len(b),
                                                 self._stream()))
 
-    def draws(self, key, batch: int, want_labels: bool = False):
-        """(used_alpha (B,), eps (B,S,C)[, labels]) from a jax PRNG key, generated on device."""
+    def draws(self, key, batch: int, want_labels: bool = False, global_batch: Optional[int] = None,
+              first_row: int = 0, continuous_noise: bool = True):
+        """(used_alpha (B,), eps (B,S,C)[, labels]) from a jax PRNG key, generated on device.
+
+        With ``global_batch`` / ``first_row`` the result is rows [first_row, first_row + batch) of the draws of a
+        global batch (data-parallel ranks consume slices of ONE threefry stream: DP(seed) == single-GPU(seed))."""
         dev = self._ws.device
         shape = (batch, self.seq_len, self.cfg.channels) if ARCHS[self.cfg.arch] == 0 else (batch, self.cfg.channels)
         used = torch.empty((batch,), dtype=torch.float32, device=dev)
         eps = torch.empty(shape, dtype=torch.float32, device=dev)
         labels = torch.empty((batch,), dtype=torch.int32, device=dev) if want_labels else None
         k = (C.c_uint32 * 2)(int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF)
-        _lib.check(self.lib.smd_ddpm_draws(self._plan, k, batch, used.data_ptr(), eps.data_ptr(), _ptr(labels),
-                                           self._stream()))
+        _lib.check(self.lib.smd_ddpm_draws_sharded(self._plan, k, int(global_batch or batch), int(first_row), batch,
+                                                   1 if continuous_noise else 0, used.data_ptr(), eps.data_ptr(),
+                                                   _ptr(labels), self._stream()))
         return (used, eps, labels) if want_labels else (used, eps)
 
     # ------------------------------------------------------------------ optimizer step (train_ncsn.py:260-288)
@@ -239,13 +244,13 @@ class Engine:
         self.ema_params = self.params.clone() if ema else None
         self._scratch = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.loss_sum = self._grads_buf[n:n + 1]
+        self.loss_sum = self._grads_buf[n:n + 1]       # sum of this shard's per-example losses
+        self.loss_mean = self._grads_buf[n + 1:n + 2]  # loss_sum / global batch (SUM over ranks = global mean loss)
         self.opt_step = 0
 
     def compute_grads(self, x0, used_alpha, eps, global_batch: Optional[int] = None) -> None:
         """grads <- d(mean over the GLOBAL batch of the loss)/d params for this shard; loss_sum <- sum of losses."""
-        self.loss_sum.zero_()
-        self.ddpm_grads(x0, used_alpha, eps, self.grads, self.loss_sum, global_batch)
+        self.ddpm_grads(x0, used_alpha, eps, self.grads, self._grads_buf[self.arena_floats:], global_batch)
 
     def reduce_grads(self, world_size: int, process_group=None) -> None:
         """SUM all-reduce of the gradient arena and the loss scalar over the data-parallel ranks (call right after
@@ -263,14 +268,14 @@ class Engine:
                 self._comm_stream = torch.cuda.Stream()
             with torch.cuda.stream(self._comm_stream):
                 _lib.check(self.lib.smd_wait_tail_grads(self._plan, C.c_void_p(self._comm_stream.cuda_stream)))
-                # + 1: the loss sum stored behind the arena rides along (it is final long before the tail gradients)
-                w_tail = dist.all_reduce(self._grads_buf[first:first + count + 1], op=dist.ReduceOp.SUM,
+                # + 2: the loss scalars stored behind the arena ride along (final long before the tail gradients)
+                w_tail = dist.all_reduce(self._grads_buf[first:first + count + 2], op=dist.ReduceOp.SUM,
                                          group=process_group, async_op=True)
             w_head = dist.all_reduce(self.grads[:first], op=dist.ReduceOp.SUM, group=process_group, async_op=True)
             w_head.wait()
             w_tail.wait()      # the current stream now waits for both reductions
         else:
-            dist.all_reduce(self._grads_buf[:self.grads.numel() + 1], op=dist.ReduceOp.SUM, group=process_group)
+            dist.all_reduce(self._grads_buf[:self.grads.numel() + 2], op=dist.ReduceOp.SUM, group=process_group)
 
     def grads_tail_range(self):
         """(first_float, num_floats) of the gradient-arena slice that is final after the tail backward."""
@@ -294,7 +299,7 @@ class Engine:
         self.compute_grads(x0, used_alpha, eps, global_batch=batch * world_size)
         self.reduce_grads(world_size, process_group)
         self.apply_grads(lr, grad_clip)
-        return self.loss_sum / float(batch * world_size), self.grad_norm
+        return self.loss_mean, self.grad_norm
 
     # ------------------------------------------------------------------ sampler
     def sampler_setup(self, betas: np.ndarray, key=(0, 0)) -> None:
@@ -304,6 +309,11 @@ class Engine:
         _lib.check(self.lib.smd_sampler_setup(self._plan, b.ctypes.data_as(C.POINTER(C.c_float)), len(b), k,
                                               self._stream()))
         self._sampler_T = len(b)
+
+    def set_sampler_shard(self, first_row: int = 0, total_rows: int = 0) -> None:
+        """This engine's sampler calls hold samples [first_row, ...) of a global batch of total_rows samples and draw
+        that slice of the chain's threefry streams (0, 0: off)."""
+        _lib.check(self.lib.smd_sampler_set_shard(self._plan, int(first_row), int(total_rows)))
 
     def reverse_step(self, x, t: int, z=None, infill_x=None, infill_mask=None, infill_z=None, x_next=None,
                      eps_hat=None, collection=None, metrics=None):

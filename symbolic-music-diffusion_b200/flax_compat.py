@@ -10,7 +10,9 @@ flax.serialization.to_bytes): msgpack of `to_state_dict(target)` where
 
 The parameter tree uses pre-Linen flax.nn auto-names `ClassName_<i>`, `i` counting ALL submodules created so far in
 the parent (also the parameter-less ones: TransformerPositionalEncoding, NoiseEncoding, FeaturewiseAffine), and the
-explicit names query / key / value / out inside SelfAttention (models/ncsn.py:122-179, models/shared.py:33-75).
+explicit names query / key / value / out inside the attention block, which is auto-named after its base class
+`MultiHeadDotProductAttention_<i>` (nn.SelfAttention is a .partial of it)  (models/ncsn.py:122-179,
+models/shared.py:33-75).
 
 NOT VERIFIED against flax itself: neither flax 0.3.0 nor a checkpoint written by it can exist in this environment.
 Both conventions above are restated from the flax 0.3.0 sources as remembered; `tests/test_flax_compat.py` pins the
@@ -85,8 +87,11 @@ def _tree_paths(cfg) -> Dict[str, Tuple[Tuple[str, ...], str]]:
     for l in range(L):
         b = 2 + 5 * l
         out[f"l{l}.ln1"] = ((f"LayerNorm_{b}",), "ln")
-        out[f"l{l}.attn.qkv"] = ((f"SelfAttention_{b + 1}",), "qkv")
-        out[f"l{l}.attn.out"] = ((f"SelfAttention_{b + 1}", "out"), "attn_out")
+        # nn.SelfAttention is MultiHeadDotProductAttention.partial(inputs_kv=None); pre-Linen Module.partial keeps the
+        # base class __name__, so the auto-name is MultiHeadDotProductAttention_<i> (as in pre-Linen ViT checkpoints).
+        # `SelfAttention_<i>` (what round 1 wrote) is still accepted on restore (_ALIASES).
+        out[f"l{l}.attn.qkv"] = ((f"MultiHeadDotProductAttention_{b + 1}",), "qkv")
+        out[f"l{l}.attn.out"] = ((f"MultiHeadDotProductAttention_{b + 1}", "out"), "attn_out")
         out[f"l{l}.ln2"] = ((f"LayerNorm_{b + 2}",), "ln")
         out[f"l{l}.ffn1"] = ((f"Dense_{b + 3}",), "dense")
         out[f"l{l}.ffn2"] = ((f"Dense_{b + 4}",), "dense")
@@ -141,7 +146,10 @@ def params_from_flax(tree: dict, cfg) -> Dict[str, np.ndarray]:
         node = tree
         for p in path:
             if p not in node:
-                raise KeyError("flax parameter tree has no " + "/".join(path))
+                alt = p.replace("MultiHeadDotProductAttention_", "SelfAttention_")
+                if alt not in node:
+                    raise KeyError("flax parameter tree has no " + "/".join(path))
+                p = alt
             node = node[p]
         return node
 

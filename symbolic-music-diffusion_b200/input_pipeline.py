@@ -316,15 +316,101 @@ def _synthetic_examples(shape, count: int, seed: int):
     return gen
 
 
-def _cached(path: str, compute):
-    if os.path.exists(path):
-        return load(path)
-    v = compute()
-    try:
-        save(v, path)
-    except OSError:
-        pass
-    return v
+def _save_atomic(obj, path: str) -> None:
+    """Write-then-rename: a concurrent reader (another rank under torchrun) never sees a half-written pickle."""
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    tmp = f"{path}.tmp.{os.getpid()}"
+    save(obj, tmp)
+    os.replace(tmp, path)
+
+
+def _cached_many(paths, compute):
+    """Values cached one per pickle in `paths` (utils/data_utils.py:63-156 keeps min / max / cardinality that way).
+    `compute()` returns all of them from ONE pass over the data.  Under torch.distributed only rank 0 computes and
+    writes; the other ranks wait at a barrier and read what rank 0 wrote, so every rank normalises identically."""
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if all(os.path.exists(q) for q in paths):
+        return tuple(load(q) for q in paths)
+    vals = None
+    if not multi or dist.get_rank() == 0:
+        vals = tuple(compute())
+        try:
+            for q, v in zip(paths, vals):
+                _save_atomic(v, q)
+        except OSError:
+            if multi:
+                raise
+    if multi:
+        dist.barrier()
+        if vals is None:
+            vals = tuple(load(q) for q in paths)
+    return vals
+
+
+class DevicePrefetcher:
+    """input_pipeline.py:209-210 (`dataset.prefetch(AUTOTUNE)`) for the GPU path: a background thread pulls host
+    batches, stages them in pinned memory and issues the host->device copy on its own CUDA stream, `depth` batches
+    ahead of the training step; iteration yields device tensors whose copy the consumer stream has been made to wait
+    for.  Without a CUDA device the batches are yielded as they are (host arrays) -- there is nothing to overlap."""
+
+    def __init__(self, dataset, depth: int = 2, device=None):
+        self.dataset = dataset
+        self.depth = max(1, int(depth))
+        self.device = device
+        for attr in ("examples", "min", "max", "batch_size"):
+            if hasattr(dataset, attr):
+                setattr(self, attr, getattr(dataset, attr))
+
+    def __iter__(self):
+        import queue
+        import threading
+        import torch
+        if not torch.cuda.is_available():
+            yield from self.dataset
+            return
+        dev = torch.device(self.device or f"cuda:{torch.cuda.current_device()}")
+        copy_stream = torch.cuda.Stream(device=dev)
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+        END = object()
+
+        def worker():
+            try:
+                torch.cuda.set_device(dev)
+                for b in self.dataset:
+                    if stop.is_set():
+                        return
+                    host = torch.from_numpy(np.ascontiguousarray(b, np.float32)).pin_memory()
+                    with torch.cuda.stream(copy_stream):
+                        d = host.to(dev, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    q.put((d, ev, host))        # `host` stays referenced until the consumer has the batch
+                q.put(END)
+            except BaseException as e:          # surface loader errors in the training thread
+                q.put(e)
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is END:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                d, ev, _host = item
+                torch.cuda.current_stream().wait_event(ev)
+                d.record_stream(torch.cuda.current_stream())
+                yield d
+        finally:
+            stop.set()
+            while not q.empty():
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    break
 
 
 def get_dataset(dataset="", data_shape=(2,), problem="vae", batch_size=128, normalize=True, pca_ckpt="",
@@ -364,15 +450,15 @@ def get_dataset(dataset="", data_shape=(2,), problem="vae", batch_size=128, norm
                     lo, hi = min(lo, np.float32(b.min())), max(hi, np.float32(b.max()))
                 return lo, hi
             if cache_dir:
-                lo = _cached(os.path.join(cache_dir, f"{split}_{config}_min.pkl"), lambda: minmax()[0])
-                hi = _cached(os.path.join(cache_dir, f"{split}_{config}_max.pkl"), lambda: minmax()[1])
+                lo, hi = _cached_many([os.path.join(cache_dir, f"{split}_{config}_min.pkl"),
+                                       os.path.join(cache_dir, f"{split}_{config}_max.pkl")], minmax)   # one pass
             else:
                 lo, hi = minmax()
             ds.min, ds.max, ds._norm = lo, hi, True
         if include_cardinality:
             def count(ds=ds):
                 return sum(1 for _ in ds._raw_batches())
-            ds.examples = (_cached(os.path.join(cache_dir, f"{split}_{batch_size}_cardinality.pkl"), count)
-                           if cache_dir else count())
+            ds.examples = (_cached_many([os.path.join(cache_dir, f"{split}_{batch_size}_cardinality.pkl")],
+                                        lambda: (count(),))[0] if cache_dir else count())
         out.append(ds)
     return out[0], out[1]

@@ -25,12 +25,22 @@ def split(key, num: int = 2) -> np.ndarray:
     return np.array(list(out), dtype=np.uint32).reshape(num, 2)
 
 
-def normal(key, shape, device=None) -> torch.Tensor:
+def normal(key, shape, device=None, rows=None) -> torch.Tensor:
+    """jax.random.normal(key, shape).  ``rows=(first, count)`` returns only rows [first, first + count) of the
+    leading axis (a data-parallel rank's slice of the global draw; threefry is counter based)."""
     lib = _lib.load_library()
-    n = int(np.prod(shape))
-    out = torch.empty(tuple(shape), dtype=torch.float32, device=device or "cuda")
+    shape = tuple(int(s) for s in shape)
+    total = int(np.prod(shape))
     k = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
-    _lib.check(lib.smd_threefry_normal(k, out.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    st = torch.cuda.current_stream().cuda_stream
+    if rows is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device or "cuda")
+        _lib.check(lib.smd_threefry_normal(k, out.data_ptr(), total, st))
+        return out
+    first, count = int(rows[0]), int(rows[1])
+    per = total // shape[0]
+    out = torch.empty((count,) + shape[1:], dtype=torch.float32, device=device or "cuda")
+    _lib.check(lib.smd_threefry_normal_slice(k, out.data_ptr(), count * per, first * per, total, st))
     return out
 
 

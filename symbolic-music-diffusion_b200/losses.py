@@ -26,10 +26,8 @@ def diffusion_loss(batch, model, betas, rng, continuous_noise=False, reduction="
     if getattr(eng, "_obj_betas", None) is None or not np.array_equal(eng._obj_betas, betas):
         eng.objective_setup(betas)
         eng._obj_betas = betas.copy()
-    if not continuous_noise:
-        # the reference's discrete branch is commented out upstream (losses.py:287-288,301-302): only the
-        # label range changes (minval 0), which would index alphas_prod[-1]; not supported here.
-        raise ValueError("diffusion_loss: only continuous_noise=True is implemented (all ddpm-*.cfg use it)")
-    used, eps = eng.draws((int(rng[0]), int(rng[1])), x0.shape[0])
+    # continuous_noise only changes the label range (losses.py:272-275: minval = int(continuous_noise)); the discrete
+    # branch is commented out upstream (losses.py:287-288, 301-302), so label 0 reads alphas_prod[-1] (wraps) as there
+    used, eps = eng.draws((int(rng[0]), int(rng[1])), x0.shape[0], continuous_noise=bool(continuous_noise))
     loss = eng.ddpm_loss(x0, used, eps)
     return reduce_fn(loss, reduction)

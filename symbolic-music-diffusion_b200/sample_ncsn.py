@@ -50,13 +50,14 @@ def generate_samples(sample_shape, num_samples, rng_seed=1):
     rng, optimizer = _restore(FLAGS.model_dir, sample_shape)
     sigmas = ebm_utils.create_noise_schedule(FLAGS.sigma_begin, FLAGS.sigma_end, FLAGS.num_sigmas, FLAGS.schedule_type)
     world, rank = parallel.world_size(), parallel.rank()
-    local = parallel.shard_size(num_samples)
-    key = random.split(rng, world)[rank] if world > 1 else rng
+    rng, sample_rng = random.split(rng)          # sample_ncsn.py:350
     t0 = time.time()
-    generated, collection, ld_metrics = train_ncsn.sample(optimizer.target, sigmas, key, sample_shape,
-                                                          num_samples=local, sampling=FLAGS.sampling,
+    # every rank holds the same key; rank r generates rows [r*N/W, (r+1)*N/W) of the N-sample run (its slice of the
+    # initial draw and of each step's noise), so the gathered result is the single-process result
+    generated, collection, ld_metrics = train_ncsn.sample(optimizer.target, sigmas, sample_rng, sample_shape,
+                                                          num_samples=num_samples, sampling=FLAGS.sampling,
                                                           epsilon=FLAGS.ld_epsilon, steps=FLAGS.ld_steps,
-                                                          denoise=FLAGS.denoise)
+                                                          denoise=FLAGS.denoise, shard=(rank, world))
     torch.cuda.synchronize()
     logging.info("Generated samples in %f seconds", time.time() - t0)
     generated = parallel.gather_rows(generated)

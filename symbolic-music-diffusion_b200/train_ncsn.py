@@ -121,7 +121,8 @@ def evaluate(dataset, model, sigmas, rng):
 
 
 def lr_at(step: int) -> float:
-    """flax create_stepped_learning_rate_schedule as called at train_ncsn.py:340-342."""
+    """flax create_stepped_learning_rate_schedule as called at train_ncsn.py:340-342, evaluated at the 0-based
+    global step like lr_scheduler(global_step) at train_ncsn.py:362: lr0 * gamma^max(0, ceil(step/interval) - 1)."""
     n = 0 if step <= 0 else (step - 1) // FLAGS.lr_schedule_interval
     return FLAGS.learning_rate * (FLAGS.lr_gamma ** n)
 
@@ -141,13 +142,15 @@ def train_step(objective, batch, optimizer, sigmas, rng, learning_rate, ema=None
         eng._obj_betas = betas.copy()
     if not hasattr(eng, "grads"):
         eng.init_train_state(ema=False)
-    key = random.split(rng, world)[rank] if world > 1 else rng   # independent noise per shard
-    used, eps = eng.draws((int(key[0]), int(key[1])), local)
+    # every rank holds the SAME key and consumes rows [rank*local, (rank+1)*local) of the global batch's threefry
+    # streams (labels, alpha-bar, eps): an N-GPU run with seed s sees exactly the noise of the 1-GPU run with seed s
+    used, eps = eng.draws((int(rng[0]), int(rng[1])), local, global_batch=local * world, first_row=rank * local,
+                          continuous_noise=FLAGS.continuous_noise)
     eng.compute_grads(x0, used, eps, global_batch=local * world)
-    eng.reduce_grads(parallel.world_size())     # tail gradients are reduced underneath the trunk backward
-    optimizer.apply_gradient(eng.grads, learning_rate=learning_rate, max_norm=FLAGS.grad_clip,
-                             ema=None if ema is None else ema.params.flat, mu=FLAGS.mu)
-    metrics = {"loss": eng.loss_sum / float(local * world), "grad": optimizer.grad_norm, "lr": learning_rate}
+    eng.reduce_grads(world)     # tail gradients are reduced underneath the trunk backward
+    optimizer.apply_gradient(eng.grads, learning_rate=learning_rate, max_norm=FLAGS.grad_clip, ema=ema, mu=FLAGS.mu,
+                             engine=eng)
+    metrics = {"loss": eng.loss_mean, "grad": optimizer.grad_norm, "lr": learning_rate}
     return optimizer, metrics
 
 
@@ -171,47 +174,60 @@ def train(train_batches, valid_batches, sigmas, output_dir=None, verbose=True):
             writer = SummaryWriter(os.path.join(output_dir, "train"))
         except Exception:  # tensorboard is optional
             writer = None
-    steps_per_epoch = train_batches.examples
-    total_steps = FLAGS.max_steps or FLAGS.epochs * steps_per_epoch
-    global_step, t0 = 0, time.time()
-    done = False
+    if FLAGS.snapshot_sampling:
+        # train_ncsn.py:405-486: in-training sampling writes matplotlib / note_seq artefacts (out of scope); every
+        # ddpm-*.cfg passes --nosnapshot_sampling.  Say so instead of silently ignoring the flag.
+        logging.warning("--snapshot_sampling is not implemented on this path (plots / MIDI are out of scope); "
+                        "--eval_samples=%d ignored", FLAGS.eval_samples)
+    examples = train_batches.examples            # batches per epoch (utils/data_utils.py:63-90)
+
+    class _LocalRows:                            # rows [rank*B/W, (rank+1)*B/W) of every global batch
+        def __iter__(self_inner):
+            return (parallel.shard_rows(b) for b in train_batches)
+    # input_pipeline.py:209-210 prefetch: pinned staging + host->device copy on a side stream, 2 batches ahead
+    loader = input_pipeline.DevicePrefetcher(_LocalRows(), depth=2)
+    sampling_step = -1
     for epoch in range(FLAGS.epochs):
-        for batch in train_batches:
+        start_time = time.time()
+        for step, batch in enumerate(loader):                           # this rank's rows, already on the device
             rng, train_rng = random.split(rng)
-            global_step += 1
-            lr = lr_at(global_step)
-            optimizer, metrics = train_step(objective, parallel.shard_rows(batch), optimizer, sigmas, train_rng, lr, ema)
-            if global_step % FLAGS.logging_freq == 0 and parallel.rank() == 0:
-                dt = time.time() - t0
-                metrics.update({"batch/s": FLAGS.logging_freq / dt, "ms/batch": 1e3 * dt / FLAGS.logging_freq})
-                train_utils.log_metrics(metrics, global_step, total_steps, epoch=epoch, summary_writer=writer,
-                                        verbose=verbose)
-                t0 = time.time()
-            if global_step % FLAGS.snapshot_freq == 0 or global_step == total_steps:
+            global_step = step + epoch * examples                       # train_ncsn.py:359 (0-based)
+            optimizer, metrics = train_step(objective, batch, optimizer, sigmas, train_rng,
+                                            lr_at(global_step), ema)    # EMA (train_ncsn.py:364-365) is fused in
+            if step % FLAGS.logging_freq == 0 and parallel.rank() == 0:
+                elapsed = time.time() - start_time
+                metrics.update({"batch/s": (step + 1) / elapsed, "ms/batch": elapsed * 1000 / (step + 1)})
+                train_utils.log_metrics(metrics, step, examples, epoch=epoch, summary_writer=writer, verbose=verbose)
+            if (step % FLAGS.snapshot_freq == 0 and step > 0) or step == examples - 1:     # train_ncsn.py:380-381
+                sampling_step += 1
                 rng, eval_rng = random.split(rng)
                 ev = evaluate(valid_batches, optimizer.target, sigmas, eval_rng)
                 improved, early_stop = early_stop.update(ev["loss"])
                 if parallel.rank() == 0:
-                    logging.info("eval step %d: loss %.6f", global_step, ev["loss"])
-                    if FLAGS.save_ckpt and output_dir:
-                        checkpoints.save_checkpoint(output_dir, (optimizer, ema, early_stop), global_step,
+                    train_utils.log_metrics(ev, global_step, examples * FLAGS.epochs, summary_writer=None,
+                                            verbose=verbose)
+                    # train_ncsn.py:395-399: with --early_stopping only improved models are written
+                    if FLAGS.save_ckpt and output_dir and (not FLAGS.early_stopping or improved):
+                        checkpoints.save_checkpoint(output_dir, (optimizer, ema, early_stop), sampling_step,
                                                     keep=FLAGS.checkpoints_to_keep)
                 if FLAGS.early_stopping and early_stop.should_stop:
-                    done = True
-            if FLAGS.max_steps and global_step >= FLAGS.max_steps:
-                done = True
-            if done:
-                break
-        if done:
-            break
+                    logging.info("EARLY STOP: Ended training after %s epochs.", epoch + 1)
+                    return optimizer
+            if FLAGS.max_steps is not None and global_step >= FLAGS.max_steps:             # train_ncsn.py:492-494
+                if writer is not None:
+                    writer.flush()
+                return optimizer
     if writer is not None:
         writer.flush()
     return optimizer
 
 
 def sample(scorenet, sigmas, rng, sample_shape, num_samples=2400, sampling="ald", epsilon=1e-3, steps=100,
-           denoise=True):
-    """train_ncsn.py:499-551: initial noise from `rng`, dispatch on the sampler, collate metrics."""
+           denoise=True, shard=None):
+    """train_ncsn.py:499-551: initial noise from `rng`, dispatch on the sampler, collate metrics.
+
+    shard=(rank, world) (not in the reference): this process generates rows [rank*n/world, (rank+1)*n/world) of the
+    num_samples-sample run -- its slice of the initial normal draw and of every step's noise stream."""
     if sampling == "ddpm":
         algorithm = ebm_utils.diffusion_dynamics
     elif sampling in ("ald", "cas"):
@@ -219,8 +235,15 @@ def sample(scorenet, sigmas, rng, sample_shape, num_samples=2400, sampling="ald"
     else:
         raise ValueError(f"Unknown sampling algorithm: {sampling}")
     init_rng, ld_rng = random.split(rng)
-    init = random.normal(init_rng, (num_samples, *sample_shape))
-    generated, collection, ld_metrics = algorithm(ld_rng, scorenet, sigmas, init, epsilon, steps, denoise, False)
+    if shard is None or shard[1] <= 1:
+        init = random.normal(init_rng, (num_samples, *sample_shape))
+        generated, collection, ld_metrics = algorithm(ld_rng, scorenet, sigmas, init, epsilon, steps, denoise, False)
+    else:
+        local = parallel.shard_size(num_samples)
+        first = shard[0] * local
+        init = random.normal(init_rng, (num_samples, *sample_shape), rows=(first, local))
+        generated, collection, ld_metrics = algorithm(ld_rng, scorenet, sigmas, init, epsilon, steps, denoise, False,
+                                                      shard=(first, num_samples))
     return generated, collection, ebm_utils.collate_sampling_metrics(ld_metrics)
 
 

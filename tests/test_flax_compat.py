@@ -9,6 +9,10 @@ from smd_b200 import checkpoints, flax_compat, ncsn, optim, train_utils
 from smd_b200 import jrandom  # noqa: F401  (host key helpers only; no GPU call below)
 
 
+def torch_equal(a, b):
+    return bool(torch.equal(a.cpu(), b.cpu()))
+
+
 def _target(arch="TransformerDDPM", shape=(32, 42), **kw):
     module = getattr(ncsn, arch).partial(**kw)
     from smd_b200 import nn
@@ -41,13 +45,13 @@ def test_pre_linen_tree_naming_transformer():
     st = flax_compat.to_flax_state((opt, ema, es))
     p = st["0"]["target"]["params"]
     # counter per parent over ALL submodules: 0 is the parameter-less positional encoding, layers take 5 each
-    expect = {"Dense_1", "LayerNorm_2", "SelfAttention_3", "LayerNorm_4", "Dense_5", "Dense_6",
-              "LayerNorm_7", "SelfAttention_8", "LayerNorm_9", "Dense_10", "Dense_11",
+    expect = {"Dense_1", "LayerNorm_2", "MultiHeadDotProductAttention_3", "LayerNorm_4", "Dense_5", "Dense_6",
+              "LayerNorm_7", "MultiHeadDotProductAttention_8", "LayerNorm_9", "Dense_10", "Dense_11",
               "LayerNorm_12", "Dense_13", "DenseFiLM_14", "DenseResBlock_15", "DenseFiLM_16", "DenseResBlock_17",
               "LayerNorm_18", "Dense_19"}
     assert set(p) == expect
-    assert p["SelfAttention_3"]["query"]["kernel"].shape == (128, 8, 16) and p["SelfAttention_3"]["key"]["bias"].shape == (8, 16)
-    assert p["SelfAttention_3"]["out"]["kernel"].shape == (8, 16, 128)
+    assert p["MultiHeadDotProductAttention_3"]["query"]["kernel"].shape == (128, 8, 16) and p["MultiHeadDotProductAttention_3"]["key"]["bias"].shape == (8, 16)
+    assert p["MultiHeadDotProductAttention_3"]["out"]["kernel"].shape == (8, 16, 128)
     assert set(p["DenseFiLM_14"]) == {"Dense_1", "Dense_2", "Dense_3", "Dense_4"} and p["DenseFiLM_14"]["Dense_4"]["kernel"].shape == (512, 2048)
     assert set(p["DenseResBlock_15"]) == {"LayerNorm_0", "Dense_2", "LayerNorm_3", "Dense_5"}
     assert p["Dense_1"]["kernel"].shape == (42, 128) and p["Dense_19"]["kernel"].shape == (2048, 42)
@@ -84,3 +88,21 @@ def test_restore_rejects_a_checkpoint_of_another_architecture(tmp_path):
     checkpoints.save_checkpoint(str(tmp_path), _target(num_layers=1, num_heads=8, num_mlp_layers=1), 1, fmt="flax")
     with pytest.raises((KeyError, ValueError)):
         checkpoints.restore_checkpoint(str(tmp_path), _target(num_layers=2, num_heads=8, num_mlp_layers=1))
+
+
+def test_restore_accepts_the_round1_attention_block_spelling():
+    """Checkpoints written before the naming fix called the attention block SelfAttention_<i>."""
+    opt, ema, es = _target(num_layers=1, num_heads=8, num_mlp_layers=1, mlp_dims=2048)
+    st = flax_compat.to_flax_state((opt, ema, es))
+
+    def rename(tree):
+        if not isinstance(tree, dict):
+            return tree
+        return {k.replace("MultiHeadDotProductAttention_", "SelfAttention_"): rename(v) for k, v in tree.items()}
+
+    old = rename(st)
+    assert "SelfAttention_3" in old["0"]["target"]["params"]
+    opt2, ema2, es2 = _target(num_layers=1, num_heads=8, num_mlp_layers=1, mlp_dims=2048)
+    before = opt.target.arena.flat.clone()
+    opt2, ema2, es2 = flax_compat.load_flax_state(old, (opt2, ema2, es2))
+    assert torch_equal(opt2.target.arena.flat, before)

@@ -77,7 +77,8 @@ def test_train_and_sample_cli_synthetic(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     from smd_b200 import checkpoints
     names = checkpoints.list_checkpoints(str(tmp_path / "run"))
-    assert names == ["checkpoint_3", "checkpoint_6"], names
+    # numbered by sampling_step like train_ncsn.py:382,395-399 (snapshots at steps 3 and 6; --max_steps ends the run)
+    assert names == ["checkpoint_0", "checkpoint_1"], names
     r = subprocess.run([sys.executable, "-m", "smd_b200.sample_ncsn", f"--flagfile={cfg}", "--sample_size=16"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
