@@ -134,6 +134,11 @@ inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue&
   const int tiles = ((M + rows_per_tile - 1) / rows_per_tile) * ((op.N + op.BN - 1) / op.BN) * splits;
   int groups = device_sm_count() / kCG;
   if (tiles < groups) groups = tiles;
+  if constexpr ((kF & F_LNF) != 0 && (kF & F_RAGGED) == 0) {
+    // the n-tiles of one row block exchange LayerNorm partials: keep them in the same scheduling round
+    const int num_n = (op.N + op.BN - 1) / op.BN;
+    if (groups > num_n) groups -= groups % num_n;
+  }
   if (groups < 1) groups = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * kCG));
@@ -155,6 +160,12 @@ inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue&
 
 template <int kCG>
 inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
+  if (ep.lnf_part != nullptr) {
+    // LN-fused two-pass epilogue (the caller arms it only for full, aligned tiles; see smd_api.cu::arm_lnf)
+    if (!epi_clean(op, ep) || op.N % op.BN != 0 || op.BN % 64 != 0 || op.k_splits > 1) return cudaErrorInvalidValue;
+    if (ep.residual != nullptr || ep.out_f32 != nullptr) return launch_gemm_inst<kCG, kEpiLnfB>(op, M, ep, st);
+    return launch_gemm_inst<kCG, kEpiLnfA>(op, M, ep, st);
+  }
   const uint32_t need = epi_needs(ep);
   if (epi_clean(op, ep)) {
     auto fits = [&](uint32_t kind) { return (need & ~kind) == 0; };

@@ -22,9 +22,12 @@ enum : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SWISH = 2 };
 // instruction fetch).  kEpiGeneric keeps every feature, the ragged / unaligned row-per-thread path included.
 enum : uint32_t {
   F_BIAS = 1u, F_RES = 2u, F_F32 = 4u, F_BF16 = 8u, F_PRE = 16u, F_STATS = 32u, F_LN = 64u, F_GG = 128u,
-  F_ATOMIC = 256u, F_ACT = 512u, F_RAGGED = 1024u, F_SCALE = 2048u
+  F_ATOMIC = 256u, F_ACT = 512u, F_RAGGED = 1024u, F_SCALE = 2048u, F_LNF = 4096u
 };
 static constexpr uint32_t kEpiGeneric = 0xFFFu;
+// Two-pass epilogues that finish the NEXT layer's LayerNorm -> FiLM -> swish inside this GEMM (see the F_LNF branch):
+static constexpr uint32_t kEpiLnfA = F_LNF | F_BIAS | F_BF16 | F_PRE | F_STATS;            // res-block a (+ bf16 pre-LN save)
+static constexpr uint32_t kEpiLnfB = F_LNF | F_BIAS | F_RES | F_F32 | F_BF16 | F_STATS;    // res-block b / post / in
 static constexpr uint32_t kEpiF32 = F_BIAS | F_F32 | F_STATS;                     // qkv, post, res-block a, dX outputs
 static constexpr uint32_t kEpiF32Res = F_BIAS | F_RES | F_F32 | F_STATS;          // res-block b
 static constexpr uint32_t kEpiAct = F_BIAS | F_ACT | F_BF16 | F_PRE | F_STATS;    // FFN up (+GELU); res-block a (bf16 + row stats)
@@ -49,6 +52,17 @@ struct GemmEpilogue {
   int atomic_out;               // out_f32 += v with atomics (split-K weight-gradient GEMMs; buffer pre-zeroed)
   const __nv_bfloat16* gelu_grad_of;  // v *= gelu_tanh'(gelu_grad_of[row][col]) (FFN backward), or null
   int ld_gg;
+  // ---- F_LNF: out_bf16 <- act2( film( LayerNorm(v; ln_gamma, ln_beta) ) ) over the FULL row of N columns, which
+  // spans several n-tiles computed by different CTAs: every tile publishes its per-row (sum, sumsq) partial to
+  // lnf_part and bumps the row group's counter; the tile stays parked in TMEM until the group's counter shows all
+  // partials, then the same warps normalise it (models/shared.py:61-69).  row_stats (optional) gets the totals.
+  float* lnf_part;              // [M_pad][lnf_slots][2] partial sums, slot = n_tile * 2 + column group
+  uint32_t* lnf_cnt;            // [M_pad / 32] arrival counters, zeroed before the launch
+  const float* film;            // scale at film[r * film_ld + c], shift at film[r * film_ld + N + c]; null = no FiLM
+  int film_ld;                  // row pitch of the (scale | shift) table
+  int film_bcast;               // 1: every row uses table row (*film_row_dev or 0); 0: row r uses table row r / 32
+  const int* film_row_dev;
+  int act2;                     // activation after the affine (ACT_SWISH / ACT_NONE)
 };
 
 struct GemmShape {
@@ -252,6 +266,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr bool H_BF16 = (kF & F_BF16) != 0, H_PRE = (kF & F_PRE) != 0, H_STATS = (kF & F_STATS) != 0;
     constexpr bool H_LN = (kF & F_LN) != 0, H_GG = (kF & F_GG) != 0, H_ATOMIC = (kF & F_ATOMIC) != 0;
     constexpr bool H_ACT = (kF & F_ACT) != 0, H_RAGGED = (kF & F_RAGGED) != 0, H_SCALE = (kF & F_SCALE) != 0;
+    constexpr bool H_LNF = (kF & F_LNF) != 0 && !H_RAGGED;
     const uint32_t q = warp & 3u;                      // TMEM lane quadrant this warp may access
     const int eg = static_cast<int>(warp - 4u) >> 2;   // column group 0/1: the two warps of a quadrant split the chunks
     float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * (32 * 33);
@@ -273,7 +288,213 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool aligned_ok = !H_RAGGED ||
                             ((!has_res || (ep.ld_res & 3) == 0) && (!has_f32 || (ep.ld_f32 & 3) == 0) &&
                              ((!has_bf16 && !has_pre) || (ep.ld_bf16 & 7) == 0) && (!has_gg || (ep.ld_gg & 7) == 0));
-    if constexpr (H_LN && !H_RAGGED) {
+    if constexpr (H_LNF) {
+      // ---------- two-pass epilogue: full-row (N = num_n * BN columns) LayerNorm -> FiLM -> activation -> bf16 ----------
+      // The row spans num_n tiles that other CTAs compute in the same scheduling round (tiles are m-major), so the
+      // row statistics are exchanged through global memory: pass 1 forms v = acc + bias (+ residual), stores the
+      // fp32 / pre-LN outputs, parks v back in TMEM and publishes the per-row (sum, sumsq) of its columns into its own
+      // slot; a per-32-row counter tells when all num_n * 2 slots are in; pass 2 sums the slots in a FIXED order
+      // (bit-reproducible, unlike atomics), normalises the parked tile and writes the next GEMM's bf16 operand.
+      // Deadlock freedom: tiles are visited in increasing index by co-resident persistent CTAs and a wait only targets
+      // pass 1 of tiles < index + num_n, which never waits on anything later (launch only one such kernel at a time).
+      static_assert(kEW == 8, "the LN-fused epilogue is written for 8 epilogue warps");
+      const int nslots = num_n * 2;
+      const float inv_n = 1.0f / static_cast<float>(sh.N);
+      const int act2 = ep.act2;
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        const int n_idx = tile % num_n;
+        const int row_base = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u);
+        const int row = row_base + static_cast<int>(lane);
+        const bool row_ok = row < sh.M;
+        const int n0 = n_idx * BN;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
+        float s1 = 0.f, s2 = 0.f;
+        float4 rpre[H_RES ? 8 : 1];
+        auto prefetch = [&](int c) {
+          if constexpr (H_RES) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row_base + it * 4 + f_r;
+              rpre[it] = (has_res && grow < sh.M)
+                             ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ld_res + n0 + c + f_c)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        };
+        prefetch(eg * 32);
+        // ---------------- pass 1 ----------------
+        for (int c0 = eg * 32; c0 < BN; c0 += 64) {
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
+          const int col0 = n0 + c0;
+          float4 bq[8];
+          if (has_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bq[i] = __ldg(b4 + i);
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (has_bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[4 * i] += bq[i].x; v[4 * i + 1] += bq[i].y; v[4 * i + 2] += bq[i].z; v[4 * i + 3] += bq[i].w; }
+          }
+          if constexpr (H_RES) {
+            if (has_res) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                float* d = scr + (it * 4 + f_r) * 33 + f_c;
+                d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
+              }
+              if (c0 + 64 < BN) prefetch(c0 + 64);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
+              __syncwarp();
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+          // park v in TMEM for pass 2
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+          tmem_st_32x32(taddr + static_cast<uint32_t>(c0), r);
+          if constexpr (H_F32) {
+            if (has_f32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + f_r, grow = row_base + rr;
+                if (grow < sh.M) {
+                  const float* sp = scr + rr * 33 + f_c;
+                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c) =
+                      make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          if constexpr (H_PRE) {
+            if (has_pre) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + h_r, grow = row_base + rr;
+                if (grow < sh.M) {
+                  const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
+                  *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                      make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        tmem_st_wait();
+        // publish this warp's partial of every row and count the arrival
+        {
+          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * 2 + eg);
+          __stcg(slot, make_float2(s1, s2));
+          __threadfence();
+          __syncwarp();
+          uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
+          if (lane == 0) {
+            red_release_gpu_add(cnt, 1u);
+            // ---------------- wait for the other n-tiles of this row group ----------------
+            uint32_t spins = 0;
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_gpu(cnt) < static_cast<uint32_t>(nslots)) {
+              if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
+            }
+          }
+          __syncwarp();
+        }
+        float t1 = 0.f, t2 = 0.f;
+        {
+          const float4* pp = reinterpret_cast<const float4*>(ep.lnf_part + static_cast<size_t>(row) * nslots * 2);
+          for (int s = 0; s < nslots / 2; ++s) {     // fixed order: the statistics are bit-reproducible
+            const float4 p = __ldcg(pp + s);
+            t1 += p.x; t2 += p.y; t1 += p.z; t2 += p.w;
+          }
+        }
+        const float mean = t1 * inv_n;
+        const float rstd = rsqrtf(t2 * inv_n - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
+        if (has_stats && row_ok && n_idx == 0 && eg == 0)
+          *reinterpret_cast<float2*>(ep.row_stats + 2 * static_cast<size_t>(row)) = make_float2(t1, t2);
+        // FiLM row of this warp's 32 rows (one sample when seq_len == 32)
+        const float* film_row = nullptr;
+        if (ep.film) {
+          const int fr = ep.film_bcast ? (ep.film_row_dev ? *ep.film_row_dev : 0) : (row_base >> 5);
+          film_row = ep.film + static_cast<size_t>(fr) * ep.film_ld;
+        }
+        // ---------------- pass 2 ----------------
+        for (int c0 = eg * 32; c0 < BN; c0 += 64) {
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
+          const int col0 = n0 + c0;
+          // per-column affine of this lane's 8 output columns: y = w * A + B with A = gamma * scale, B = beta * scale + shift
+          float A[8], Bc[8];
+          {
+            const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0 + h_c);
+            const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0 + h_c);
+            const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+            A[0] = g0.x; A[1] = g0.y; A[2] = g0.z; A[3] = g0.w; A[4] = g1.x; A[5] = g1.y; A[6] = g1.z; A[7] = g1.w;
+            Bc[0] = b0.x; Bc[1] = b0.y; Bc[2] = b0.z; Bc[3] = b0.w; Bc[4] = b1.x; Bc[5] = b1.y; Bc[6] = b1.z; Bc[7] = b1.w;
+            if (film_row) {
+              const float4* s4 = reinterpret_cast<const float4*>(film_row + col0 + h_c);
+              const float4* h4 = reinterpret_cast<const float4*>(film_row + sh.N + col0 + h_c);
+              const float4 s0 = __ldg(s4), s1v = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
+              const float hf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { Bc[j] = fmaf(Bc[j], sc[j], hf[j]); A[j] *= sc[j]; }
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = (__uint_as_float(r[i]) - mean) * rstd;
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + h_r, grow = row_base + rr;
+            const float* sp = scr + rr * 33 + h_c;
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float y0 = act_apply(fmaf(sp[2 * j], A[2 * j], Bc[2 * j]), act2);
+              const float y1 = act_apply(fmaf(sp[2 * j + 1], A[2 * j + 1], Bc[2 * j + 1]), act2);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&p2);
+            }
+            if (grow < sh.M)
+              *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          __syncwarp();
+        }
+        // release this accumulator stage back to the MMA issuer
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else if constexpr (H_LN && !H_RAGGED) {
       // ---------- single-pass full-row LayerNorm epilogue (N == BN <= 128: attention out-proj, FFN down) ----------
       // The two warps of a TMEM quadrant split the row's chunks, keep their values in registers, exchange the
       // per-row (sum, sumsq) partials through shared memory (named barrier of 64 threads) and each normalises

@@ -69,7 +69,7 @@ struct smd_plan {
   std::vector<smd::PackJob> pack_jobs;
   int pack_tiles = 0;
   // ---- GEMM ops ----
-  std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b;
+  std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b, op_b2;
   std::vector<FfnOp> op_ffn;   // fused FFN (cta_group 2, mlp_dims % 128 == 0)
   GemmOp op_post, op_out, op_in;
   // sampler

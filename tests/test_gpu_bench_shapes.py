@@ -11,7 +11,7 @@ true fp32 CPU oracle on the same seeded inputs.
   c512  base, C=512 (no slice) B=128                                forward + loss
 
 Every test appends the MEASURED errors to gpurun_out/parity_r02.json (copied to profiles/ after a GPU run); the
-asserted bounds are <= 2x the values measured on B200 (profiles/r02_parity_measured.json) -- bf16 tensor-core operands,
+asserted bounds are 2x the values measured on B200 (profiles/r02_parity_measured.json) -- bf16 tensor-core operands,
 fp32 accumulation, against an all-fp32 reference: SURVEY section 7 "Precision vs parity".
 """
 import json
@@ -31,16 +31,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BASE = dict(num_layers=6, num_heads=8, num_mlp_layers=2)
 LARGE = dict(num_layers=8, num_heads=16, num_mlp_layers=3)
 
-# stated tolerances vs the true fp32 oracle (<= 2x measured, see module docstring)
-# PROVISIONAL (round-1 bounds) until the first measured run of this file
-TOL_FWD_REL_L2 = 3e-2
-TOL_FWD_MAX_ABS = 0.15
-TOL_LOSS_REL = 2e-2
-TOL_GRAD_COS = 0.999
-TOL_GRAD_NORM = 2e-2
-TOL_GRAD_TENSOR = 5e-2
-TOL_STATE = 5e-3
-TOL_CHAIN = {999: 5e-2, 299: 5e-2}
+# Stated tolerances vs the true fp32 oracle = 2x the worst value measured on B200 (profiles/r02_parity_measured.json):
+#   eps_hat rel-L2 3.8e-3 .. 6.0e-3, max-abs 1.4e-2 .. 3.0e-2; |d loss| / loss 1.7e-5 .. 7.7e-4 (worst single example
+#   2.1e-3); gradient: worst tensor rel-L2 6.9e-3 .. 8.9e-3, norm ratio within 1e-3, 1 - cosine < 1e-4;
+#   state after one reverse step 1.1e-5; 200-step chain from t=999 4.6e-4, 300-step chain down to t=0 4.7e-3.
+# (SURVEY section 7 proposed rel-L2 5e-3 / max-abs 3e-2 / |d loss| 2e-3 for bf16 operands: met to within 20%.)
+TOL_FWD_REL_L2 = 1.2e-2
+TOL_FWD_MAX_ABS = 6e-2
+TOL_LOSS_REL = 2e-3
+TOL_LOSS_REL_EXAMPLE = 5e-3
+TOL_GRAD_COS = 0.9998
+TOL_GRAD_NORM = 3e-3
+TOL_GRAD_TENSOR = 2e-2
+TOL_STATE = 3e-5
+TOL_PATHS = 2e-6
+TOL_CHAIN = {999: 1e-3, 299: 1e-2}
 
 
 def record(name, **vals):
@@ -113,10 +118,10 @@ def _check_loss_and_grads(name, arch, kw, batch, shape):
     cos = dot / (np.sqrt(nn_got) * np.sqrt(total))
     nratio = float(np.sqrt(nn_got / total))
     record(name, fwd_rel_l2=fwd, fwd_max_abs=mabs, dloss_rel=dl, dloss_rel_train_path=dl_tr, dloss_rel_worst_example=dl_ex,
-           grad_cos=cos, grad_norm_ratio=nratio, grad_worst_tensor_rel_l2=worst, grad_worst_tensor=worst_name,
+           grad_cos=cos, grad_one_minus_cos=1.0 - cos, grad_norm_ratio=nratio, grad_worst_tensor_rel_l2=worst, grad_worst_tensor=worst_name,
            tokens=batch * (shape[0] if len(shape) == 2 else 1), loss=loss_ref)
     assert fwd < TOL_FWD_REL_L2 and mabs < TOL_FWD_MAX_ABS
-    assert dl < TOL_LOSS_REL and dl_tr < TOL_LOSS_REL
+    assert dl < TOL_LOSS_REL and dl_tr < TOL_LOSS_REL and dl_ex < TOL_LOSS_REL_EXAMPLE
     assert cos > TOL_GRAD_COS and abs(nratio - 1.0) < TOL_GRAD_NORM
     assert worst < TOL_GRAD_TENSOR, (worst, worst_name)
 
@@ -205,7 +210,7 @@ def test_sampling_n1000_reverse_step_graph_path(lib, name, channels):
     assert e_eps < TOL_FWD_REL_L2 and e_abs < TOL_FWD_MAX_ABS
     # x' = mu1 * clip(x/sqrt(abar) - sqrt(1-abar)/sqrt(abar) eps_hat) + mu2 x + sigma z with mu1(t=999) ~ 8e-4:
     # the eps_hat error is damped by mu1 * 12.2 ~ 1e-2 before it reaches the state
-    assert e_graph < TOL_STATE and e_plain < TOL_STATE and e_paths < TOL_STATE
+    assert e_graph < TOL_STATE and e_plain < TOL_STATE and e_paths < TOL_PATHS
     assert m_err < 5e-3
 
 

@@ -1,8 +1,9 @@
 """Score-network parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
 
 Tolerances (stated): vs the bf16-operand-emulating oracle rel-L2 <= 1e-2 (kernel logic; only accumulation order,
-fast-exp and flipped bf16 roundings differ -- measured 2e-3 at 2 layers, 4e-3 at 6); vs the true fp32/fp64 oracle rel-L2 <= 3e-2 and max-abs <= 0.15 on eps_hat
-(bf16 tensor-core operands, fp32 accumulate -- SURVEY section 7 "Precision vs parity")."""
+fast-exp and flipped bf16 roundings differ -- measured 2e-3 at 2 layers, 4e-3 at 6); vs the true fp32/fp64 oracle rel-L2
+<= 1.2e-2 and max-abs <= 6e-2 on eps_hat, |d loss| <= 5e-3 loss per example (bf16 tensor-core operands, fp32 accumulate --
+2x the values measured at the benchmarked sizes, profiles/r02_parity_measured.json)."""
 import os
 
 import numpy as np
@@ -37,8 +38,8 @@ def test_transformer_forward_parity(lib, case, cg):
     ref_bf = O.transformer_ddpm(p, torch.from_numpy(x), torch.from_numpy(t), emulate_bf16=True, **okw)
     ref32 = O.transformer_ddpm(p, torch.from_numpy(x), torch.from_numpy(t), **okw)
     assert rel_l2(y, ref_bf) < 1e-2
-    assert rel_l2(y, ref32) < 3e-2
-    assert float((y.cpu() - ref32).abs().max()) < 0.15
+    assert rel_l2(y, ref32) < 1.2e-2
+    assert float((y.cpu() - ref32).abs().max()) < 6e-2
 
 
 def test_forward_batch_ragged_and_broadcast_t(lib):
@@ -64,7 +65,7 @@ def test_dense_ddpm_forward_parity(lib):
     ref_bf = O.dense_ddpm(p, torch.from_numpy(x), torch.from_numpy(t), emulate_bf16=True, **okw)
     ref32 = O.dense_ddpm(p, torch.from_numpy(x), torch.from_numpy(t), **okw)
     assert rel_l2(y, ref_bf) < 1e-2
-    assert rel_l2(y, ref32) < 3e-2
+    assert rel_l2(y, ref32) < 1.2e-2
 
 
 def test_golden_fixture(lib):
@@ -75,10 +76,10 @@ def test_golden_fixture(lib):
     eng = Engine(ModelConfig(**kw), max_batch=3, cta_group=2)
     eng.set_params(eng.init_params(int(g["param_seed"]), perturb=float(g["perturb"])))
     y = eng.forward(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda())
-    assert rel_l2(y, torch.from_numpy(g["y64"])) < 3e-2
+    assert rel_l2(y, torch.from_numpy(g["y64"])) < 1.2e-2
     loss = eng.ddpm_loss(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["used_alpha"]).cuda(),
                          torch.from_numpy(g["eps"]).cuda())
-    np.testing.assert_allclose(loss.cpu().numpy(), g["loss64"], rtol=3e-2)
+    np.testing.assert_allclose(loss.cpu().numpy(), g["loss64"], rtol=5e-3)
 
 
 def test_ddpm_loss_parity(lib):
@@ -96,9 +97,9 @@ def test_ddpm_loss_parity(lib):
     okw = oracle_kwargs(eng.cfg)
     ref, ref_pred = O.diffusion_loss_tensors(lambda a, c: O.transformer_ddpm(p, a, c, **okw), torch.from_numpy(x0),
                                              torch.from_numpy(used), torch.from_numpy(eps), "none")
-    assert rel_l2(pred, ref_pred) < 3e-2
-    # |d loss| <= 2e-2 * loss (stated tolerance on ddpm_loss for bf16 operands)
-    np.testing.assert_allclose(loss.cpu().numpy(), ref.numpy(), rtol=2e-2)
+    assert rel_l2(pred, ref_pred) < 1.2e-2
+    # |d loss| <= 5e-3 * loss per example (stated tolerance on ddpm_loss for bf16 operands; measured 2e-3 worst case)
+    np.testing.assert_allclose(loss.cpu().numpy(), ref.numpy(), rtol=5e-3)
 
 
 def test_fused_ffn_kernel(lib):

@@ -1,7 +1,9 @@
 """Backward / optimizer parity: hand-written CUDA backward vs torch autograd on the CPU oracle.
 
-Tolerances (stated): per-tensor rel-L2 <= 5e-2 for tensors carrying >= 1e-4 of the gradient energy, global cosine
->= 0.999 and |norm ratio - 1| <= 2e-2 (bf16 tensor-core operands in both forward and backward GEMMs)."""
+Tolerances (stated): per-tensor rel-L2 <= 3e-2 for tensors carrying >= 1e-4 of the gradient energy, global cosine
+>= 0.9995 and |norm ratio - 1| <= 1e-2 (bf16 tensor-core operands in both forward and backward GEMMs; at the benchmarked
+sizes the measured values are 9e-3 / 1 - 1e-4 / 1e-3, profiles/r02_parity_measured.json -- the small batches here are
+noisier per tensor)."""
 import numpy as np
 import pytest
 import torch
@@ -56,7 +58,7 @@ def test_gradients_match_autograd(lib, case, cg):
     torch.cuda.synchronize()
     got = eng.flat_to_dict(eng.grads)
     loss_ref, ref = _oracle_grads(arch, eng, flat, x0, used, eps, emulate=False)
-    assert abs(float(eng.loss_sum) / batch - loss_ref) < 2e-2 * loss_ref
+    assert abs(float(eng.loss_sum) / batch - loss_ref) < 5e-3 * loss_ref
     total = sum(float((g ** 2).sum()) for g in ref.values())
     dot = nn_got = 0.0
     report = []
@@ -67,10 +69,10 @@ def test_gradients_match_autograd(lib, case, cg):
         e = rel_l2(gg, g)
         report.append((e, name))
         if float((g ** 2).sum()) >= 1e-4 * total:
-            assert e < 5e-2, f"{name}: rel-L2 {e:.3e}\n" + "\n".join(f"{a:.3e} {b}" for a, b in sorted(report)[-12:])
+            assert e < 3e-2, f"{name}: rel-L2 {e:.3e}\n" + "\n".join(f"{a:.3e} {b}" for a, b in sorted(report)[-12:])
     cos = dot / (np.sqrt(nn_got) * np.sqrt(total))
-    assert cos > 0.999, (cos, sorted(report)[-12:])
-    assert abs(np.sqrt(nn_got / total) - 1.0) < 2e-2
+    assert cos > 0.9995, (cos, sorted(report)[-12:])
+    assert abs(np.sqrt(nn_got / total) - 1.0) < 1e-2
     # every tensor (also the tiny ones) must at least be close in absolute terms
     for name, g in ref.items():
         gg = torch.from_numpy(got[name])
