@@ -53,7 +53,13 @@ typedef struct smd_config {
   int training;        /* 1: reserve the saved-activation / gradient buffers of smd_ddpm_grads */
   int sampler_T;       /* > 0: reserve a (K, sampler_T, 2*mlp_dims) FiLM table so the sampler evaluates the FiLM
                           generator once per schedule instead of once per step (all samples share t) */
+  int precision;       /* smd_precision.  SMD_PRECISION_BF16X3 (forward / sampling only, ~3x the GEMM time): every
+                          tensor-core operand is split into bf16 hi + lo halves and the GEMMs add the cross terms
+                          (hi*hi + hi*lo + lo*hi, fp32 accumulate), activations use exact tanhf / expf and attention runs
+                          in fp32 -- the mode that shows the kernels reproduce the reference's fp32 arithmetic to ~1e-5
+                          rather than to bf16 accuracy (tests/test_gpu_strict.py) */
 } smd_config;
+enum smd_precision { SMD_PRECISION_BF16 = 0, SMD_PRECISION_BF16X3 = 1 };
 
 const char* smd_last_error(void);
 int smd_version(void);

@@ -91,13 +91,14 @@ static cudaError_t gemm_k(const GemmOp& op0, int rows, int K, int splits, const 
 
 using namespace smd;
 
-extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0, const float* used_alpha,
-                              const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
-                              smd_stream_t stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!p->cfg.training) { set_error("plan was not created with training = 1"); return SMD_ERR_STATE; }
-  if (!p->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
-  if (batch < 1 || batch > p->cfg.max_batch || global_batch < batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+// ind: device table {x0, used_alpha, eps} read by the kernels instead of the pointer arguments (graph replay), or null.
+// capturing: the call is being recorded into a CUDA graph -- the three "tail gradients are final" events that
+// smd_wait_tail_grads hands to the caller's communication stream are then recorded as EXTERNAL event nodes, so a stream
+// outside the graph can wait on them after the graph has been launched.
+static int grads_impl(smd_plan* p, const float* params, const float* x0, const float* used_alpha, const float* eps,
+                      const float* const* ind, int batch, int global_batch, float* grads, float* loss_sum,
+                      cudaStream_t st, bool capturing) {
+  const unsigned ext = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
   TrainState& ts = p->train;
   uint8_t* ws = p->ws;
   const smd_config& c = p->cfg;
@@ -111,7 +112,29 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   auto B16 = [&](size_t off) { return ts.at<__nv_bfloat16>(ws, off); };
   auto F32 = [&](size_t off) { return ts.at<float>(ws, off); };
 
-  SMD_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * p->arena, st));
+  { int rcs = ensure_side_stream(p); if (rcs) return rcs; }
+  cudaStream_t side = p->side_stream;
+  cudaStream_t dws = p->dw_stream;
+  // Weight-gradient GEMMs are leaves of the backward graph: they run on dw_stream next to the dX chain; every gradient
+  // operand they read has its own buffer, so nothing they read is rewritten within this backward pass.
+  auto fork_dw = [&]() -> cudaError_t {
+    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
+    if (e1 != cudaSuccess) return e1;
+    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
+  };
+  // dX GEMM outputs (gradient wrt a bf16 activation), stored as bf16: half the epilogue / LayerNorm-backward bytes
+  __nv_bfloat16* g16 = B16(ts.off_g32a);
+  float* du32 = F32(ts.off_g32b);   // gradient of the fp32 residual stream u
+  float* stats = p->buf<float>("stats");
+  const size_t sstride = static_cast<size_t>(p->Mp) * 2;
+  const int nkb = Mk / 64;
+  float* xt = p->buf<float>("xt");
+
+  // Zeroing the 100 MB gradient arena (~20 us) goes to the weight-gradient stream: the forward pass does not touch it
+  // and every writer either runs on that stream or is ordered after ev_gz below.
+  SMD_CUDA(fork_dw());
+  SMD_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * p->arena, dws));
+  SMD_CUDA(cudaEventRecord(p->ev_gz, dws));
   // FiLM (scale|shift) gradients are accumulated with atomics by the two CTAs of a sample and by both uses of a pair
   SMD_CUDA(cudaMemsetAsync(ts.at<float>(ws, ts.off_dss), 0,
                            sizeof(float) * static_cast<size_t>(ts.K > 0 ? ts.K : 1) * c.max_batch * 2 * Md, st));
@@ -135,39 +158,23 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   }
 
   // ---------------- forward (keeps every activation) ----------------
-  float* xt = p->buf<float>("xt");
   float* cond = p->buf<float>("tvec");
   float* pred = p->buf<float>("eps_hat");
-  launch_q_sample(x0, eps, used_alpha, xt, cond, batch, per, st); CNT();
+  launch_q_sample(x0, eps, used_alpha, xt, cond, batch, per, st, ind); CNT();
   int rc = run_forward(p, params, xt, cond, 0, batch, pred, st, &ts);
   if (rc) return rc;
+  SMD_CUDA(cudaStreamWaitEvent(st, p->ev_gz, 0));   // gradient arena zeroed (long done by now)
 
   // ---------------- objective ----------------
   const float gscale = 1.0f / (static_cast<float>(global_batch) * static_cast<float>(per));
   float* dpred32 = F32(ts.off_dpred32);
   __nv_bfloat16* dpred16 = B16(ts.off_dpred16);
-  { int rcs = ensure_side_stream(p); if (rcs) return rcs; }
-  cudaStream_t side = p->side_stream;
-  cudaStream_t dws = p->dw_stream;
-  // Weight-gradient GEMMs are leaves of the backward graph: they run on dw_stream next to the dX chain; every gradient
-  // operand they read has its own buffer, so nothing they read is rewritten within this backward pass.
-  auto fork_dw = [&]() -> cudaError_t {
-    cudaError_t e1 = cudaEventRecord(p->ev_dw, st);
-    if (e1 != cudaSuccess) return e1;
-    return cudaStreamWaitEvent(dws, p->ev_dw, 0);
-  };
   ddpm_loss_bwd_kernel<<<batch, 256, 0, st>>>(eps, pred, F32(ts.off_loss), loss_sum, ts.at<unsigned int>(ws, ts.off_loss_ctr),
-                                              1.0f / static_cast<float>(global_batch), dpred32, dpred16, gscale, S, C, Cp);
+                                              1.0f / static_cast<float>(global_batch), dpred32, dpred16, gscale, S, C, Cp,
+                                              ind);
   CNT();
   SMD_CUDA(fork_dw());
   launch_colsum<float>(dpred32, C, G("out.bias"), M, C, dws); CNT();
-
-  // dX GEMM outputs (gradient wrt a bf16 activation), stored as bf16: half the epilogue / LayerNorm-backward bytes
-  __nv_bfloat16* g16 = B16(ts.off_g32a);
-  float* du32 = F32(ts.off_g32b);   // gradient of the fp32 residual stream u
-  float* stats = p->buf<float>("stats");
-  const size_t sstride = static_cast<size_t>(p->Mp) * 2;
-  const int nkb = Mk / 64;
 
   // ---------------- output projection + final LayerNorm ----------------
   {
@@ -258,9 +265,11 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
     launch_colsum<float>(de1, 512, G(pre + "film.d1.bias"), batch, 512, side); CNT();
     launch_small_linear_bwd_w(enc, de1, G(pre + "film.d1.kernel"), batch, 128, 512, side); CNT();
   }
-  SMD_CUDA(cudaEventRecord(p->ev_join, side));
-  SMD_CUDA(cudaEventRecord(p->ev_tail, st));   // every k*. / out_ln / out gradient is final (smd_wait_tail_grads)
-  SMD_CUDA(cudaEventRecord(p->ev_dwtail, dws));
+  // every k*. / out_ln / out gradient is final once these three have fired (smd_wait_tail_grads)
+  SMD_CUDA(cudaEventRecordWithFlags(p->evx_join, side, ext));
+  SMD_CUDA(cudaEventRecord(p->ev_join, side));   // internal join marker (last node of the side stream: `st` waits on it)
+  SMD_CUDA(cudaEventRecordWithFlags(p->ev_tail, st, ext));
+  SMD_CUDA(cudaEventRecordWithFlags(p->ev_dwtail, dws, ext));
   SMD_LAUNCH_CHECK("backward tail");
 
   if (ts.L == 0) {
@@ -368,5 +377,65 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   SMD_CUDA(cudaStreamWaitEvent(st, p->ev_dwjoin, 0));
   SMD_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
   SMD_LAUNCH_CHECK("backward trunk");
+  return SMD_OK;
+}
+
+// SMD_TRAIN_GRAPH=0 switches the graph replay of the train step off (eager launches, 3 streams, as in round 1)
+static bool train_graph_enabled() {
+  static const bool on = [] { const char* v = getenv("SMD_TRAIN_GRAPH"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
+static void drop_train_graph(smd_plan* p) {
+  if (p->tg_exec) { cudaGraphExecDestroy(p->tg_exec); p->tg_exec = nullptr; }
+  p->tg_valid = false;
+}
+
+extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0, const float* used_alpha,
+                              const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
+                              smd_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!p->cfg.training) { set_error("plan was not created with training = 1"); return SMD_ERR_STATE; }
+  if (!p->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (batch < 1 || batch > p->cfg.max_batch || global_batch < batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (!train_graph_enabled() || !capturable)
+    return grads_impl(p, params, x0, used_alpha, eps, nullptr, batch, global_batch, grads, loss_sum, st, false);
+  // Graph replay: the pass's ~150 launches on three streams (dX chain, weight-gradient GEMMs, FiLM generator) are
+  // captured once into one CUDA graph with the same fork / join structure.  The per-step inputs (x0, used_alpha, eps)
+  // reach the kernels through a 3-pointer device table, so new input tensors do not force a re-capture; the events a
+  // data-parallel caller waits on (smd_wait_tail_grads) are external event-record nodes of the graph.
+  const bool same = p->tg_valid && p->tg_params == params && p->tg_grads == grads && p->tg_loss == loss_sum &&
+                    p->tg_batch == batch && p->tg_global == global_batch;
+  const float** ind = p->buf<const float*>("t.ind");
+  if (!same) {
+    const bool warm = p->tg_warm && p->tg_params == params && p->tg_batch == batch;
+    drop_train_graph(p);
+    p->tg_params = params; p->tg_grads = grads; p->tg_loss = loss_sum; p->tg_batch = batch; p->tg_global = global_batch;
+    if (!warm) {
+      // first use of this configuration runs eagerly: lazy one-time calls (function attributes, stream / event
+      // creation) stay out of the capture
+      p->tg_warm = true;
+      return grads_impl(p, params, x0, used_alpha, eps, nullptr, batch, global_batch, grads, loss_sum, st, false);
+    }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches.load();
+    SMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = grads_impl(p, params, nullptr, nullptr, nullptr, ind, batch, global_batch, grads, loss_sum, st, true);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    p->tg_nodes = g_launches.load() - before;
+    g_launches.store(before);   // captured launches are counted per replay
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { set_error(std::string("train graph capture: ") + cudaGetErrorString(ce)); return SMD_ERR_CUDA; }
+    ce = cudaGraphInstantiate(&p->tg_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { set_error(std::string("train graph instantiate: ") + cudaGetErrorString(ce)); return SMD_ERR_CUDA; }
+    p->tg_valid = true;
+  }
+  // (pageable source: the driver stages these 24 bytes before returning, so the host array may die with this frame)
+  const float* host_ind[3] = {x0, used_alpha, eps};
+  SMD_CUDA(cudaMemcpyAsync(ind, host_ind, sizeof(host_ind), cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaGraphLaunch(p->tg_exec, st));
+  g_launches.fetch_add(p->tg_nodes, std::memory_order_relaxed);
   return SMD_OK;
 }

@@ -1023,8 +1023,10 @@ inline void launch_small_linear_bwd_x(const float* g, const float* W, const floa
 __global__ void __launch_bounds__(256)
 ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
                      float* __restrict__ loss_sum, unsigned int* __restrict__ done_counter, float inv_global_batch,
-                     float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16, float gscale, int S, int C, int Cp) {
+                     float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16, float gscale, int S, int C, int Cp,
+                     const float* const* __restrict__ ind) {
   pdl_trigger();
+  if (ind) eps = ind[2];
   const int b = blockIdx.x;
   const int per = S * C;
   const size_t base = static_cast<size_t>(b) * per;

@@ -48,6 +48,8 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, ui
 
 struct GemmOp {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmA_lo, tmB_lo;   // strict-precision mode: the lo halves of both operands (has_lo)
+  bool has_lo = false;
   int N = 0, K = 0, BN = 0, cg = 1, a_mn = 0, b_mn = 0, k_splits = 1;
 };
 
@@ -61,7 +63,14 @@ inline int choose_bn(int N, int cg) {
 
 // A: K-major [a_rows][K] (a_mn=0) or MN-major [K][a_rows] (a_mn=1); same for B with N rows.
 inline bool make_gemm_op(GemmOp* op, const void* A, uint64_t a_rows, const void* B, uint64_t b_rows_total, int N,
-                         int K, int BN, int cg, int a_mn, int b_mn, uint64_t k_rows_a = 0, uint64_t k_rows_b = 0) {
+                         int K, int BN, int cg, int a_mn, int b_mn, uint64_t k_rows_a = 0, uint64_t k_rows_b = 0,
+                         size_t lo_bytes = 0) {
+  if (lo_bytes) {
+    GemmOp lo;
+    if (!make_gemm_op(&lo, static_cast<const uint8_t*>(A) + lo_bytes, a_rows, static_cast<const uint8_t*>(B) + lo_bytes,
+                      b_rows_total, N, K, BN, cg, a_mn, b_mn, k_rows_a, k_rows_b, 0)) return false;
+    op->tmA_lo = lo.tmA; op->tmB_lo = lo.tmB; op->has_lo = true;
+  }
   op->N = N; op->K = K; op->BN = BN; op->cg = cg; op->a_mn = a_mn; op->b_mn = b_mn; op->k_splits = 1;
   if (K % 64 != 0) { set_error("GEMM K must be a multiple of 64"); return false; }
   if (BN % (16 * cg) != 0 || BN > 256 || BN < 16 * cg) { set_error("bad BN " + std::to_string(BN)); return false; }

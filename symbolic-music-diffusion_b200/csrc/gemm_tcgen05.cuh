@@ -57,12 +57,16 @@ struct GemmEpilogue {
   // lnf_part and bumps the row group's counter; the tile stays parked in TMEM until the group's counter shows all
   // partials, then the same warps normalise it (models/shared.py:61-69).  row_stats (optional) gets the totals.
   float* lnf_part;              // [M_pad][lnf_slots][2] partial sums, slot = n_tile * 2 + column group
+  __nv_bfloat16* lnf_ring;      // [gridDim][2][128][BN] bf16 parking for v when neither out_f32 nor out_bf16_pre keeps it
   uint32_t* lnf_cnt;            // [M_pad / 32] arrival counters, zeroed before the launch
   const float* film;            // scale at film[r * film_ld + c], shift at film[r * film_ld + N + c]; null = no FiLM
   int film_ld;                  // row pitch of the (scale | shift) table
   int film_bcast;               // 1: every row uses table row (*film_row_dev or 0); 0: row r uses table row r / 32
   const int* film_row_dev;
   int act2;                     // activation after the affine (ACT_SWISH / ACT_NONE)
+  // ---- strict-precision mode (bf16x3): every bf16 operand written through out_bf16 also gets its lo half at
+  // out_bf16 + lo_delta (elements), and the activations use exact tanhf / expf.  0 = off.
+  long long lo_delta;
 };
 
 struct GemmShape {
@@ -106,6 +110,28 @@ __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   const float u = c * (x + 0.044715f * x * x * x);
   const float th = tanh_fast(u);
   return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * c * (1.0f + 3.0f * 0.044715f * x * x);
+}
+
+// exact variants for the strict-precision mode (the tanh.approx forms above are good to ~5e-4 absolute)
+__device__ __forceinline__ float act_apply_exact(float v, int act) {
+  if (act == ACT_GELU_TANH) {
+    const float c = 0.7978845608028654f;
+    return 0.5f * v * (1.0f + tanhf(c * (v + 0.044715f * v * v * v)));
+  } else if (act == ACT_SWISH) {
+    return v / (1.0f + expf(-v));
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// lo halves of a pair: bf16(x - float(bf16(x)))
+__device__ __forceinline__ uint32_t pack_bf16x2_lo(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 p = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  return *reinterpret_cast<uint32_t*>(&p);
 }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -289,24 +315,126 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             ((!has_res || (ep.ld_res & 3) == 0) && (!has_f32 || (ep.ld_f32 & 3) == 0) &&
                              ((!has_bf16 && !has_pre) || (ep.ld_bf16 & 7) == 0) && (!has_gg || (ep.ld_gg & 7) == 0));
     if constexpr (H_LNF) {
-      // ---------- two-pass epilogue: full-row (N = num_n * BN columns) LayerNorm -> FiLM -> activation -> bf16 ----------
-      // The row spans num_n tiles that other CTAs compute in the same scheduling round (tiles are m-major), so the
-      // row statistics are exchanged through global memory: pass 1 forms v = acc + bias (+ residual), stores the
-      // fp32 / pre-LN outputs, parks v back in TMEM and publishes the per-row (sum, sumsq) of its columns into its own
-      // slot; a per-32-row counter tells when all num_n * 2 slots are in; pass 2 sums the slots in a FIXED order
-      // (bit-reproducible, unlike atomics), normalises the parked tile and writes the next GEMM's bf16 operand.
-      // Deadlock freedom: tiles are visited in increasing index by co-resident persistent CTAs and a wait only targets
-      // pass 1 of tiles < index + num_n, which never waits on anything later (launch only one such kernel at a time).
+      // ---------- epilogue that also finishes the NEXT LayerNorm -> FiLM -> activation over the FULL row ----------
+      // The row (N = num_n * BN columns) spans num_n tiles computed by other CTAs in the same scheduling round (tiles
+      // are m-major), so the row statistics are exchanged through global memory.
+      //   pass 1 (per tile): v = acc + bias (+ residual); v is stored -- fp32 to out_f32 (kinds with F_F32), otherwise
+      //     bf16 to out_bf16_pre or, when that is null, to a per-CTA ring in lnf_ring -- the TMEM stage is released at
+      //     once, and the warp publishes its per-row (sum, sumsq) into its own slot and bumps the row group's counter;
+      //   pass 2 (one tile LATER, so the exchange latency hides behind the next tile's pass 1): the counter is checked,
+      //     the slots are summed in a FIXED order (bit-reproducible, unlike atomics), v is read back through L2 and
+      //     out_bf16 <- act2(film(LN(v))) is written -- what the stand-alone ln_film_act kernel did with an HBM round
+      //     trip and a launch of its own.
+      // Deadlock freedom: tiles are visited in increasing index by co-resident persistent CTAs; a wait only targets
+      // pass 1 of tiles of the same round, which never waits on anything (launch one such kernel at a time).
       static_assert(kEW == 8, "the LN-fused epilogue is written for 8 epilogue warps");
+      constexpr bool SRC_F32 = H_F32;
       const int nslots = num_n * 2;
       const float inv_n = 1.0f / static_cast<float>(sh.N);
       const int act2 = ep.act2;
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
+      __nv_bfloat16* ring = ep.lnf_ring ? ep.lnf_ring + static_cast<size_t>(blockIdx.x) * 2 * kBM * BN : nullptr;
+      int p_row_base = -1, p_n0 = 0, p_nidx = 0, p_stride = 0;   // tile whose pass 2 is pending
+      const void* p_src = nullptr;
+      auto pass2 = [&]() {
+        const int row_base = p_row_base, n0 = p_n0;
+        const int row = row_base + static_cast<int>(lane);
+        uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
+        if (lane == 0) {
+          uint32_t spins = 0;
+          const unsigned long long t0 = global_timer_ns();
+          while (ld_acquire_gpu(cnt) < static_cast<uint32_t>(nslots)) {
+            if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
+          }
+        }
+        __syncwarp();
+        float t1 = 0.f, t2 = 0.f;
+        {
+          const float4* pp = reinterpret_cast<const float4*>(ep.lnf_part + static_cast<size_t>(row) * nslots * 2);
+          for (int s = 0; s < nslots / 2; ++s) {     // fixed order: the statistics are bit-reproducible
+            const float4 p = __ldcg(pp + s);
+            t1 += p.x; t2 += p.y; t1 += p.z; t2 += p.w;
+          }
+        }
+        const float mean_l = t1 * inv_n;
+        const float rstd_l = rsqrtf(t2 * inv_n - mean_l * mean_l + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
+        if (has_stats && row < sh.M && p_nidx == 0 && eg == 0)
+          *reinterpret_cast<float2*>(ep.row_stats + 2 * static_cast<size_t>(row)) = make_float2(t1, t2);
+        scr[2 * lane] = mean_l; scr[2 * lane + 1] = rstd_l;
+        __syncwarp();
+        const float* film_row = nullptr;       // FiLM row of this warp's 32 rows (one sample when seq_len == 32)
+        if (ep.film) {
+          const int fr = ep.film_bcast ? (ep.film_row_dev ? *ep.film_row_dev : 0) : (row_base >> 5);
+          film_row = ep.film + static_cast<size_t>(fr) * ep.film_ld;
+        }
+        for (int c0 = eg * 32; c0 < BN; c0 += 64) {
+          const int col0 = n0 + c0;
+          // per-column affine of this lane's 8 columns: y = xhat * A + B, A = gamma * scale, B = beta * scale + shift
+          float A[8], Bc[8];
+          {
+            const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0 + h_c);
+            const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0 + h_c);
+            const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+            A[0] = g0.x; A[1] = g0.y; A[2] = g0.z; A[3] = g0.w; A[4] = g1.x; A[5] = g1.y; A[6] = g1.z; A[7] = g1.w;
+            Bc[0] = b0.x; Bc[1] = b0.y; Bc[2] = b0.z; Bc[3] = b0.w; Bc[4] = b1.x; Bc[5] = b1.y; Bc[6] = b1.z; Bc[7] = b1.w;
+            if (film_row) {
+              const float4* s4 = reinterpret_cast<const float4*>(film_row + col0 + h_c);
+              const float4* h4 = reinterpret_cast<const float4*>(film_row + sh.N + col0 + h_c);
+              const float4 s0 = __ldg(s4), s1v = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
+              const float hf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { Bc[j] = fmaf(Bc[j], sc[j], hf[j]); A[j] *= sc[j]; }
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + h_r, grow = row_base + rr;
+            float x[8];
+            if constexpr (SRC_F32) {
+              const float* sp = static_cast<const float*>(p_src) + static_cast<size_t>(rr) * p_stride + c0 + h_c;
+              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+              if (grow < sh.M) { a0 = __ldcg(reinterpret_cast<const float4*>(sp)); a1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1); }
+              x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+            } else {
+              const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(p_src) + static_cast<size_t>(rr) * p_stride + c0 + h_c;
+              uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+              if (grow < sh.M) raw = __ldcg(reinterpret_cast<const uint4*>(sp));
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hp[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+            }
+            const float mean = scr[2 * rr], rstd = scr[2 * rr + 1];
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float y0 = act_apply(fmaf((x[2 * j] - mean) * rstd, A[2 * j], Bc[2 * j]), act2);
+              const float y1 = act_apply(fmaf((x[2 * j + 1] - mean) * rstd, A[2 * j + 1], Bc[2 * j + 1]), act2);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&p2);
+            }
+            if (grow < sh.M)
+              *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        __syncwarp();
+      };
+      int iter = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++iter) {
         const int n_idx = tile % num_n;
         const int row_base = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u);
         const int row = row_base + static_cast<int>(lane);
-        const bool row_ok = row < sh.M;
         const int n0 = n_idx * BN;
+        // where pass 1 leaves v for pass 2 (element [0][0] = this warp's first row, the tile's first column)
+        const void* src; int stride;
+        __nv_bfloat16* vb = nullptr;
+        if constexpr (SRC_F32) {
+          src = ep.out_f32 + static_cast<size_t>(row_base) * ep.ld_f32 + n0; stride = ep.ld_f32;
+        } else {
+          if (has_pre) { vb = ep.out_bf16_pre + static_cast<size_t>(row_base) * ep.ld_bf16 + n0; stride = ep.ld_bf16; }
+          else { vb = ring + (static_cast<size_t>(iter & 1) * kBM + q * 32u) * BN; stride = BN; }
+          src = vb;
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
@@ -360,132 +488,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
-          // park v in TMEM for pass 2
+          if constexpr (SRC_F32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
-          tmem_st_32x32(taddr + static_cast<uint32_t>(c0), r);
-          if constexpr (H_F32) {
-            if (has_f32) {
+            for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+            __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
-              __syncwarp();
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + f_r, grow = row_base + rr;
-                if (grow < sh.M) {
-                  const float* sp = scr + rr * 33 + f_c;
-                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c) =
-                      make_float4(sp[0], sp[1], sp[2], sp[3]);
-                }
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + f_r, grow = row_base + rr;
+              if (grow < sh.M) {
+                const float* sp = scr + rr * 33 + f_c;
+                *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c) =
+                    make_float4(sp[0], sp[1], sp[2], sp[3]);
               }
-              __syncwarp();
             }
-          }
-          if constexpr (H_PRE) {
-            if (has_pre) {
+            __syncwarp();
+          } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + h_r, grow = row_base + rr;
+              if (!has_pre || grow < sh.M) {
+                const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
+                *reinterpret_cast<uint4*>(vb + static_cast<size_t>(rr) * stride + c0 + h_c) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
               }
-              __syncwarp();
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int rr = it * 8 + h_r, grow = row_base + rr;
-                if (grow < sh.M) {
-                  const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                  *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
-                      make_uint4(sp[0], sp[1], sp[2], sp[3]);
-                }
-              }
-              __syncwarp();
             }
+            __syncwarp();
           }
         }
-        tmem_st_wait();
-        // publish this warp's partial of every row and count the arrival
-        {
-          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * 2 + eg);
-          __stcg(slot, make_float2(s1, s2));
-          __threadfence();
-          __syncwarp();
-          uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
-          if (lane == 0) {
-            red_release_gpu_add(cnt, 1u);
-            // ---------------- wait for the other n-tiles of this row group ----------------
-            uint32_t spins = 0;
-            const unsigned long long t0 = global_timer_ns();
-            while (ld_acquire_gpu(cnt) < static_cast<uint32_t>(nslots)) {
-              if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
-            }
-          }
-          __syncwarp();
-        }
-        float t1 = 0.f, t2 = 0.f;
-        {
-          const float4* pp = reinterpret_cast<const float4*>(ep.lnf_part + static_cast<size_t>(row) * nslots * 2);
-          for (int s = 0; s < nslots / 2; ++s) {     // fixed order: the statistics are bit-reproducible
-            const float4 p = __ldcg(pp + s);
-            t1 += p.x; t2 += p.y; t1 += p.z; t2 += p.w;
-          }
-        }
-        const float mean = t1 * inv_n;
-        const float rstd = rsqrtf(t2 * inv_n - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
-        if (has_stats && row_ok && n_idx == 0 && eg == 0)
-          *reinterpret_cast<float2*>(ep.row_stats + 2 * static_cast<size_t>(row)) = make_float2(t1, t2);
-        // FiLM row of this warp's 32 rows (one sample when seq_len == 32)
-        const float* film_row = nullptr;
-        if (ep.film) {
-          const int fr = ep.film_bcast ? (ep.film_row_dev ? *ep.film_row_dev : 0) : (row_base >> 5);
-          film_row = ep.film + static_cast<size_t>(fr) * ep.film_ld;
-        }
-        // ---------------- pass 2 ----------------
-        for (int c0 = eg * 32; c0 < BN; c0 += 64) {
-          __syncwarp();
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
-          const int col0 = n0 + c0;
-          // per-column affine of this lane's 8 output columns: y = w * A + B with A = gamma * scale, B = beta * scale + shift
-          float A[8], Bc[8];
-          {
-            const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0 + h_c);
-            const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0 + h_c);
-            const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-            A[0] = g0.x; A[1] = g0.y; A[2] = g0.z; A[3] = g0.w; A[4] = g1.x; A[5] = g1.y; A[6] = g1.z; A[7] = g1.w;
-            Bc[0] = b0.x; Bc[1] = b0.y; Bc[2] = b0.z; Bc[3] = b0.w; Bc[4] = b1.x; Bc[5] = b1.y; Bc[6] = b1.z; Bc[7] = b1.w;
-            if (film_row) {
-              const float4* s4 = reinterpret_cast<const float4*>(film_row + col0 + h_c);
-              const float4* h4 = reinterpret_cast<const float4*>(film_row + sh.N + col0 + h_c);
-              const float4 s0 = __ldg(s4), s1v = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
-              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
-              const float hf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { Bc[j] = fmaf(Bc[j], sc[j], hf[j]); A[j] *= sc[j]; }
-            }
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = (__uint_as_float(r[i]) - mean) * rstd;
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + h_r, grow = row_base + rr;
-            const float* sp = scr + rr * 33 + h_c;
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float y0 = act_apply(fmaf(sp[2 * j], A[2 * j], Bc[2 * j]), act2);
-              const float y1 = act_apply(fmaf(sp[2 * j + 1], A[2 * j + 1], Bc[2 * j + 1]), act2);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
-              pk[j] = *reinterpret_cast<uint32_t*>(&p2);
-            }
-            if (grow < sh.M)
-              *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-          __syncwarp();
-        }
-        // release this accumulator stage back to the MMA issuer
+        // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA issuer
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -493,7 +528,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        // publish this warp's partial of every row (and, with it, the stored v) and count the arrival
+        {
+          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * 2 + eg);
+          __stcg(slot, make_float2(s1, s2));
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) red_release_gpu_add(ep.lnf_cnt + (row_base >> 5), 1u);
+        }
+        if (p_row_base >= 0) pass2();             // the previous tile: its row group has long been completed
+        p_row_base = row_base; p_n0 = n0; p_nidx = n_idx; p_src = src; p_stride = stride;
       }
+      if (p_row_base >= 0) pass2();
     } else if constexpr (H_LN && !H_RAGGED) {
       // ---------- single-pass full-row LayerNorm epilogue (N == BN <= 128: attention out-proj, FFN down) ----------
       // The two warps of a TMEM quadrant split the row's chunks, keep their values in registers, exchange the
@@ -586,6 +632,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const float mean = t1 * inv_n;
         const float rstd = rsqrtf(t2 * inv_n - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
         if (has_bf16) {
+          for (int half = 0; half < (ep.lo_delta ? 2 : 1); ++half) {   // strict mode: a second sweep writes the lo halves
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (j < nchunk) {
@@ -599,9 +646,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const float w1 = (vv[j][4 * i + 1] - mean) * (rstd * g.y) + b.y;
                 const float w2 = (vv[j][4 * i + 2] - mean) * (rstd * g.z) + b.z;
                 const float w3 = (vv[j][4 * i + 3] - mean) * (rstd * g.w) + b.w;
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(w0, w1), p1 = __floats2bfloat162_rn(w2, w3);
-                scrw[lane * 33 + 2 * i] = *reinterpret_cast<uint32_t*>(&p0);
-                scrw[lane * 33 + 2 * i + 1] = *reinterpret_cast<uint32_t*>(&p1);
+                if (half == 0) {
+                  scrw[lane * 33 + 2 * i] = pack_bf16x2(w0, w1);
+                  scrw[lane * 33 + 2 * i + 1] = pack_bf16x2(w2, w3);
+                } else {
+                  scrw[lane * 33 + 2 * i] = pack_bf16x2_lo(w0, w1);
+                  scrw[lane * 33 + 2 * i + 1] = pack_bf16x2_lo(w2, w3);
+                }
               }
               __syncwarp();
 #pragma unroll
@@ -609,12 +660,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int rr = it * 8 + h_r, grow = row_base + rr;
                 if (grow < sh.M) {
                   const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                  *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + c0 + h_c) =
+                  *reinterpret_cast<uint4*>(ep.out_bf16 + (half ? ep.lo_delta : 0) + static_cast<size_t>(grow) * ep.ld_bf16 + c0 + h_c) =
                       make_uint4(sp[0], sp[1], sp[2], sp[3]);
                 }
               }
               __syncwarp();
             }
+          }
           }
         }
       }
@@ -828,6 +880,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if constexpr (H_BF16) {
               if (write_bf16) {
+                for (int half = 0; half < (ep.lo_delta ? 2 : 1); ++half) {   // strict mode: second sweep = lo halves
                 if (H_LN && do_ln) {
                   const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0);
                   const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0);
@@ -838,9 +891,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const float w1 = (v[4 * i + 1] - mean) * (rstd * g.y) + b.y;
                     const float w2 = (v[4 * i + 2] - mean) * (rstd * g.z) + b.z;
                     const float w3 = (v[4 * i + 3] - mean) * (rstd * g.w) + b.w;
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(w0, w1), p1 = __floats2bfloat162_rn(w2, w3);
-                    scrw[lane * 33 + 2 * i] = *reinterpret_cast<uint32_t*>(&p0);
-                    scrw[lane * 33 + 2 * i + 1] = *reinterpret_cast<uint32_t*>(&p1);
+                    scrw[lane * 33 + 2 * i] = half ? pack_bf16x2_lo(w0, w1) : pack_bf16x2(w0, w1);
+                    scrw[lane * 33 + 2 * i + 1] = half ? pack_bf16x2_lo(w2, w3) : pack_bf16x2(w2, w3);
+                  }
+                } else if (ep.lo_delta) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float y0 = act_apply_exact(v[2 * j], act), y1 = act_apply_exact(v[2 * j + 1], act);
+                    scrw[lane * 33 + j] = half ? pack_bf16x2_lo(y0, y1) : pack_bf16x2(y0, y1);
                   }
                 } else {
 #pragma unroll
@@ -855,11 +913,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   const int rr = it * 8 + h_r, grow = row_base + rr;
                   if (grow < sh.M) {
                     const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                    *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                    *reinterpret_cast<uint4*>(ep.out_bf16 + (half ? ep.lo_delta : 0) + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
                         make_uint4(sp[0], sp[1], sp[2], sp[3]);
                   }
                 }
                 __syncwarp();
+                }
               }
             }
             continue;
@@ -921,8 +980,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (i < ncols && col0 + i < sh.N) {
                   float w;
                   if (do_ln) w = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + i)) + __ldg(ep.ln_beta + col0 + i);
-                  else w = act_apply(v[i], act);
+                  else w = ep.lo_delta ? act_apply_exact(v[i], act) : act_apply(v[i], act);
                   op[i] = __float2bfloat16_rn(w);
+                  if (ep.lo_delta) op[i + ep.lo_delta] = __float2bfloat16_rn(w - __bfloat162float(__float2bfloat16_rn(w)));
                 }
               }
             }

@@ -7,11 +7,14 @@ namespace smd {
 // ---------------------------------------------------------------------------------------------------
 // q_sample (utils/losses.py:295-300)
 // ---------------------------------------------------------------------------------------------------
+// ind (optional): device table {x0, used_alpha, eps} that overrides the pointer arguments -- a captured CUDA graph of
+// the train step reads its per-step inputs through it, so new input tensors do not force a re-capture
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ eps,
                                 const float* __restrict__ ua, float* __restrict__ xt, float* __restrict__ cond, int B,
-                                int per_sample) {
+                                int per_sample, const float* const* __restrict__ ind) {
   pdl_trigger();
   pdl_wait();
+  if (ind) { x0 = ind[0]; ua = ind[1]; eps = ind[2]; }
   const size_t total = static_cast<size_t>(B) * per_sample;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -23,11 +26,11 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
   }
 }
 void launch_q_sample(const float* x0, const float* eps, const float* used_alpha, float* xt, float* cond, int B,
-                     int per_sample, cudaStream_t st) {
+                     int per_sample, cudaStream_t st, const float* const* ind) {
   const size_t total = static_cast<size_t>(B) * per_sample;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl_g(kPdlMisc, q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample);
+  launch_pdl_g(kPdlMisc, q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample, ind);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -36,7 +39,7 @@ void launch_q_sample(const float* x0, const float* eps, const float* used_alpha,
 __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
              const float* __restrict__ posenc, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-             float* __restrict__ h, __nv_bfloat16* __restrict__ a, int M, int C, int S) {
+             float* __restrict__ h, __nv_bfloat16* __restrict__ a, int M, int C, int S, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -72,13 +75,16 @@ embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const flo
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int o = lane + 32 * j;
-    a[static_cast<size_t>(m) * 128 + o] = __float2bfloat16_rn((v[j] - mean) * (rstd * ln_g[o]) + ln_b[o]);
+    const float y = (v[j] - mean) * (rstd * ln_g[o]) + ln_b[o];
+    a[static_cast<size_t>(m) * 128 + o] = __float2bfloat16_rn(y);
+    if (lo_delta) a[static_cast<size_t>(m) * 128 + o + lo_delta] = bf16_lo_part(y);
   }
 }
 void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
-                  const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st) {
+                  const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st, long long lo_delta) {
   const int blocks = (M + 7) / 8;
-  launch_pdl_g(kPdlMisc, embed_kernel, dim3(blocks), dim3(256), 0, st, x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S);
+  launch_pdl_g(kPdlMisc, embed_kernel, dim3(blocks), dim3(256), 0, st, x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S,
+               lo_delta);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -86,7 +92,7 @@ void launch_embed(const float* x, const float* W_in, const float* b_in, const fl
 // ---------------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
-                                 float* __restrict__ probs, int B, int H) {
+                                 float* __restrict__ probs, int B, int H, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   // a CTA owns HPB = blockDim.x / 32 heads of one sample (W = HPB * DH columns of k and v): small CTAs, several
@@ -150,6 +156,7 @@ __global__ void attention_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
 #pragma unroll
   for (int d = 0; d < DH; d += 2) {
     *reinterpret_cast<__nv_bfloat162*>(orow + d) = __floats2bfloat162_rn(acc[d], acc[d + 1]);
+    if (lo_delta) { orow[d + lo_delta] = bf16_lo_part(acc[d]); orow[d + 1 + lo_delta] = bf16_lo_part(acc[d + 1]); }
   }
   if (probs != nullptr) {
     float* pr = probs + ((static_cast<size_t>(b) * H + h) * 32 + lane) * 32;
@@ -289,14 +296,15 @@ attention_mma_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ 
     }
 }
 
-void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st) {
+void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st,
+                      long long lo_delta) {
   const int dh = 128 / H;
   int hpb = H;
   while (hpb > 4 && hpb % 2 == 0) hpb /= 2;
   const dim3 grid(B, H / hpb);
   const int threads = hpb * 32;
   static const bool simt = [] { const char* v = getenv("SMD_ATTENTION_SIMT"); return v && v[0] == '1'; }();
-  if (!simt && dh % 8 == 0 && dh <= 32) {
+  if (!simt && lo_delta == 0 && dh % 8 == 0 && dh <= 32) {   // (strict mode: fp32 SIMT attention, no tf32 rounding)
     const size_t smem = 3 * 32 * static_cast<size_t>(hpb * dh + 4) * sizeof(uint32_t);
 #define SMD_ATT_MMA(DHV)                                                                                          \
   {                                                                                                               \
@@ -313,10 +321,10 @@ void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, 
 #undef SMD_ATT_MMA
     return;
   }
-  if (dh == 16) launch_pdl_g(kPdlAttention, attention_kernel<16>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
-  else if (dh == 8) launch_pdl_g(kPdlAttention, attention_kernel<8>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
-  else if (dh == 32) launch_pdl_g(kPdlAttention, attention_kernel<32>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
-  else if (dh == 4) launch_pdl_g(kPdlAttention, attention_kernel<4>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H);
+  if (dh == 16) launch_pdl_g(kPdlAttention, attention_kernel<16>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H, lo_delta);
+  else if (dh == 8) launch_pdl_g(kPdlAttention, attention_kernel<8>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H, lo_delta);
+  else if (dh == 32) launch_pdl_g(kPdlAttention, attention_kernel<32>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H, lo_delta);
+  else if (dh == 4) launch_pdl_g(kPdlAttention, attention_kernel<4>, dim3(grid), dim3(threads), 0, st, qkv, o, probs_or_null, B, H, lo_delta);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(MAXT)
 ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats, const float* __restrict__ g,
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
                    int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
-                   const int* __restrict__ film_row_dev) {
+                   const int* __restrict__ film_row_dev, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t lsm[];
@@ -429,7 +437,7 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
       }
       if (act == 2) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = swishf(y[i]);
+        for (int i = 0; i < 4; ++i) y[i] = lo_delta ? swish_exact(y[i]) : swishf(y[i]);
       }
       __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
       __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
@@ -437,6 +445,11 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
       pk.x = *reinterpret_cast<uint32_t*>(&p0);
       pk.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * N + c) = pk;
+      if (lo_delta) {
+        __nv_bfloat16* lo = out + static_cast<size_t>(row) * N + c + lo_delta;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lo[i] = bf16_lo_part(y[i]);
+      }
     }
     __syncthreads();                                   // everyone is done reading this buffer
     if (threadIdx.x == 0 && grp + 2 < ngroups) issue(grp + 2);
@@ -444,7 +457,7 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
 }
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
-                        int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16) {
+                        int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16, long long lo_delta) {
   const int blocks = (M + 31) / 32;
   const int threads = N / 4;
   const bool bf = (u16 != nullptr);
@@ -458,7 +471,7 @@ void launch_ln_film_act(const float* u, const float* stats, const float* g, cons
       attr = true;                                                                                               \
     }                                                                                                            \
     launch_pdl_g(kPdlLnFilmFwd, ln_film_act_kernel<MAXT, BF>, dim3(blocks), dim3(threads), smem, st, in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
-                                                                out, M, N, S, film_row_dev);                     \
+                                                                out, M, N, S, film_row_dev, lo_delta);           \
   }
   if (threads <= 512) {
     if (bf) SMD_LN_LAUNCH(512, true) else SMD_LN_LAUNCH(512, false)
@@ -604,7 +617,7 @@ void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int
 }
 // All weight repacks of one optimizer step in ONE launch: blockmap[b] = (job, tile) for every 64x64 tile.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs,
-                                                         const int2* __restrict__ blockmap) {
+                                                         const int2* __restrict__ blockmap, long long lo_delta) {
   __shared__ float tile[64][65];
   const int2 bm = blockmap[blockIdx.x];
   const PackJob job = jobs[bm.x];
@@ -622,30 +635,40 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict
     __syncthreads();
     for (int i = ty; i < 64; i += 4) {
       const int n = n0 + i, k = k0 + tx;
-      if (n < N && k < K) dst[static_cast<size_t>(n) * job.ld + k] = __float2bfloat16_rn(tile[tx][i]);
+      if (n < N && k < K) {
+        dst[static_cast<size_t>(n) * job.ld + k] = __float2bfloat16_rn(tile[tx][i]);
+        if (lo_delta) dst[static_cast<size_t>(n) * job.ld + k + lo_delta] = bf16_lo_part(tile[tx][i]);
+      }
     }
   } else {               // dst[k][n] = src[k][n] with row pitch ld
     for (int i = ty; i < 64; i += 4) {
       const int k = k0 + i, n = n0 + tx;
-      if (k < K && n < N) dst[static_cast<size_t>(k) * job.ld + n] = __float2bfloat16_rn(src[static_cast<size_t>(k) * N + n]);
+      if (k < K && n < N) {
+        const float w = src[static_cast<size_t>(k) * N + n];
+        dst[static_cast<size_t>(k) * job.ld + n] = __float2bfloat16_rn(w);
+        if (lo_delta) dst[static_cast<size_t>(k) * job.ld + n + lo_delta] = bf16_lo_part(w);
+      }
     }
   }
 }
 void launch_pack_multi(const float* params, const PackJob* jobs_dev, const void* blockmap_dev, int total_tiles,
-                       cudaStream_t st) {
-  pack_multi_kernel<<<total_tiles, 256, 0, st>>>(params, jobs_dev, static_cast<const int2*>(blockmap_dev));
+                       cudaStream_t st, long long lo_delta) {
+  pack_multi_kernel<<<total_tiles, 256, 0, st>>>(params, jobs_dev, static_cast<const int2*>(blockmap_dev), lo_delta);
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n,
+                                 long long lo_delta) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     dst[i] = __float2bfloat16_rn(src[i]);
+    if (lo_delta) dst[i + lo_delta] = bf16_lo_part(src[i]);
+  }
 }
-void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st, long long lo_delta) {
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  cast_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+  cast_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n, lo_delta);
 }
 
 // ---------------------------------------------------------------------------------------------------

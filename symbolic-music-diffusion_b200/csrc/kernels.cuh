@@ -35,6 +35,13 @@ __device__ __forceinline__ float swishf(float v) {
   const float h = 0.5f * v;
   return fmaf(h, tanh_approx(h), h);
 }
+// Strict-precision mode (SMD precision = bf16x3): every bf16 tensor-core operand x is kept as the pair
+// (hi = bf16(x), lo = bf16(x - hi)); lo lives `lo_delta` elements behind hi (0 = mode off) and the GEMMs add the
+// hi*lo + lo*hi cross terms, so products carry ~16 mantissa bits.  Activations then use the accurate functions.
+__device__ __forceinline__ __nv_bfloat16 bf16_lo_part(float x) {
+  return __float2bfloat16_rn(x - __bfloat162float(__float2bfloat16_rn(x)));
+}
+__device__ __forceinline__ float swish_exact(float v) { return v / (1.0f + expf(-v)); }
 __device__ __forceinline__ float swish_grad(float v) {  // d/dv [v * sigmoid(v)] = s * (1 + v * (1 - s))
   const float s = fmaf(0.5f, tanh_approx(0.5f * v), 0.5f);
   return s * fmaf(v, 1.0f - s, 1.0f);
@@ -136,22 +143,25 @@ __device__ __forceinline__ float jax_normal_from_bits(uint32_t bits) {
 // ---------------------------------------------------------------------------------------------------
 // x_t = sqrt(ua[b]) * x0 + sqrt(1 - ua[b]) * eps ; cond[b] = sqrt(ua[b])        (utils/losses.py:295-300)
 void launch_q_sample(const float* x0, const float* eps, const float* used_alpha, float* xt, float* cond, int B,
-                     int per_sample, cudaStream_t st);
+                     int per_sample, cudaStream_t st, const float* const* ind = nullptr);
 
 // h[m,:] = x[m,:] @ W_in + b_in + posenc[m % S,:]; a[m,:] = bf16(LN(h[m,:]; g, b))   (models/ncsn.py:155-160)
 void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
-                  const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st);
+                  const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st,
+                  long long lo_delta = 0);
 
 // unmasked multi-head self-attention over S = 32 positions (flax.nn.SelfAttention core, models/ncsn.py:161)
 // qkv fp32 [M][3E] -> o bf16 [M][E];  optionally saves the probabilities P [B][H][32][32] fp32 for backward
-void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st);
+void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st,
+                      long long lo_delta = 0);
 
 // out[m,:] = bf16( act( film( LN(u[m,:]; stats, g, b) ) ) )                        (models/shared.py:62-64,66-68)
 // stats[m] = (sum, sumsq) over the N columns; scale/shift rows selected by m / S (or row 0 if film_bcast)
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
                         int S, cudaStream_t st, const int* film_row_dev = nullptr,
-                        const __nv_bfloat16* u16 = nullptr);   // u16: the LayerNorm input stored as bf16 (u == null)
+                        const __nv_bfloat16* u16 = nullptr,    // u16: the LayerNorm input stored as bf16 (u == null)
+                        long long lo_delta = 0);
 
 // enc[r, j] = sin((5000 t_r) f_j), enc[r, 64 + j] = cos(...)                          (models/ncsn.py:25-41)
 void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R, cudaStream_t st);
@@ -169,9 +179,9 @@ void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int
 // one launch for a list of repack jobs (mode 0: transpose to [N][K] with pitch ld; mode 1: plain cast, pitch ld)
 struct PackJob { long long src_off; void* dst; int K, N, mode, ld, tile0, tiles_n; };
 void launch_pack_multi(const float* params, const PackJob* jobs_dev, const void* blockmap_dev, int total_tiles,
-                       cudaStream_t st);
+                       cudaStream_t st, long long lo_delta = 0);
 // bf16 dst[i] = src[i]
-void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st, long long lo_delta = 0);
 
 struct ReverseStepArgs {
   const float* x;          // state (N, S, C)

@@ -60,6 +60,10 @@ struct smd_plan {
   std::map<std::string, long long> off;
   long long arena = 0;
   int Mp = 0;  // padded token rows
+  // strict-precision mode: the workspace is allocated twice; the lo half of a bf16 operand at byte offset o lives at
+  // o + lo_bytes (lo_elems in bf16 elements; both 0 when the mode is off)
+  size_t lo_bytes = 0;
+  long long lo_elems = 0;
   int K = 0;   // number of FiLM res-blocks (num_mlp_layers, or num_layers for DenseDDPM)
   // ---- workspace carve (byte offsets) ----
   std::map<std::string, size_t> ws_off;
@@ -99,6 +103,16 @@ struct smd_plan {
   cudaStream_t dw_stream = nullptr;     // trunk weight-gradient GEMMs (leaves of the backward graph)
   cudaEvent_t ev_fork = nullptr, ev_film = nullptr, ev_dss = nullptr, ev_join = nullptr, ev_dw = nullptr, ev_dwjoin = nullptr, ev_tail = nullptr, ev_dwtail = nullptr;
   smd::TrainState train;
+  // graph replay of smd_ddpm_grads (backward.cu)
+  cudaGraphExec_t tg_exec = nullptr;
+  long long tg_nodes = 0;
+  bool tg_valid = false, tg_warm = false;
+  cudaEvent_t ev_gz = nullptr;      // gradient arena zeroed (on the weight-gradient stream)
+  cudaEvent_t evx_join = nullptr;   // "FiLM generator gradients final", waitable from outside the graph
+  const float* tg_params = nullptr;
+  float* tg_grads = nullptr;
+  float* tg_loss = nullptr;
+  int tg_batch = 0, tg_global = 0;
 
   template <typename Tp>
   Tp* buf(const std::string& n) const { return reinterpret_cast<Tp*>(ws + ws_off.at(n)); }

@@ -122,6 +122,7 @@ static void build_workspace(smd_plan* p) {
   // epilogues (one u32 per 32 rows and fused launch); the whole region is zeroed once per forward
   ws_add(p, "stats", (2 * K + 1) * Mp * 2 * 4 + (2 * K + 2) * (Mp / 32) * 4);
   ws_add(p, "lnf_part", Mp * (Md / 256 * 2) * 2 * 4);   // per-tile partial sums [row][n_tile * 2 + column group][2]
+  ws_add(p, "lnf_ring", static_cast<size_t>(160) * 2 * 128 * 256 * 2);   // per-CTA bf16 parking (inference, GEMM a)
   // FiLM generator
   ws_add(p, "tvec", B * 4);
   ws_add(p, "enc", B * kFilmEmb * 4);
@@ -149,6 +150,12 @@ static void build_workspace(smd_plan* p) {
     ws_add(p, "ftab", K * T * 2 * Md * 4);
   }
   if (c.training) train_workspace(p->train, c, p->Mp, p->K, [&](const std::string& n, size_t b) { return ws_add(p, n, b); });
+  if (c.precision == SMD_PRECISION_BF16X3) {
+    ws_add(p, "x3.scratch", Mp * Md * 4);     // fp32 cross-term accumulator of the three-pass GEMMs
+    p->lo_bytes = p->ws_bytes;                // second copy of the workspace: the lo halves, at the same offsets
+    p->lo_elems = static_cast<long long>(p->lo_bytes / 2);
+    p->ws_bytes *= 2;
+  }
 }
 
 // sinusoid frequency table, float32 like jnp (models/ncsn.py:33-35, models/shared.py:41-43)
@@ -166,7 +173,7 @@ static int build_ops(smd_plan* p) {
   auto Wsh = [&](const std::string& n) { return static_cast<const void*>(p->buf<__nv_bfloat16>("wshadow") + p->off.at(n)); };
   // forward GEMM: A K-major activations [Mp][K], B = (in,out) weight read MN-major ([K][N]) from the shadow arena
   auto fwd = [&](GemmOp* op, const std::string& a, const std::string& w, int K, int N, int BN) {
-    return make_gemm_op(op, A(a), Mp, Wsh(w), static_cast<uint64_t>(N), N, K, BN, cg, 0, 1);
+    return make_gemm_op(op, A(a), Mp, Wsh(w), static_cast<uint64_t>(N), N, K, BN, cg, 0, 1, 0, 0, p->lo_bytes);
   };
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
     p->op_qkv.resize(c.num_layers); p->op_o.resize(c.num_layers);
@@ -198,10 +205,35 @@ static int build_ops(smd_plan* p) {
   {
     const int BN = Cp >= 256 ? 256 : Cp;
     const int ocg = (BN % (64 * cg) == 0) ? cg : 1;
-    if (!make_gemm_op(&p->op_out, A("act"), Mp, A("w.out_pad"), static_cast<uint64_t>(Cp), C, Md, BN, ocg, 0, 1))
+    if (!make_gemm_op(&p->op_out, A("act"), Mp, A("w.out_pad"), static_cast<uint64_t>(Cp), C, Md, BN, ocg, 0, 1, 0, 0,
+                      p->lo_bytes))
       return SMD_ERR_CUDA;
   }
   return SMD_OK;
+}
+
+// Every forward GEMM goes through here.  Default precision: one launch.  bf16x3: the product of the (hi, lo) operand
+// pairs as three launches -- scratch = A_lo B_hi (+ the layer's residual); scratch += A_hi B_lo; then the real launch
+// A_hi B_hi with the layer's epilogue taking `scratch` as its residual -- all accumulated in fp32.
+static cudaError_t gemm(smd_plan* p, const GemmOp& op, int M, GemmEpilogue e, cudaStream_t st) {
+  if (p->lo_bytes == 0) return launch_gemm(op, M, e, st);
+  if (!op.has_lo) return cudaErrorInvalidValue;
+  float* scratch = p->buf<float>("x3.scratch");
+  GemmOp o1 = op; o1.tmA = op.tmA_lo;
+  GemmEpilogue e1 = epi();
+  e1.residual = e.residual; e1.ld_res = e.ld_res;
+  e1.out_f32 = scratch; e1.ld_f32 = op.N;
+  cudaError_t err = launch_gemm(o1, M, e1, st);
+  if (err != cudaSuccess) return err;
+  GemmOp o2 = op; o2.tmB = op.tmB_lo;
+  GemmEpilogue e2 = epi();
+  e2.residual = scratch; e2.ld_res = op.N;
+  e2.out_f32 = scratch; e2.ld_f32 = op.N;
+  err = launch_gemm(o2, M, e2, st);
+  if (err != cudaSuccess) return err;
+  e.residual = scratch; e.ld_res = op.N;
+  e.lo_delta = p->lo_elems;
+  return launch_gemm(op, M, e, st);
 }
 
 // FiLM generator for all K blocks: t (R values) -> ss[k][R][2*Md]   (models/ncsn.py:47-61)
@@ -236,6 +268,8 @@ int ensure_side_stream(smd_plan* p) {
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dwjoin, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming));
   SMD_CUDA(cudaEventCreateWithFlags(&p->ev_dwtail, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->evx_join, cudaEventDisableTiming));
+  SMD_CUDA(cudaEventCreateWithFlags(&p->ev_gz, cudaEventDisableTiming));
   return SMD_OK;
 }
 
@@ -247,7 +281,7 @@ static bool lnf_enabled() {
 // one FiLM (scale | shift) row per sample of 32 rows, or one row for everybody (sampler): the fused epilogue cannot
 // serve DenseDDPM's one-row-per-example case (a 32-row warp tile would span 32 FiLM rows)
 bool lnf_usable(const smd_plan* p, int S, int t_broadcast) {
-  return lnf_enabled() && (S == 32 || t_broadcast || p->film_tab_on) && p->cfg.mlp_dims % 256 == 0;
+  return lnf_enabled() && p->lo_bytes == 0 && (S == 32 || t_broadcast || p->film_tab_on) && p->cfg.mlp_dims % 256 == 0;
 }
 // FiLM table / row selection of block k (shared by the fused epilogue and the stand-alone kernel)
 static void film_source(const smd_plan* p, int k, int t_broadcast, const float** scale, int* bcast, const int** row_dev) {
@@ -272,6 +306,7 @@ void arm_lnf(const smd_plan* p, const float* params, GemmEpilogue* e, const std:
   e->ln_gamma = p->P(params, ln + "scale"); e->ln_beta = p->P(params, ln + "bias");
   e->out_bf16 = out; e->ld_bf16 = Md;
   e->lnf_part = p->buf<float>("lnf_part");
+  e->lnf_ring = p->buf<__nv_bfloat16>("lnf_ring");
   e->lnf_cnt = cnt0 + static_cast<size_t>(ln_slot) * (p->Mp / 32);
   e->row_stats = want_totals ? stats + static_cast<size_t>(ln_slot) * sstride : nullptr;
   e->film = nullptr; e->film_ld = 2 * Md; e->film_bcast = 0; e->film_row_dev = nullptr; e->act2 = ACT_NONE;
@@ -352,36 +387,38 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
       u_in = save->u(p->ws, k); r1_out = reinterpret_cast<__nv_bfloat16*>(save->r1(p->ws, k)); act_a = save->act_a(p->ws, k);
       act_b = save->act_b(p->ws, k); u_out = save->u(p->ws, k + 1);
     }
+    const bool strict = p->lo_bytes != 0;
     launch_ln_film_act(u_in, stats + (2 * k) * sstride, p->P(params, pre + "ln_a.scale"), p->P(params, pre + "ln_a.bias"),
-                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st, frow_dev); CNT();
+                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st, frow_dev, nullptr, p->lo_elems); CNT();
     GemmEpilogue e = epi();
     e.bias = p->P(params, pre + "a.bias");
-    e.out_bf16 = r1_out; e.ld_bf16 = Md;
+    if (strict) { e.out_f32 = r1; e.ld_f32 = Md; }       // (strict mode keeps the pre-LayerNorm intermediate in fp32)
+    else { e.out_bf16 = r1_out; e.ld_bf16 = Md; }
     e.row_stats = stats + (2 * k + 1) * sstride;
     GemmOp opa = p->op_a[k];
     GemmOp opb = p->op_b[k];
     if (save) { if (!retarget_a(&opa, act_a, p->Mp) || !retarget_a(&opb, act_b, p->Mp)) return SMD_ERR_CUDA; }
-    SMD_CUDA(launch_gemm(opa, M, e, st));
-    launch_ln_film_act(nullptr, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
+    SMD_CUDA(gemm(p, opa, M, e, st));
+    launch_ln_film_act(strict ? r1 : nullptr, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
                        p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st, frow_dev,
-                       r1_out); CNT();
+                       strict ? nullptr : r1_out, p->lo_elems); CNT();
     e = epi();
     e.bias = p->P(params, pre + "b.bias");
     e.residual = u_in; e.ld_res = Md;
     e.out_f32 = u_out; e.ld_f32 = Md;
     e.row_stats = stats + (2 * k + 2) * sstride;
-    SMD_CUDA(launch_gemm(opb, M, e, st));
+    SMD_CUDA(gemm(p, opb, M, e, st));
   }
   float* u_last = save ? save->u(p->ws, p->K) : u;
   __nv_bfloat16* act_o = save ? save->act_out(p->ws) : act;
   launch_ln_film_act(u_last, stats + (2 * p->K) * sstride, p->P(params, "out_ln.scale"), p->P(params, "out_ln.bias"),
-                     nullptr, nullptr, 0, 0, 0, act_o, M, Md, S, st); CNT();
+                     nullptr, nullptr, 0, 0, 0, act_o, M, Md, S, st, nullptr, nullptr, p->lo_elems); CNT();
   GemmEpilogue e = epi();
   e.bias = p->P(params, "out.bias");
   e.out_f32 = y; e.ld_f32 = C;
   GemmOp opo = p->op_out;
   if (save) { if (!retarget_a(&opo, act_o, p->Mp)) return SMD_ERR_CUDA; }
-  SMD_CUDA(launch_gemm(opo, M, e, st));
+  SMD_CUDA(gemm(p, opo, M, e, st));
   SMD_LAUNCH_CHECK("tail");
   return SMD_OK;
 }
@@ -425,7 +462,7 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
     __nv_bfloat16* hidden = p->buf<__nv_bfloat16>("hidden");
     if (save) { h = save->h(p->ws, 0); a = save->a1(p->ws, 0); }
     launch_embed(x, p->P(params, "in.kernel"), p->P(params, "in.bias"), p->buf<float>("posenc"),
-                 p->P(params, "l0.ln1.scale"), p->P(params, "l0.ln1.bias"), h, a, M, C, S, st); CNT();
+                 p->P(params, "l0.ln1.scale"), p->P(params, "l0.ln1.bias"), h, a, M, C, S, st, p->lo_elems); CNT();
     for (int l = 0; l < c.num_layers; ++l) {
       const std::string pre = "l" + std::to_string(l) + ".";
       GemmOp oq = p->op_qkv[l], oo = p->op_o[l], o1 = p->op_ffn1[l], o2 = p->op_ffn2[l];
@@ -445,19 +482,19 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
       GemmEpilogue e = epi();
       e.bias = p->P(params, pre + "attn.qkv.bias");
       e.out_f32 = qkv; e.ld_f32 = 3 * kE;
-      SMD_CUDA(launch_gemm(oq, M, e, st));
-      launch_attention(qkv, o, probs, batch, c.num_heads, st); CNT();
+      SMD_CUDA(gemm(p, oq, M, e, st));
+      launch_attention(qkv, o, probs, batch, c.num_heads, st, p->lo_elems); CNT();
       e = epi();
       e.bias = p->P(params, pre + "attn.out.bias");
       e.residual = h_in; e.ld_res = kE;
       e.out_f32 = h_mid; e.ld_f32 = kE;
       e.out_bf16 = a2; e.ld_bf16 = kE;
       e.ln_gamma = p->P(params, pre + "ln2.scale"); e.ln_beta = p->P(params, pre + "ln2.bias");
-      SMD_CUDA(launch_gemm(oo, M, e, st));
+      SMD_CUDA(gemm(p, oo, M, e, st));
       const std::string nl = (l + 1 < c.num_layers) ? ("l" + std::to_string(l + 1) + ".ln1.") : std::string("post_ln.");
       // worth it once the token count fills the machine (one CTA pair per 256 tokens); training keeps the two-GEMM
       // path: it has to write the hidden activations anyway and at batch 128 only 16 pairs would be busy
-      if (p->op_ffn[l].ok && ffn_fused_enabled() && (ffn_fused_forced() || (!save && M >= 32 * 256))) {
+      if (p->op_ffn[l].ok && p->lo_bytes == 0 && ffn_fused_enabled() && (ffn_fused_forced() || (!save && M >= 32 * 256))) {
         // FFN up + GELU + FFN down + residual + next LayerNorm in one launch; the hidden activation stays on chip
         FfnOp fo = p->op_ffn[l];
         if (save && !make_tmap_bf16(&fo.tmA, a2, p->Mp, 128, 128)) return SMD_ERR_CUDA;
@@ -475,14 +512,14 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
       e.bias = p->P(params, pre + "ffn1.bias");
       e.out_bf16 = hidden; e.ld_bf16 = Md; e.act = ACT_GELU_TANH;
       e.out_bf16_pre = hid_pre;
-      SMD_CUDA(launch_gemm(o1, M, e, st));
+      SMD_CUDA(gemm(p, o1, M, e, st));
       e = epi();
       e.bias = p->P(params, pre + "ffn2.bias");
       e.residual = h_mid; e.ld_res = kE;
       e.out_f32 = h_out; e.ld_f32 = kE;
       e.out_bf16 = a_next; e.ld_bf16 = kE;
       e.ln_gamma = p->P(params, nl + "scale"); e.ln_beta = p->P(params, nl + "bias");
-      SMD_CUDA(launch_gemm(o2, M, e, st));
+      SMD_CUDA(gemm(p, o2, M, e, st));
     }
     GemmEpilogue e = epi();
     e.bias = p->P(params, "post.bias");
@@ -496,17 +533,17 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
     }
     GemmOp op = p->op_post;
     if (save) { if (!retarget_a(&op, save->a_post(p->ws), p->Mp)) return SMD_ERR_CUDA; }
-    SMD_CUDA(launch_gemm(op, M, e, st));
+    SMD_CUDA(gemm(p, op, M, e, st));
   } else {
     __nv_bfloat16* xb = p->buf<__nv_bfloat16>("xb");
     const int Cp = (C + 63) / 64 * 64;
     if (Cp != C) { set_error("DenseDDPM on the CUDA path needs channels % 64 == 0"); return SMD_ERR_INVALID; }
-    launch_cast_bf16(x, xb, static_cast<size_t>(M) * C, st); CNT();
+    launch_cast_bf16(x, xb, static_cast<size_t>(M) * C, st, p->lo_elems); CNT();
     GemmEpilogue e = epi();
     e.bias = p->P(params, "in.bias");
     e.out_f32 = u0; e.ld_f32 = Md;
     e.row_stats = stats;
-    SMD_CUDA(launch_gemm(p->op_in, M, e, st));
+    SMD_CUDA(gemm(p, p->op_in, M, e, st));
   }
   SMD_LAUNCH_CHECK("trunk");
   if (film_on_side) SMD_CUDA(cudaStreamWaitEvent(st, p->ev_film, 0));
@@ -627,6 +664,8 @@ int smd_plan_create(const smd_config* cfg, smd_plan** out) {
   if (c.cta_group != 1 && c.cta_group != 2) { set_error("cta_group must be 1 or 2"); return SMD_ERR_INVALID; }
   if (c.mlp_dims < 256 || c.mlp_dims % 256 != 0 || c.mlp_dims > 4096) { set_error("mlp_dims must be a multiple of 256 in [256, 4096]"); return SMD_ERR_INVALID; }
   if (c.channels < 1 || c.max_batch < 1 || c.num_layers < 1) { set_error("bad sizes"); return SMD_ERR_INVALID; }
+  if (c.precision != SMD_PRECISION_BF16 && c.precision != SMD_PRECISION_BF16X3) { set_error("unknown precision"); return SMD_ERR_INVALID; }
+  if (c.precision == SMD_PRECISION_BF16X3 && c.training) { set_error("precision bf16x3 covers the forward pass / sampler only (training = 0)"); return SMD_ERR_INVALID; }
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
     if (c.seq_len != 32) { set_error("TransformerDDPM CUDA path supports seq_len == 32 only (all reference configs)"); return SMD_ERR_INVALID; }
     if (c.num_heads != 4 && c.num_heads != 8 && c.num_heads != 16 && c.num_heads != 32) { set_error("num_heads must be 4, 8, 16 or 32"); return SMD_ERR_INVALID; }
@@ -646,6 +685,9 @@ int smd_plan_create(const smd_config* cfg, smd_plan** out) {
 void smd_plan_destroy(smd_plan* plan) {
   if (!plan) return;
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+  if (plan->tg_exec) cudaGraphExecDestroy(plan->tg_exec);
+  if (plan->evx_join) cudaEventDestroy(plan->evx_join);
+  if (plan->ev_gz) cudaEventDestroy(plan->ev_gz);
   if (plan->own_event) cudaEventDestroy(plan->own_event);
   if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   if (plan->ev_film) cudaEventDestroy(plan->ev_film);
@@ -682,6 +724,8 @@ int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
   SMD_CUDA(cudaMemset(workspace, 0, plan->ws_bytes));  // padded rows / columns of every operand start finite
   plan->packed = false;
   plan->sampler_ready = false;
+  if (plan->tg_exec) { cudaGraphExecDestroy(plan->tg_exec); plan->tg_exec = nullptr; }
+  plan->tg_valid = false; plan->tg_warm = false;
   int rc = build_ops(plan);
   if (rc) return rc;
   float f[64];
@@ -705,9 +749,9 @@ int smd_bind_workspace(smd_plan* plan, void* workspace, size_t bytes) {
 static int refresh_operands(smd_plan* plan, const float* params, bool shadow_is_fresh, cudaStream_t st) {
   if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
   if (!shadow_is_fresh) {
-    launch_cast_bf16(params, plan->buf<__nv_bfloat16>("wshadow"), static_cast<size_t>(plan->arena), st); CNT();
+    launch_cast_bf16(params, plan->buf<__nv_bfloat16>("wshadow"), static_cast<size_t>(plan->arena), st, plan->lo_elems); CNT();
   }
-  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), plan->buf<void>("packmap"), plan->pack_tiles, st); CNT();
+  launch_pack_multi(params, plan->buf<PackJob>("packjobs"), plan->buf<void>("packmap"), plan->pack_tiles, st, plan->lo_elems); CNT();
   SMD_LAUNCH_CHECK("pack_weights");
   plan->packed = true;
   plan->film_tab_ready = false;   // parameters changed
@@ -734,10 +778,11 @@ int smd_grads_tail_range(const smd_plan* plan, long long* first_float, long long
 }
 
 int smd_wait_tail_grads(smd_plan* plan, smd_stream_t stream) {
-  if (!plan || !plan->ev_tail || !plan->ev_join) { set_error("no smd_ddpm_grads call has been enqueued on this plan"); return SMD_ERR_STATE; }
+  if (!plan || !plan->ev_tail || !plan->evx_join) { set_error("no smd_ddpm_grads call has been enqueued on this plan"); return SMD_ERR_STATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // (recorded by plain cudaEventRecord calls, or -- graph replay -- by external event-record nodes of the graph)
   SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_tail, 0));   // tail + output-layer gradients (caller's stream)
-  SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));   // FiLM generator gradients (side stream)
+  SMD_CUDA(cudaStreamWaitEvent(st, plan->evx_join, 0));  // FiLM generator gradients (side stream)
   SMD_CUDA(cudaStreamWaitEvent(st, plan->ev_dwtail, 0)); // res-block weight gradients (weight-gradient stream)
   return SMD_OK;
 }

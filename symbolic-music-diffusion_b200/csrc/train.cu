@@ -55,7 +55,8 @@ void train_workspace(TrainState& ts, const smd_config& c, int Mp, int K,
   ts.off_de = add("t.de", B * 512 * 4);
   ts.off_de2 = add("t.de2", B * 512 * 4);
   ts.off_loss = add("t.loss", B * 4);
-  ts.off_loss_ctr = add("t.loss_ctr", 64);   // block-completion counter of the loss kernel (zeroed at bind, self-resetting)
+  ts.off_loss_ctr = add("t.loss_ctr", 64);
+  add("t.ind", 64);   // device table {x0, used_alpha, eps} of the graph-replayed step   // block-completion counter of the loss kernel (zeroed at bind, self-resetting)
   const size_t Bp = (B + 127) / 128 * 128;
   ts.off_e2_16 = add("t.e2_16", Bp * 512 * 2);
   ts.off_dss16 = add("t.dss16", Bp * 2 * Md * 2);

@@ -16,6 +16,7 @@ import torch
 from . import lib as _lib
 
 ARCHS = {"TransformerDDPM": 0, "TransformerDDPM4": 0, "DenseDDPM": 1}
+PRECISIONS = {"bf16": 0, "bf16x3": 1}
 
 
 @dataclass
@@ -54,16 +55,21 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 class Engine:
     def __init__(self, cfg: ModelConfig, max_batch: int, cta_group: int = 2, training: bool = False,
-                 device: Optional[str] = None, sampler_T: Optional[int] = None):
+                 device: Optional[str] = None, sampler_T: Optional[int] = None, precision: Optional[str] = None):
         if cfg.arch not in ARCHS:
             raise ValueError(f"unknown architecture {cfg.arch!r}")
         self.cfg = cfg
         self.max_batch = int(max_batch)
         self.lib = _lib.load_library()
+        # "bf16" (default, the timed path) or "bf16x3" (strict: split operands, exact activations; forward only)
+        precision = precision or os.environ.get("SMD_PRECISION", "bf16")
+        if precision not in PRECISIONS:
+            raise ValueError(f"unknown precision {precision!r} (expected one of {sorted(PRECISIONS)})")
+        self.precision = precision
         c = _lib.SmdConfig(ARCHS[cfg.arch], cfg.num_layers, cfg.num_heads, cfg.num_mlp_layers, cfg.mlp_dims,
                            cfg.seq_len if ARCHS[cfg.arch] == 0 else 1, cfg.channels, self.max_batch,
                            int(cta_group), int(training),
-                           int((0 if training else 1000) if sampler_T is None else sampler_T))
+                           int((0 if training else 1000) if sampler_T is None else sampler_T), PRECISIONS[precision])
         h = C.c_void_p()
         _lib.check(self.lib.smd_plan_create(C.byref(c), C.byref(h)))
         self._plan = h

@@ -17,7 +17,7 @@ class SmdConfig(C.Structure):
     _fields_ = [("arch", C.c_int), ("num_layers", C.c_int), ("num_heads", C.c_int),
                 ("num_mlp_layers", C.c_int), ("mlp_dims", C.c_int), ("seq_len", C.c_int),
                 ("channels", C.c_int), ("max_batch", C.c_int), ("cta_group", C.c_int),
-                ("training", C.c_int), ("sampler_T", C.c_int)]
+                ("training", C.c_int), ("sampler_T", C.c_int), ("precision", C.c_int)]
 
 
 _P = C.c_void_p

@@ -157,6 +157,9 @@ def train_step(objective, batch, optimizer, sigmas, rng, learning_rate, ema=None
 def train(train_batches, valid_batches, sigmas, output_dir=None, verbose=True):
     """train_ncsn.py:291-496 (the MNIST / toy plotting branches are out of scope)."""
     objective = _objective()
+    if torch.cuda.is_available() and torch.cuda.current_stream().cuda_stream == 0:
+        # the legacy default stream cannot be captured: a private stream lets libsmd replay the step from a CUDA graph
+        torch.cuda.set_stream(torch.cuda.Stream())
     first = next(iter(valid_batches))
     input_shape = tuple(first.shape[1:])
     rng = random.PRNGKey(FLAGS.seed)

@@ -55,6 +55,25 @@ def main():
     if r == 0:
         print(f"fraction of parameters with |d update| > 1e-4: {frac:.2e}")
     assert dl < 1e-4 and dg < 5e-3 and gq < 5e-3 and same == 0.0 and frac < 1e-2, (dl, dg, gq, same, frac, dp_)
+    # ---- graph-replayed steps (a capturable stream): the all-reduce of the tail slice waits on the graph's external
+    # event nodes; replicas must stay bit-identical and keep tracking the single-rank run
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for step in range(3):
+            rs = np.random.default_rng(100 + step)
+            xs = rs.uniform(-1, 1, (B, 32, 42)).astype(np.float32)
+            es = rs.standard_normal((B, 32, 42)).astype(np.float32)
+            us = rs.uniform(0.05, 0.99, (B,)).astype(np.float32)
+            loss_dp, _ = e_dp.train_step(t(xs[sl]), t(us[sl]), t(es[sl]), lr=1e-3, world_size=w)
+            loss_1, _ = e_1.train_step(t(xs), t(us), t(es), lr=1e-3, world_size=1)
+            side.synchronize()
+            ref = e_dp.params.clone()
+            dist.broadcast(ref, src=0)
+            same_g = float((ref - e_dp.params).abs().max())
+            dlg = abs(float(loss_dp) - float(loss_1)) / abs(float(loss_1))
+            if r == 0:
+                print(f"graph step {step}: dloss {dlg:.2e} rank-divergence {same_g:.1e}")
+            assert same_g == 0.0 and dlg < 2e-3, (step, same_g, dlg)
     if r == 0:
         print("dp-ok")
     parallel.shutdown()

@@ -177,3 +177,41 @@ def test_tail_gradients_are_final_at_the_tail_event(lib):
         torch.cuda.synchronize()
         assert torch.equal(snap, eng.grads[first:first + count])
         assert float(eng.grads[:first].abs().sum()) > 0
+
+
+def test_graph_replayed_step_equals_eager_launches(lib):
+    """On a capturable stream smd_ddpm_grads replays one CUDA graph (3-stream fork / join captured once, per-step input
+    pointers through a device table).  Same gradients as the eager launches, also when every step brings new tensors,
+    and the tail-gradient events still work from a stream outside the graph."""
+    import ctypes as C
+    from smd_b200 import Engine, ModelConfig
+    from smd_b200 import lib as L
+    kw, arch, batch = CASES["base2"]
+    shape = (32, kw["channels"])
+
+    def make():
+        e = Engine(ModelConfig(arch=arch, **kw), max_batch=batch, cta_group=2, training=True)
+        e.set_params(e.init_params(seed=2, perturb=0.05))
+        e.init_train_state()
+        return e
+
+    eager, graph = make(), make()
+    stream, side = torch.cuda.Stream(), torch.cuda.Stream()
+    first, count = graph.grads_tail_range()
+    snap = torch.empty(count, dtype=torch.float32, device="cuda")
+    for step in range(5):
+        x0, used, eps = _draws(batch, shape, seed=10 + step)
+        args = [torch.from_numpy(a).cuda() for a in (x0, used, eps)]       # fresh tensors every step
+        eager.compute_grads(*args)                                         # legacy default stream: never captured
+        torch.cuda.synchronize()
+        n0 = graph.launch_count()
+        with torch.cuda.stream(stream):
+            graph.compute_grads(*[a.clone() for a in args])                # step 0 eager (warm-up), 1 captures, 2.. replay
+            with torch.cuda.stream(side):
+                L.check(graph.lib.smd_wait_tail_grads(graph._plan, C.c_void_p(side.cuda_stream)))
+                snap.copy_(graph.grads[first:first + count], non_blocking=True)
+        torch.cuda.synchronize()
+        assert graph.launch_count() - n0 > 50                              # replayed launches are still counted
+        assert rel_l2(graph.grads, eager.grads) < 1e-5, step               # (split-K atomics: not bitwise)
+        assert torch.equal(snap, graph.grads[first:first + count]), step   # the tail slice was final at the event
+        assert abs(float(graph.loss_sum) - float(eager.loss_sum)) <= 1e-6 * abs(float(eager.loss_sum))
