@@ -120,9 +120,24 @@ inline bool epi_clean(const GemmOp& op, const GemmEpilogue& e) {
          (!e.bias || a16(e.bias)) && (!e.ln_gamma || (a16(e.ln_gamma) && a16(e.ln_beta)));
 }
 
+// Number of epilogue warps of the instantiation launch_gemm will pick (mirrors launch_gemm_cg): the per-tile statistics
+// partials (GemmEpilogue::stats_part) have (epi warps / 4) slots per n-tile.
+inline int epi_warps_for(const GemmOp& op, const GemmEpilogue& ep) {
+  if (ep.lnf_part != nullptr || !epi_clean(op, ep)) return 8;
+  const uint32_t need = epi_needs(ep);
+  const bool short_k = op.K <= 256;
+  if ((need & ~kEpiF32) == 0) return short_k ? 12 : 8;
+  if ((need & ~kEpiAtomic) == 0 || (need & ~kEpiF32Res) == 0) return 8;
+  if ((need & ~kEpiAct) == 0) return short_k ? 12 : 8;
+  return 8;
+}
+inline int stats_slots_for(const GemmOp& op, const GemmEpilogue& ep) {
+  return ((op.N + op.BN - 1) / op.BN) * (epi_warps_for(op, ep) / 4);
+}
+
 template <int kCG, uint32_t kF, int kEW = 8>
 inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
-  using SM = GemmSmem<kCG, kEW>;
+  using SM = GemmSmem<kCG, kEW, lnf_kind(kF)>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG, kF, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -172,8 +187,12 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
   if (ep.lnf_part != nullptr) {
     // LN-fused two-pass epilogue (the caller arms it only for full, aligned tiles; see smd_api.cu::arm_lnf)
     if (!epi_clean(op, ep) || op.N % op.BN != 0 || op.BN % 64 != 0 || op.k_splits > 1) return cudaErrorInvalidValue;
-    if (ep.residual != nullptr || ep.out_f32 != nullptr) return launch_gemm_inst<kCG, kEpiLnfB>(op, M, ep, st);
-    return launch_gemm_inst<kCG, kEpiLnfA>(op, M, ep, st);
+    if constexpr (kCG == 2) {   // (the 64 KB parking buffer only fits next to the 32 KB pipeline slots of CTA pairs)
+      if (ep.residual != nullptr || ep.out_f32 != nullptr) return launch_gemm_inst<kCG, kEpiLnfB>(op, M, ep, st);
+      return launch_gemm_inst<kCG, kEpiLnfA>(op, M, ep, st);
+    } else {
+      return cudaErrorInvalidValue;
+    }
   }
   const uint32_t need = epi_needs(ep);
   if (epi_clean(op, ep)) {

@@ -11,6 +11,7 @@
 // models/ncsn.py:155-178, models/shared.py:65,69).
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace smd {
@@ -45,6 +46,9 @@ struct GemmEpilogue {
   int ld_bf16;
   int act;                      // activation applied on the bf16 output path
   float* row_stats;             // [M][2] += (sum v, sum v^2) over this tile's columns (atomics), or null
+  float* stats_part;            // if set (with row_stats): instead of atomics every (n-tile, column-group) warp stores its
+                                // partial to stats_part[(row * nslots + n_tile * (epi_warps / 4) + group) * 2]; the
+                                // consumer (ln_film_act) adds the slots in a fixed order: bit-reproducible statistics
   const float* ln_gamma;        // full-row LayerNorm (requires N <= BN, a single n-tile): bf16 out = LN(v)*g+b
   const float* ln_beta;
   __nv_bfloat16* out_bf16_pre;  // bf16 [M][ld_bf16] <- v before the activation (training saves), or null
@@ -57,13 +61,13 @@ struct GemmEpilogue {
   // lnf_part and bumps the row group's counter; the tile stays parked in TMEM until the group's counter shows all
   // partials, then the same warps normalise it (models/shared.py:61-69).  row_stats (optional) gets the totals.
   float* lnf_part;              // [M_pad][lnf_slots][2] partial sums, slot = n_tile * 2 + column group
-  __nv_bfloat16* lnf_ring;      // [gridDim][2][128][BN] bf16 parking for v when neither out_f32 nor out_bf16_pre keeps it
   uint32_t* lnf_cnt;            // [M_pad / 32] arrival counters, zeroed before the launch
   const float* film;            // scale at film[r * film_ld + c], shift at film[r * film_ld + N + c]; null = no FiLM
   int film_ld;                  // row pitch of the (scale | shift) table
   int film_bcast;               // 1: every row uses table row (*film_row_dev or 0); 0: row r uses table row r / 32
   const int* film_row_dev;
   int act2;                     // activation after the affine (ACT_SWISH / ACT_NONE)
+  int lnf_nowait;               // measurement only (SMD_LNF_NOWAIT=1): skip the wait for the other tiles' partials
   // ---- strict-precision mode (bf16x3): every bf16 operand written through out_bf16 also gets its lo half at
   // out_bf16 + lo_delta (elements), and the activations use exact tanhf / expf.  0 = off.
   long long lo_delta;
@@ -83,7 +87,8 @@ static constexpr int kAccCols = 256;
 
 // kEW = number of epilogue warps (8: two per TMEM lane quadrant; 12: three, for epilogue-bound small-K GEMMs).
 // The pipeline depth is whatever fits next to the epilogue scratch in the 227 KB of shared memory.
-template <int kCG, int kEW = 8>
+// kPark: the LN-fused epilogue (F_LNF) parks the tile as bf16 [128][256] in shared memory between its two passes.
+template <int kCG, int kEW = 8, bool kPark = false>
 struct GemmSmem {
   static constexpr int kBRowsMax = 256 / kCG;
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB
@@ -92,11 +97,13 @@ struct GemmSmem {
   static constexpr int kBarBytes = 256;
   static constexpr int kEpiWarps = kEW;
   static constexpr int kScratchBytes = kEpiWarps * 32 * 33 * 4;            // per-epilogue-warp transpose scratch
+  static constexpr int kParkBytes = kPark ? kBM * 256 * 2 : 0;             // 64 KB
   static constexpr int kMaxSmem = 232448;                                  // 227 KB
-  static constexpr int kStages = (kMaxSmem - 1024 - kBarBytes - kScratchBytes) / kStageBytes;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kScratchBytes + 1024;  // + alignment slack
+  static constexpr int kStages = (kMaxSmem - 1024 - kBarBytes - kScratchBytes - kParkBytes) / kStageBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kScratchBytes + kParkBytes + 1024;  // + alignment slack
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
 };
+static constexpr bool lnf_kind(uint32_t kF) { return (kF & F_LNF) != 0 && (kF & F_RAGGED) == 0; }
 
 // MUFU.TANH (abs error ~5e-4, far below the bf16 rounding of everything that consumes it)
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -151,7 +158,7 @@ template <int kCG, uint32_t kF, int kEW = 8>
 __global__ void __launch_bounds__(128 + 32 * kEW, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape sh, const GemmEpilogue ep) {
-  using SM = GemmSmem<kCG, kEW>;
+  using SM = GemmSmem<kCG, kEW, lnf_kind(kF)>;
   static_assert(SM::kStages >= 3, "pipeline too shallow");
   static_assert(!((kF & F_LN) && !(kF & F_RAGGED)) || kEW == 8, "the paired LayerNorm epilogue needs 8 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
@@ -318,123 +325,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // ---------- epilogue that also finishes the NEXT LayerNorm -> FiLM -> activation over the FULL row ----------
       // The row (N = num_n * BN columns) spans num_n tiles computed by other CTAs in the same scheduling round (tiles
       // are m-major), so the row statistics are exchanged through global memory.
-      //   pass 1 (per tile): v = acc + bias (+ residual); v is stored -- fp32 to out_f32 (kinds with F_F32), otherwise
-      //     bf16 to out_bf16_pre or, when that is null, to a per-CTA ring in lnf_ring -- the TMEM stage is released at
-      //     once, and the warp publishes its per-row (sum, sumsq) into its own slot and bumps the row group's counter;
-      //   pass 2 (one tile LATER, so the exchange latency hides behind the next tile's pass 1): the counter is checked,
-      //     the slots are summed in a FIXED order (bit-reproducible, unlike atomics), v is read back through L2 and
-      //     out_bf16 <- act2(film(LN(v))) is written -- what the stand-alone ln_film_act kernel did with an HBM round
-      //     trip and a launch of its own.
+      //   pass 1: v = acc + bias (+ residual) -> fp32 out_f32 / bf16 out_bf16_pre stores as usual, per-row (sum, sumsq)
+      //     of this warp's columns, and v parked as bf16 in shared memory (XOR-swizzled 16-byte chunks); the TMEM stage
+      //     goes back to the MMA issuer right away;
+      //   exchange: the warp publishes its partial into its own slot, bumps the row group's counter and, while the
+      //     other n-tiles arrive, stages the per-column affine (gamma * scale, beta * scale + shift) of its columns;
+      //   pass 2: the slots are summed in a FIXED order (bit-reproducible, unlike atomics) and the parked tile becomes
+      //     out_bf16 = act2(film(LN(v))) -- what the stand-alone ln_film_act kernel did with an HBM round trip and a
+      //     launch of its own.  (Like that path's bf16 r1, the LayerNorm input is the bf16-rounded v; the statistics
+      //     are those of the fp32 v.)
       // Deadlock freedom: tiles are visited in increasing index by co-resident persistent CTAs; a wait only targets
       // pass 1 of tiles of the same round, which never waits on anything (launch one such kernel at a time).
       static_assert(kEW == 8, "the LN-fused epilogue is written for 8 epilogue warps");
-      constexpr bool SRC_F32 = H_F32;
       const int nslots = num_n * 2;
       const float inv_n = 1.0f / static_cast<float>(sh.N);
       const int act2 = ep.act2;
-      __nv_bfloat16* ring = ep.lnf_ring ? ep.lnf_ring + static_cast<size_t>(blockIdx.x) * 2 * kBM * BN : nullptr;
-      int p_row_base = -1, p_n0 = 0, p_nidx = 0, p_stride = 0;   // tile whose pass 2 is pending
-      const void* p_src = nullptr;
-      auto pass2 = [&]() {
-        const int row_base = p_row_base, n0 = p_n0;
-        const int row = row_base + static_cast<int>(lane);
-        uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
-        if (lane == 0) {
-          uint32_t spins = 0;
-          const unsigned long long t0 = global_timer_ns();
-          while (ld_acquire_gpu(cnt) < static_cast<uint32_t>(nslots)) {
-            if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
-          }
-        }
-        __syncwarp();
-        float t1 = 0.f, t2 = 0.f;
-        {
-          const float4* pp = reinterpret_cast<const float4*>(ep.lnf_part + static_cast<size_t>(row) * nslots * 2);
-          for (int s = 0; s < nslots / 2; ++s) {     // fixed order: the statistics are bit-reproducible
-            const float4 p = __ldcg(pp + s);
-            t1 += p.x; t2 += p.y; t1 += p.z; t2 += p.w;
-          }
-        }
-        const float mean_l = t1 * inv_n;
-        const float rstd_l = rsqrtf(t2 * inv_n - mean_l * mean_l + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
-        if (has_stats && row < sh.M && p_nidx == 0 && eg == 0)
-          *reinterpret_cast<float2*>(ep.row_stats + 2 * static_cast<size_t>(row)) = make_float2(t1, t2);
-        scr[2 * lane] = mean_l; scr[2 * lane + 1] = rstd_l;
-        __syncwarp();
-        const float* film_row = nullptr;       // FiLM row of this warp's 32 rows (one sample when seq_len == 32)
-        if (ep.film) {
-          const int fr = ep.film_bcast ? (ep.film_row_dev ? *ep.film_row_dev : 0) : (row_base >> 5);
-          film_row = ep.film + static_cast<size_t>(fr) * ep.film_ld;
-        }
-        for (int c0 = eg * 32; c0 < BN; c0 += 64) {
-          const int col0 = n0 + c0;
-          // per-column affine of this lane's 8 columns: y = xhat * A + B, A = gamma * scale, B = beta * scale + shift
-          float A[8], Bc[8];
-          {
-            const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0 + h_c);
-            const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0 + h_c);
-            const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-            A[0] = g0.x; A[1] = g0.y; A[2] = g0.z; A[3] = g0.w; A[4] = g1.x; A[5] = g1.y; A[6] = g1.z; A[7] = g1.w;
-            Bc[0] = b0.x; Bc[1] = b0.y; Bc[2] = b0.z; Bc[3] = b0.w; Bc[4] = b1.x; Bc[5] = b1.y; Bc[6] = b1.z; Bc[7] = b1.w;
-            if (film_row) {
-              const float4* s4 = reinterpret_cast<const float4*>(film_row + col0 + h_c);
-              const float4* h4 = reinterpret_cast<const float4*>(film_row + sh.N + col0 + h_c);
-              const float4 s0 = __ldg(s4), s1v = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
-              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
-              const float hf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { Bc[j] = fmaf(Bc[j], sc[j], hf[j]); A[j] *= sc[j]; }
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + h_r, grow = row_base + rr;
-            float x[8];
-            if constexpr (SRC_F32) {
-              const float* sp = static_cast<const float*>(p_src) + static_cast<size_t>(rr) * p_stride + c0 + h_c;
-              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-              if (grow < sh.M) { a0 = __ldcg(reinterpret_cast<const float4*>(sp)); a1 = __ldcg(reinterpret_cast<const float4*>(sp) + 1); }
-              x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
-            } else {
-              const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(p_src) + static_cast<size_t>(rr) * p_stride + c0 + h_c;
-              uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-              if (grow < sh.M) raw = __ldcg(reinterpret_cast<const uint4*>(sp));
-              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hp[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
-            }
-            const float mean = scr[2 * rr], rstd = scr[2 * rr + 1];
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float y0 = act_apply(fmaf((x[2 * j] - mean) * rstd, A[2 * j], Bc[2 * j]), act2);
-              const float y1 = act_apply(fmaf((x[2 * j + 1] - mean) * rstd, A[2 * j + 1], Bc[2 * j + 1]), act2);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
-              pk[j] = *reinterpret_cast<uint32_t*>(&p2);
-            }
-            if (grow < sh.M)
-              *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-        __syncwarp();
+      uint8_t* park = smem + SM::kStages * SM::kStageBytes + SM::kBarBytes + SM::kScratchBytes;   // [128 rows][512 B]
+      // this warp's 32 rows; 16-byte chunk c of row r sits at chunk (c ^ (r & 7))
+      auto park_ptr = [&](int rr, int chunk) {
+        const int r = static_cast<int>(q) * 32 + rr;
+        return park + r * 512 + ((chunk ^ (r & 7)) << 4);
       };
-      int iter = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups, ++iter) {
+      float* coefA = scr;            // [128] gamma * scale of this warp's columns (chunk-major: 4 x 32)
+      float* coefB = scr + 128;      // [128] beta * scale + shift
+      float* rowst = scr + 256;      // [32][2] mean, rstd
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int n_idx = tile % num_n;
         const int row_base = (tile / num_n) * rows_per_tile + static_cast<int>(rank) * kBM + static_cast<int>(q * 32u);
         const int row = row_base + static_cast<int>(lane);
         const int n0 = n_idx * BN;
-        // where pass 1 leaves v for pass 2 (element [0][0] = this warp's first row, the tile's first column)
-        const void* src; int stride;
-        __nv_bfloat16* vb = nullptr;
-        if constexpr (SRC_F32) {
-          src = ep.out_f32 + static_cast<size_t>(row_base) * ep.ld_f32 + n0; stride = ep.ld_f32;
-        } else {
-          if (has_pre) { vb = ep.out_bf16_pre + static_cast<size_t>(row_base) * ep.ld_bf16 + n0; stride = ep.ld_bf16; }
-          else { vb = ring + (static_cast<size_t>(iter & 1) * kBM + q * 32u) * BN; stride = BN; }
-          src = vb;
-        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
@@ -488,39 +407,60 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
-          if constexpr (SRC_F32) {
+          // park the row's 32 columns as bf16: four 16-byte chunks
+          {
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
-            __syncwarp();
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + f_r, grow = row_base + rr;
-              if (grow < sh.M) {
-                const float* sp = scr + rr * 33 + f_c;
-                *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c) =
-                    make_float4(sp[0], sp[1], sp[2], sp[3]);
-              }
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(park_ptr(static_cast<int>(lane), (c0 >> 3) + j)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if constexpr (H_F32) {
+            if (has_f32) {
+              // v goes back to TMEM: the fp32 store sweep runs AFTER the partials are published, so the fence of the
+              // exchange does not have to drain 16 KB of tile stores per warp
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+              tmem_st_32x32(taddr + static_cast<uint32_t>(c0), r);
             }
-            __syncwarp();
-          } else {
+          }
+        }
+        // ---------------- exchange ----------------
+        uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
+        {
+          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * 2 + eg);
+          __stcg(slot, make_float2(s1, s2));
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) red_release_gpu_add(cnt, 1u);
+        }
+        if constexpr (H_F32) {
+          if (has_f32) {
+            tmem_st_wait();
+            for (int c0 = eg * 32; c0 < BN; c0 += 64) {
+              __syncwarp();
+              uint32_t r[32];
+              tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              scrw[lane * 33 + j] = *reinterpret_cast<uint32_t*>(&pk);
-            }
-            __syncwarp();
+              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = __uint_as_float(r[i]);
+              __syncwarp();
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rr = it * 8 + h_r, grow = row_base + rr;
-              if (!has_pre || grow < sh.M) {
-                const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                *reinterpret_cast<uint4*>(vb + static_cast<size_t>(rr) * stride + c0 + h_c) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + f_r, grow = row_base + rr;
+                if (grow < sh.M) {
+                  const float* sp = scr + rr * 33 + f_c;
+                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + n0 + c0 + f_c) =
+                      make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
               }
             }
             __syncwarp();
           }
         }
-        // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA issuer
+        // all TMEM accesses of this tile are done: hand the accumulator stage back to the MMA issuer
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -528,18 +468,112 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        // publish this warp's partial of every row (and, with it, the stored v) and count the arrival
-        {
-          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * 2 + eg);
-          __stcg(slot, make_float2(s1, s2));
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) red_release_gpu_add(ep.lnf_cnt + (row_base >> 5), 1u);
+        if constexpr (H_PRE) {
+          if (has_pre) {
+            // the pre-LayerNorm copy the backward pass wants (bf16 [M][N]) comes straight from the parked tile
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = ((eg * 32 + 64 * j) >> 3) + static_cast<int>(lane & 3u);
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + h_r, grow = row_base + rr;
+                if (64 * j + eg * 32 < BN && grow < sh.M)
+                  *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + n0 + eg * 32 + 64 * j + h_c) =
+                      *reinterpret_cast<const uint4*>(park_ptr(rr, chunk));
+              }
+            }
+          }
         }
-        if (p_row_base >= 0) pass2();             // the previous tile: its row group has long been completed
-        p_row_base = row_base; p_n0 = n0; p_nidx = n_idx; p_src = src; p_stride = stride;
+        {
+          // per-column affine of this warp's columns while the other n-tiles arrive: lane l owns 4 columns per chunk
+          const float* film_row = nullptr;       // FiLM row of this warp's 32 rows (one sample when seq_len == 32)
+          if (ep.film) {
+            const int fr = ep.film_bcast ? (ep.film_row_dev ? *ep.film_row_dev : 0) : (row_base >> 5);
+            film_row = ep.film + static_cast<size_t>(fr) * ep.film_ld;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c0 = eg * 32 + 64 * j;
+            if (c0 < BN) {
+              const int col = n0 + c0 + 4 * static_cast<int>(lane & 7u);
+              if (lane < 8) {
+                float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
+                float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+                if (film_row) {
+                  const float4 sc = __ldg(reinterpret_cast<const float4*>(film_row + col));
+                  const float4 hf = __ldg(reinterpret_cast<const float4*>(film_row + sh.N + col));
+                  b = make_float4(fmaf(b.x, sc.x, hf.x), fmaf(b.y, sc.y, hf.y), fmaf(b.z, sc.z, hf.z), fmaf(b.w, sc.w, hf.w));
+                  g = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+                }
+                *reinterpret_cast<float4*>(coefA + 32 * j + 4 * lane) = g;
+                *reinterpret_cast<float4*>(coefB + 32 * j + 4 * lane) = b;
+              }
+            }
+          }
+        }
+        if (lane == 0 && !ep.lnf_nowait) {
+          uint32_t spins = 0;
+          const unsigned long long t0 = global_timer_ns();
+          while (ld_acquire_gpu(cnt) < static_cast<uint32_t>(nslots)) {
+            if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
+          }
+        }
+        __syncwarp();
+        {
+          float t1 = 0.f, t2 = 0.f;
+          const float4* pp = reinterpret_cast<const float4*>(ep.lnf_part + static_cast<size_t>(row) * nslots * 2);
+          for (int s = 0; s < nslots / 2; ++s) {     // fixed order: the statistics are bit-reproducible
+            const float4 p = __ldcg(pp + s);
+            t1 += p.x; t2 += p.y; t1 += p.z; t2 += p.w;
+          }
+          const float mean_l = t1 * inv_n;
+          const float rstd_l = rsqrtf(t2 * inv_n - mean_l * mean_l + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
+          if (has_stats && row < sh.M && n_idx == 0 && eg == 0)
+            *reinterpret_cast<float2*>(ep.row_stats + 2 * static_cast<size_t>(row)) = make_float2(t1, t2);
+          rowst[2 * lane] = mean_l; rowst[2 * lane + 1] = rstd_l;
+        }
+        __syncwarp();
+        // ---------------- pass 2 ----------------
+        auto pass2 = [&](auto swish_tag) {
+        constexpr bool kSwish = decltype(swish_tag)::value;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = eg * 32 + 64 * j;
+          if (c0 < BN) {
+            const int col0 = n0 + c0;
+            float A[8], Bc[8];
+            {
+              const float4 a0 = *reinterpret_cast<const float4*>(coefA + 32 * j + h_c), a1 = *reinterpret_cast<const float4*>(coefA + 32 * j + h_c + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(coefB + 32 * j + h_c), b1 = *reinterpret_cast<const float4*>(coefB + 32 * j + h_c + 4);
+              A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
+              Bc[0] = b0.x; Bc[1] = b0.y; Bc[2] = b0.z; Bc[3] = b0.w; Bc[4] = b1.x; Bc[5] = b1.y; Bc[6] = b1.z; Bc[7] = b1.w;
+            }
+            const int chunk = (c0 >> 3) + static_cast<int>(lane & 3u);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + h_r, grow = row_base + rr;
+              const uint4 raw = *reinterpret_cast<const uint4*>(park_ptr(rr, chunk));
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+              const float mean = rowst[2 * rr], rstd = rowst[2 * rr + 1];
+              uint32_t pk[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float2 f = __bfloat1622float2(hp[k2]);
+                float y0 = fmaf((f.x - mean) * rstd, A[2 * k2], Bc[2 * k2]);
+                float y1 = fmaf((f.y - mean) * rstd, A[2 * k2 + 1], Bc[2 * k2 + 1]);
+                if constexpr (kSwish) { y0 = act_apply(y0, ACT_SWISH); y1 = act_apply(y1, ACT_SWISH); }
+                pk[k2] = pack_bf16x2(y0, y1);
+              }
+              if (grow < sh.M)
+                *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        };
+        if (act2 == ACT_SWISH) pass2(std::true_type{}); else pass2(std::false_type{});
+        __syncwarp();
       }
-      if (p_row_base >= 0) pass2();
     } else if constexpr (H_LN && !H_RAGGED) {
       // ---------- single-pass full-row LayerNorm epilogue (N == BN <= 128: attention out-proj, FFN down) ----------
       // The two warps of a TMEM quadrant split the row's chunks, keep their values in registers, exchange the
@@ -998,8 +1032,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }  // passes
       if constexpr (H_STATS) {
         if (has_stats && row_ok) {
-          atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row), s1);
-          atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row) + 1, s2);
+          if (ep.stats_part != nullptr && !do_ln) {
+            const int per_tile = kEW / 4;
+            float2* slot = reinterpret_cast<float2*>(ep.stats_part) +
+                           static_cast<size_t>(row) * (num_n * per_tile) + ((mn % num_n) * per_tile + eg);
+            *slot = make_float2(s1, s2);
+          } else {
+            atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row), s1);
+            atomicAdd(ep.row_stats + 2 * static_cast<size_t>(row) + 1, s2);
+          }
         }
       }
       // release this accumulator stage back to the MMA issuer

@@ -365,10 +365,12 @@ __global__ void __launch_bounds__(MAXT)
 ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats, const float* __restrict__ g,
                    const float* __restrict__ bta, const float* __restrict__ scale, const float* __restrict__ shift,
                    int film_ld, int film_bcast, int act, __nv_bfloat16* __restrict__ out, int M, int N, int S,
-                   const int* __restrict__ film_row_dev, long long lo_delta) {
+                   const int* __restrict__ film_row_dev, long long lo_delta, const float* __restrict__ part, int nslots,
+                   float* __restrict__ stats_out) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t lsm[];
+  __shared__ float2 row_mr[32];   // (mean, rstd) of this CTA's 32 rows
   constexpr int RPG = 4;                                   // rows per copy group
   constexpr int ES = IN_BF16 ? 2 : 4;
   const uint32_t row_bytes = static_cast<uint32_t>(N) * ES;
@@ -396,6 +398,25 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
     if (ngroups > 1) issue(1);
   }
   const float inv_n = 1.0f / static_cast<float>(N);
+  if (threadIdx.x < 32) {
+    // row statistics: either the (sum, sumsq) totals, or the producing GEMM's per-tile partials added in slot order
+    // (bit-reproducible; the totals are handed on to the backward pass through stats_out)
+    const int row = r0 + static_cast<int>(threadIdx.x);
+    float t1 = 0.f, t2 = 0.f;
+    if (row < M) {
+      if (part != nullptr) {
+        const float2* pp = reinterpret_cast<const float2*>(part) + static_cast<size_t>(row) * nslots;
+        for (int s = 0; s < nslots; ++s) { const float2 p2 = pp[s]; t1 += p2.x; t2 += p2.y; }
+        if (stats_out != nullptr) *reinterpret_cast<float2*>(stats_out + 2 * static_cast<size_t>(row)) = make_float2(t1, t2);
+      } else {
+        const float2 st = *reinterpret_cast<const float2*>(stats + 2 * static_cast<size_t>(row));
+        t1 = st.x; t2 = st.y;
+      }
+    }
+    const float mean = t1 * inv_n;
+    row_mr[threadIdx.x] = make_float2(mean, rsqrtf(t2 * inv_n - mean * mean + 1e-6f));
+  }
+  __syncthreads();
   const float4 g4 = *reinterpret_cast<const float4*>(g + c);
   const float4 b4 = *reinterpret_cast<const float4*>(bta + c);
   const bool film = scale != nullptr;
@@ -422,9 +443,8 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
       } else {
         x = *reinterpret_cast<const float4*>(sb + static_cast<size_t>(q) * row_bytes + static_cast<size_t>(c) * 4);
       }
-      const float2 st = *reinterpret_cast<const float2*>(stats + 2 * static_cast<size_t>(row));
-      const float mean = st.x * inv_n;
-      const float rstd = rsqrtf(st.y * inv_n - mean * mean + 1e-6f);
+      const float2 mr = row_mr[row - r0];
+      const float mean = mr.x, rstd = mr.y;
       if (film && !row_const_film) {
         const size_t frow = static_cast<size_t>(row / S);
         s4 = *reinterpret_cast<const float4*>(scale + frow * film_ld + c);
@@ -457,7 +477,8 @@ ln_film_act_kernel(const void* __restrict__ uin, const float* __restrict__ stats
 }
 void launch_ln_film_act(const float* u, const float* stats, const float* g, const float* b, const float* scale,
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
-                        int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16, long long lo_delta) {
+                        int S, cudaStream_t st, const int* film_row_dev, const __nv_bfloat16* u16, long long lo_delta,
+                        const float* part, int nslots, float* stats_out) {
   const int blocks = (M + 31) / 32;
   const int threads = N / 4;
   const bool bf = (u16 != nullptr);
@@ -471,7 +492,7 @@ void launch_ln_film_act(const float* u, const float* stats, const float* g, cons
       attr = true;                                                                                               \
     }                                                                                                            \
     launch_pdl_g(kPdlLnFilmFwd, ln_film_act_kernel<MAXT, BF>, dim3(blocks), dim3(threads), smem, st, in, stats, g, b, scale, shift, film_ld, film_bcast, act, \
-                                                                out, M, N, S, film_row_dev, lo_delta);           \
+                                                                out, M, N, S, film_row_dev, lo_delta, part, nslots, stats_out); \
   }
   if (threads <= 512) {
     if (bf) SMD_LN_LAUNCH(512, true) else SMD_LN_LAUNCH(512, false)

@@ -161,7 +161,10 @@ void launch_ln_film_act(const float* u, const float* stats, const float* g, cons
                         const float* shift, int film_ld, int film_bcast, int act, __nv_bfloat16* out, int M, int N,
                         int S, cudaStream_t st, const int* film_row_dev = nullptr,
                         const __nv_bfloat16* u16 = nullptr,    // u16: the LayerNorm input stored as bf16 (u == null)
-                        long long lo_delta = 0);
+                        long long lo_delta = 0,
+                        // part != null: the row statistics are the producing GEMM's per-tile partials
+                        // part[(row * nslots + s) * 2], added here in slot order; the totals go to stats_out (or null)
+                        const float* part = nullptr, int nslots = 0, float* stats_out = nullptr);
 
 // enc[r, j] = sin((5000 t_r) f_j), enc[r, 64 + j] = cos(...)                          (models/ncsn.py:25-41)
 void launch_noise_encoding(const float* t, const float* freqs, float* enc, int R, cudaStream_t st);

@@ -71,6 +71,7 @@ struct smd_plan {
   uint8_t* ws = nullptr;
   bool packed = false;
   std::vector<smd::PackJob> pack_jobs;
+  std::vector<int> stat_slots;   // per wide LayerNorm: partial slots per row its producing GEMM wrote (0: atomics / totals)
   int pack_tiles = 0;
   // ---- GEMM ops ----
   std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b, op_b2;

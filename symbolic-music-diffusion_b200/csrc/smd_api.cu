@@ -121,8 +121,7 @@ static void build_workspace(smd_plan* p) {
   // per-row LayerNorm (sum, sumsq) of the 2K+1 wide LayerNorms, followed by the arrival counters of the LN-fused GEMM
   // epilogues (one u32 per 32 rows and fused launch); the whole region is zeroed once per forward
   ws_add(p, "stats", (2 * K + 1) * Mp * 2 * 4 + (2 * K + 2) * (Mp / 32) * 4);
-  ws_add(p, "lnf_part", Mp * (Md / 256 * 2) * 2 * 4);   // per-tile partial sums [row][n_tile * 2 + column group][2]
-  ws_add(p, "lnf_ring", static_cast<size_t>(160) * 2 * 128 * 256 * 2);   // per-CTA bf16 parking (inference, GEMM a)
+  ws_add(p, "lnf_part", Mp * (Md / 256 * 3) * 2 * 4);   // per-tile partial sums [row][n_tile * (2 or 3) + column group][2]
   // FiLM generator
   ws_add(p, "tvec", B * 4);
   ws_add(p, "enc", B * kFilmEmb * 4);
@@ -215,8 +214,15 @@ static int build_ops(smd_plan* p) {
 // Every forward GEMM goes through here.  Default precision: one launch.  bf16x3: the product of the (hi, lo) operand
 // pairs as three launches -- scratch = A_lo B_hi (+ the layer's residual); scratch += A_hi B_lo; then the real launch
 // A_hi B_hi with the layer's epilogue taking `scratch` as its residual -- all accumulated in fp32.
-static cudaError_t gemm(smd_plan* p, const GemmOp& op, int M, GemmEpilogue e, cudaStream_t st) {
-  if (p->lo_bytes == 0) return launch_gemm(op, M, e, st);
+// ln_slot >= 0: this GEMM feeds wide LayerNorm `ln_slot` through a stand-alone ln_film_act launch: its row statistics
+// go out as per-tile partials (added in a fixed order by the consumer) instead of atomics.
+static cudaError_t gemm(smd_plan* p, const GemmOp& op, int M, GemmEpilogue e, cudaStream_t st, int ln_slot = -1) {
+  auto arm_stats = [&](GemmEpilogue& ef) {
+    if (ln_slot < 0 || ef.row_stats == nullptr) return;
+    ef.stats_part = p->buf<float>("lnf_part");
+    p->stat_slots[ln_slot] = stats_slots_for(op, ef);
+  };
+  if (p->lo_bytes == 0) { arm_stats(e); return launch_gemm(op, M, e, st); }
   if (!op.has_lo) return cudaErrorInvalidValue;
   float* scratch = p->buf<float>("x3.scratch");
   GemmOp o1 = op; o1.tmA = op.tmA_lo;
@@ -233,7 +239,15 @@ static cudaError_t gemm(smd_plan* p, const GemmOp& op, int M, GemmEpilogue e, cu
   if (err != cudaSuccess) return err;
   e.residual = scratch; e.ld_res = op.N;
   e.lo_delta = p->lo_elems;
+  arm_stats(e);
   return launch_gemm(op, M, e, st);
+}
+// ln_film_act arguments for the statistics of wide LayerNorm `ln_slot` (partials + slot count, or totals)
+struct LnStats { const float* part; int nslots; float* totals; };
+static LnStats ln_stats(smd_plan* p, int ln_slot) {
+  float* totals = p->buf<float>("stats") + static_cast<size_t>(ln_slot) * p->Mp * 2;
+  const int n = p->stat_slots[ln_slot];
+  return n > 0 ? LnStats{p->buf<float>("lnf_part"), n, totals} : LnStats{nullptr, 0, totals};
 }
 
 // FiLM generator for all K blocks: t (R values) -> ss[k][R][2*Md]   (models/ncsn.py:47-61)
@@ -281,7 +295,9 @@ static bool lnf_enabled() {
 // one FiLM (scale | shift) row per sample of 32 rows, or one row for everybody (sampler): the fused epilogue cannot
 // serve DenseDDPM's one-row-per-example case (a 32-row warp tile would span 32 FiLM rows)
 bool lnf_usable(const smd_plan* p, int S, int t_broadcast) {
-  return lnf_enabled() && p->lo_bytes == 0 && (S == 32 || t_broadcast || p->film_tab_on) && p->cfg.mlp_dims % 256 == 0;
+  // (cta_group 1 stages 48 KB per pipeline slot: no room for the 64 KB parking buffer next to >= 3 slots)
+  return lnf_enabled() && p->lo_bytes == 0 && p->cfg.cta_group == 2 && (S == 32 || t_broadcast || p->film_tab_on) &&
+         p->cfg.mlp_dims % 256 == 0;
 }
 // FiLM table / row selection of block k (shared by the fused epilogue and the stand-alone kernel)
 static void film_source(const smd_plan* p, int k, int t_broadcast, const float** scale, int* bcast, const int** row_dev) {
@@ -306,10 +322,11 @@ void arm_lnf(const smd_plan* p, const float* params, GemmEpilogue* e, const std:
   e->ln_gamma = p->P(params, ln + "scale"); e->ln_beta = p->P(params, ln + "bias");
   e->out_bf16 = out; e->ld_bf16 = Md;
   e->lnf_part = p->buf<float>("lnf_part");
-  e->lnf_ring = p->buf<__nv_bfloat16>("lnf_ring");
   e->lnf_cnt = cnt0 + static_cast<size_t>(ln_slot) * (p->Mp / 32);
   e->row_stats = want_totals ? stats + static_cast<size_t>(ln_slot) * sstride : nullptr;
   e->film = nullptr; e->film_ld = 2 * Md; e->film_bcast = 0; e->film_row_dev = nullptr; e->act2 = ACT_NONE;
+  static const int nowait = [] { const char* v = getenv("SMD_LNF_NOWAIT"); return (v && v[0] == '1') ? 1 : 0; }();
+  e->lnf_nowait = nowait;
   if (k >= 0) {
     film_source(p, k, t_broadcast, &e->film, &e->film_bcast, &e->film_row_dev);
     e->act2 = ACT_SWISH;
@@ -360,8 +377,21 @@ static int run_tail_fused(smd_plan* p, const float* params, int M, int S, int t_
 // The FiLM'd residual tail shared by both architectures (models/ncsn.py:173-178, models/shared.py:61-75).
 // On entry u (fp32 [M][Md]) and stats[0] hold the block input and its row statistics.
 static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadcast, float* y, cudaStream_t st,
-                    smd::TrainState* save, bool act0_ready) {
-  if (act0_ready) return run_tail_fused(p, params, M, S, t_broadcast, y, st, save);
+                    smd::TrainState* save, bool fuse_tail, bool act0_ready) {
+  if (fuse_tail) {
+    if (!act0_ready) {
+      // first block's operand from the stand-alone kernel (the K = 128 post GEMM is epilogue-bound: fusing there costs
+      // more than the launch it saves -- measured 187 us against 27 + 61 us at 32000 tokens)
+      const float* scale; int bcast; const int* row_dev;
+      film_source(p, 0, t_broadcast, &scale, &bcast, &row_dev);
+      const LnStats ls = ln_stats(p, 0);
+      launch_ln_film_act(save ? save->u(p->ws, 0) : p->buf<float>("u"), ls.totals, p->P(params, "k0.res.ln_a.scale"),
+                         p->P(params, "k0.res.ln_a.bias"), scale, scale + p->cfg.mlp_dims, 2 * p->cfg.mlp_dims, bcast, 2,
+                         save ? save->act_a(p->ws, 0) : p->buf<__nv_bfloat16>("act"), M, p->cfg.mlp_dims, S, st, row_dev,
+                         nullptr, 0, ls.part, ls.nslots, ls.totals); CNT();
+    }
+    return run_tail_fused(p, params, M, S, t_broadcast, y, st, save);
+  }
   const int Md = p->cfg.mlp_dims, C = p->cfg.channels;
   float* u = p->buf<float>("u");
   float* r1 = p->buf<float>("r1");
@@ -388,8 +418,10 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
       act_b = save->act_b(p->ws, k); u_out = save->u(p->ws, k + 1);
     }
     const bool strict = p->lo_bytes != 0;
-    launch_ln_film_act(u_in, stats + (2 * k) * sstride, p->P(params, pre + "ln_a.scale"), p->P(params, pre + "ln_a.bias"),
-                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st, frow_dev, nullptr, p->lo_elems); CNT();
+    LnStats ls = ln_stats(p, 2 * k);
+    launch_ln_film_act(u_in, ls.totals, p->P(params, pre + "ln_a.scale"), p->P(params, pre + "ln_a.bias"),
+                       scale, shift, 2 * Md, t_broadcast, 2, act_a, M, Md, S, st, frow_dev, nullptr, p->lo_elems,
+                       ls.part, ls.nslots, ls.totals); CNT();
     GemmEpilogue e = epi();
     e.bias = p->P(params, pre + "a.bias");
     if (strict) { e.out_f32 = r1; e.ld_f32 = Md; }       // (strict mode keeps the pre-LayerNorm intermediate in fp32)
@@ -398,21 +430,24 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
     GemmOp opa = p->op_a[k];
     GemmOp opb = p->op_b[k];
     if (save) { if (!retarget_a(&opa, act_a, p->Mp) || !retarget_a(&opb, act_b, p->Mp)) return SMD_ERR_CUDA; }
-    SMD_CUDA(gemm(p, opa, M, e, st));
-    launch_ln_film_act(strict ? r1 : nullptr, stats + (2 * k + 1) * sstride, p->P(params, pre + "ln_b.scale"),
+    SMD_CUDA(gemm(p, opa, M, e, st, 2 * k + 1));
+    ls = ln_stats(p, 2 * k + 1);
+    launch_ln_film_act(strict ? r1 : nullptr, ls.totals, p->P(params, pre + "ln_b.scale"),
                        p->P(params, pre + "ln_b.bias"), scale, shift, 2 * Md, t_broadcast, 2, act_b, M, Md, S, st, frow_dev,
-                       strict ? nullptr : r1_out, p->lo_elems); CNT();
+                       strict ? nullptr : r1_out, p->lo_elems, ls.part, ls.nslots, ls.totals); CNT();
     e = epi();
     e.bias = p->P(params, pre + "b.bias");
     e.residual = u_in; e.ld_res = Md;
     e.out_f32 = u_out; e.ld_f32 = Md;
     e.row_stats = stats + (2 * k + 2) * sstride;
-    SMD_CUDA(gemm(p, opb, M, e, st));
+    SMD_CUDA(gemm(p, opb, M, e, st, 2 * k + 2));
   }
   float* u_last = save ? save->u(p->ws, p->K) : u;
   __nv_bfloat16* act_o = save ? save->act_out(p->ws) : act;
-  launch_ln_film_act(u_last, stats + (2 * p->K) * sstride, p->P(params, "out_ln.scale"), p->P(params, "out_ln.bias"),
-                     nullptr, nullptr, 0, 0, 0, act_o, M, Md, S, st, nullptr, nullptr, p->lo_elems); CNT();
+  const LnStats lo_ = ln_stats(p, 2 * p->K);
+  launch_ln_film_act(u_last, lo_.totals, p->P(params, "out_ln.scale"), p->P(params, "out_ln.bias"),
+                     nullptr, nullptr, 0, 0, 0, act_o, M, Md, S, st, nullptr, nullptr, p->lo_elems, lo_.part, lo_.nslots,
+                     lo_.totals); CNT();
   GemmEpilogue e = epi();
   e.bias = p->P(params, "out.bias");
   e.out_f32 = y; e.ld_f32 = C;
@@ -432,6 +467,7 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
   const int S = c.seq_len, C = c.channels, Md = c.mlp_dims;
   const int M = batch * S;
   float* stats = p->buf<float>("stats");
+  p->stat_slots.assign(static_cast<size_t>(2 * p->K + 1), 0);
   SMD_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * p->K + 1) * p->Mp * 2 * 4 +
                                          static_cast<size_t>(2 * p->K + 2) * (p->Mp / 32) * 4, st));
   int rc = SMD_OK;
@@ -454,6 +490,8 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
   if (rc) return rc;
   float* u0 = save ? save->u(p->ws, 0) : p->buf<float>("u");
   const bool fuse_tail = c.arch == SMD_ARCH_TRANSFORMER_DDPM && lnf_usable(p, S, t_broadcast);
+  static const bool lnf_post = [] { const char* v = getenv("SMD_LNF_POST"); return v && v[0] == '1'; }();
+  const bool fuse_post = fuse_tail && lnf_post;
   if (c.arch == SMD_ARCH_TRANSFORMER_DDPM) {
     float* h = p->buf<float>("h");
     __nv_bfloat16* a = p->buf<__nv_bfloat16>("a");
@@ -525,7 +563,7 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
     e.bias = p->P(params, "post.bias");
     e.out_f32 = u0; e.ld_f32 = Md;
     e.row_stats = stats;
-    if (fuse_tail) {
+    if (fuse_post) {
       // the first res-block's LayerNorm -> FiLM -> swish happens in this GEMM's epilogue: needs the FiLM rows now
       if (film_on_side) { SMD_CUDA(cudaStreamWaitEvent(st, p->ev_film, 0)); film_on_side = false; }
       arm_lnf(p, params, &e, "k0.res.ln_a.", 0, 0, t_broadcast, save ? save->act_a(p->ws, 0) : p->buf<__nv_bfloat16>("act"),
@@ -533,7 +571,7 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
     }
     GemmOp op = p->op_post;
     if (save) { if (!retarget_a(&op, save->a_post(p->ws), p->Mp)) return SMD_ERR_CUDA; }
-    SMD_CUDA(gemm(p, op, M, e, st));
+    SMD_CUDA(gemm(p, op, M, e, st, fuse_post ? -1 : 0));
   } else {
     __nv_bfloat16* xb = p->buf<__nv_bfloat16>("xb");
     const int Cp = (C + 63) / 64 * 64;
@@ -543,11 +581,11 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
     e.bias = p->P(params, "in.bias");
     e.out_f32 = u0; e.ld_f32 = Md;
     e.row_stats = stats;
-    SMD_CUDA(gemm(p, p->op_in, M, e, st));
+    SMD_CUDA(gemm(p, p->op_in, M, e, st, 0));
   }
   SMD_LAUNCH_CHECK("trunk");
   if (film_on_side) SMD_CUDA(cudaStreamWaitEvent(st, p->ev_film, 0));
-  return run_tail(p, params, M, S, t_broadcast, y, st, save, fuse_tail);
+  return run_tail(p, params, M, S, t_broadcast, y, st, save, fuse_tail, fuse_post);
 }
 
 // host threefry (same block function as the device one)

@@ -100,3 +100,21 @@ def test_get_dataset_errors_and_synthetic(tmp_path):
     tr, ev = ip.get_dataset(data_shape=[32, 512], batch_size=8, synthetic=True, synthetic_examples=64)
     b = next(iter(tr))
     assert b.shape == (8, 32, 512) and tr.examples == 8 and abs(b).max() <= 1.0 + 1e-6
+
+
+def test_reads_records_serialized_by_the_protobuf_runtime():
+    """tests/golden/tfrecord_protobuf.tfrecord was written by Google's protobuf runtime from the tf.train.Example
+    schema (scripts/make_tfrecord_fixture.py) with an independent bit-wise crc32c: the hand-written TFRecord /
+    protobuf reader must decode it exactly (layout of scripts/transform_encoded_data.py:71-92 upstream)."""
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    want = np.load(os.path.join(here, "tfrecord_protobuf_expected.npz"))
+    recs = list(ip.read_tfrecord(os.path.join(here, "tfrecord_protobuf.tfrecord"), verify=True))
+    assert len(recs) == 3
+    for i, payload in enumerate(recs):
+        ex = ip.parse_example(payload)
+        a = want[f"ex{i}"]
+        assert ex["inputs"].dtype == np.float32 and ex["input_shape"].dtype == np.int64
+        assert tuple(ex["input_shape"]) == a.shape
+        np.testing.assert_array_equal(ex["inputs"].reshape(a.shape).view(np.uint32), a.view(np.uint32))   # bit-exact
+    ex1 = ip.parse_example(recs[1])
+    np.testing.assert_array_equal(ex1["targets"].reshape(tuple(ex1["target_shape"])), want["ex1_targets"])
