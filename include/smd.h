@@ -38,7 +38,13 @@ enum smd_status {
   SMD_ERR_STATE = -3      /* call order (e.g. workspace not bound) */
 };
 
-enum smd_arch { SMD_ARCH_TRANSFORMER_DDPM = 0, SMD_ARCH_DENSE_DDPM = 1 };
+enum smd_arch {
+  SMD_ARCH_TRANSFORMER_DDPM = 0,
+  SMD_ARCH_DENSE_DDPM = 1,
+  /* models/ncsn.py:83-98 (DenseNCSN) with its undefined `t` read as `sigmas`: the DenseDDPM stack conditioned on sigma,
+   * output divided by sigma (a score).  Same parameter layout as SMD_ARCH_DENSE_DDPM. */
+  SMD_ARCH_DENSE_NCSN = 2
+};
 
 typedef struct smd_config {
   int arch;            /* smd_arch; TransformerDDPM4 (configs/ddpm-multi-32seq-512.cfg:1) == TransformerDDPM */
@@ -135,6 +141,28 @@ int smd_ddpm_draws(smd_plan* plan, const uint32_t host_key[2], int batch, float*
 int smd_ddpm_draws_sharded(smd_plan* plan, const uint32_t host_key[2], int global_batch, int first_row, int batch,
                            int continuous_noise, float* used_alpha, float* eps, int* labels_or_null,
                            smd_stream_t stream);
+
+/* ---- NCSN family: denoising score matching + Langevin samplers ------------------------------- */
+/* denoising_score_matching_loss (utils/losses.py:129-179) with the draws supplied: x~ = x0 + used_sigma * eps,
+ * scores = model(x~, used_sigma), loss[b] = 0.5 * sum((scores + eps / sigma)^2) * sigma^2.  pred_or_null <- scores. */
+int smd_dsm_loss(smd_plan* plan, const float* params, const float* x0, const float* used_sigma, const float* eps,
+                 int batch, float* loss_per_example, float* pred_or_null, smd_stream_t stream);
+/* gradients of mean_{global batch}(that loss); same contract as smd_ddpm_grads (loss_sum: 2 floats) */
+int smd_dsm_grads(smd_plan* plan, const float* params, const float* x0, const float* used_sigma, const float* eps,
+                  int batch, int global_batch, float* grads, float* loss_sum, smd_stream_t stream);
+/* its random draws (utils/losses.py:146-164): labels = randint(int(continuous), L); used_sigma = uniform(sigmas[l-1],
+ * sigmas[l]) (continuous) or sigmas[l]; eps = normal.  smd_dsm_setup uploads the schedule (host_sigmas: L floats). */
+int smd_dsm_setup(smd_plan* plan, const float* host_sigmas, int L, smd_stream_t stream);
+int smd_dsm_draws(smd_plan* plan, const uint32_t host_key[2], int global_batch, int first_row, int batch,
+                  int continuous_noise, float* used_sigma, float* eps, int* labels_or_null, smd_stream_t stream);
+/* One Langevin update after a network call (annealed_langevin_dynamics utils/ebm_utils.py:139-175, consistent_... :231-253):
+ *   x_next = x + alpha * grad + noise_coef * z;  with a mask: x_next = x_next (1 - mask) + (infill_x + infill_sigma z') mask.
+ * z / infill_z: supplied N(0,1) tensors or NULL -> jax.random.normal(step_key / infill_key).  metrics4 (device, 4 floats,
+ * pre-zeroed) receives grad_norm, step_norm, alpha, noise_norm; collection_slot (n,S,C) or NULL gets a copy of x_next. */
+int smd_langevin_step(smd_plan* plan, const float* x, const float* grad, int n, float alpha, float noise_coef,
+                      const uint32_t step_key[2], const float* z, const float* infill_x, const float* infill_mask,
+                      float infill_sigma, const uint32_t infill_key[2], const float* infill_z, float* x_next,
+                      float* collection_slot, float* metrics4, smd_stream_t stream);
 
 /* ---- sampler ---------------------------------------------------------------------------------------------- */
 /* host_betas: HOST pointer, T floats.  Builds the per-step coefficient / key / slot tables in the workspace.

@@ -220,11 +220,22 @@ def dense_ddpm(p: Dict[str, Tensor], inputs: Tensor, t: Tensor, num_layers: int 
     return x
 
 
+def dense_ncsn(p: Dict[str, Tensor], inputs: Tensor, sigmas: Tensor, num_layers: int = 3,
+               mlp_dims: int = 2048, emulate_bf16: bool = False, **_ignored) -> Tensor:
+    """models/ncsn.py:83-98 (DenseNCSN.apply) with its undefined `t` read as `sigmas` (broken as released; SURVEY
+    section 0): the DenseDDPM stack conditioned on sigma, output divided by sigma.  inputs (B,C), sigmas (B,1) or (B,)."""
+    B = inputs.shape[0]
+    return dense_ddpm(p, inputs, sigmas, num_layers=num_layers, mlp_dims=mlp_dims, emulate_bf16=emulate_bf16) / \
+        sigmas.reshape(B, 1)
+
+
 def model_apply(arch: str, p, inputs, t, **kw):
     if arch in ("TransformerDDPM", "TransformerDDPM4"):
         return transformer_ddpm(p, inputs, t, **kw)
     if arch == "DenseDDPM":
         return dense_ddpm(p, inputs, t, **kw)
+    if arch == "DenseNCSN":
+        return dense_ncsn(p, inputs, t, **kw)
     raise ValueError(f"unknown architecture {arch}")
 
 
@@ -315,6 +326,107 @@ def diffusion_loss_draws(rng_key, batch_shape, betas, continuous_noise=True):
     used = uniform_minmax(u, ap[labels - 1], ap[labels])
     eps = tf.normal(sample_rng, tuple(batch_shape))
     return labels, used, eps
+
+
+# ----------------------------------------------------------------------------
+# utils/losses.py:129-179  denoising_score_matching_loss  (NCSN family)
+# ----------------------------------------------------------------------------
+def dsm_loss_tensors(apply_fn, batch: Tensor, used_sigmas: Tensor, eps: Tensor, reduction: str = "mean"):
+    """losses.py:161-179 given the sampled tensors.  used_sigmas (B,), eps: batch.shape.  Returns (loss, scores)."""
+    B = batch.shape[0]
+    us = used_sigmas.reshape(B, *([1] * (batch.dim() - 1)))
+    noise = eps * us
+    perturbed = batch + noise
+    target = -1 / (us ** 2) * noise
+    scores = apply_fn(perturbed, us)
+    loss = 0.5 * ((scores.reshape(B, -1) - target.reshape(B, -1)) ** 2).sum(dim=-1) * us.reshape(B) ** 2
+    return reduce_fn(loss, reduction), scores
+
+
+def dsm_draws(rng_key, batch_shape, sigmas, continuous_noise=False):
+    """losses.py:146-164 via the jax-0.2.8 threefry restatement.  Returns labels, used_sigmas (B,), eps (unit normal;
+    the reference multiplies it by sigma at :163)."""
+    from . import threefry as tf
+    sig = np.asarray(sigmas, np.float32)
+    rng, label_rng, sample_rng = tf.split(rng_key, 3)
+    B = batch_shape[0]
+    labels = tf.randint(label_rng, (B,), int(continuous_noise), len(sig))
+    if continuous_noise:
+        rng, noise_rng = tf.split(rng, 2)
+        used = uniform_minmax(tf.uniform01(noise_rng, (B,)), sig[labels - 1], sig[labels])
+    else:
+        used = sig[labels]
+    eps = tf.normal(sample_rng, tuple(batch_shape))
+    return labels, used.astype(np.float32), eps
+
+
+# ----------------------------------------------------------------------------
+# utils/ebm_utils.py:89-198, 201-271  annealed / consistent Langevin dynamics
+# ----------------------------------------------------------------------------
+def _axis1_norm(a: Tensor) -> Tensor:   # ebm_utils.py:166-170: sqrt(sum(a^2, axis=1) + 1e-10).mean()
+    return torch.sqrt((a * a).sum(dim=1) + 1e-10).mean()
+
+
+def annealed_langevin_dynamics(apply_fn, sigmas, init: Tensor, epsilon, T: int, denoise: bool, noise_fn,
+                               infill=False, infill_samples=None, infill_masks=None):
+    """ebm_utils.py:89-198.  noise_fn(sigma_index, step) -> (z, z_infill).  Returns state, collection
+    (101 + denoise, ...), metrics (4, L, T)."""
+    sig = np.asarray(sigmas, np.float32)
+    L = len(sig)
+    dt = init.dtype
+    if not infill:
+        infill_samples, infill_masks = torch.zeros_like(init), torch.zeros_like(init)
+    idx_tab = np.linspace(1, L * T, 100).astype(np.int32)
+    collection = torch.zeros((101 + int(bool(denoise)),) + tuple(init.shape), dtype=dt)
+    collection[0] = init * (1 - infill_masks) + infill_samples * infill_masks
+    mets = torch.zeros((4, L, T), dtype=dt)
+    state = init
+    for si in range(L):
+        sigma = torch.tensor(sig[si], dtype=dt)
+        alpha = torch.tensor(np.float32(epsilon) * (sig[si] / sig[-1]) ** 2, dtype=dt)
+        for i in range(T):
+            z, zi = noise_fn(si, i)
+            y = infill_samples + sigma * (zi if zi is not None else torch.zeros_like(init))
+            grad = apply_fn(state, sigma * torch.ones((state.shape[0],) + (1,) * (state.dim() - 1), dtype=dt))
+            noise = torch.sqrt(2 * alpha) * z
+            nxt = state + alpha * grad + noise
+            nxt = nxt * (1 - infill_masks) + y * infill_masks
+            image_idx = si * T + i + 1
+            mask = idx_tab == image_idx
+            if mask.any():
+                collection[int(np.sum(np.arange(len(idx_tab)) * mask) + 1)] = nxt
+            mets[0, si, i] = _axis1_norm(grad); mets[1, si, i] = _axis1_norm(alpha * grad)
+            mets[2, si, i] = alpha; mets[3, si, i] = _axis1_norm(noise)
+            state = nxt
+    if denoise:
+        s_last = torch.tensor(sig[-1], dtype=dt)
+        state = state + s_last ** 2 * apply_fn(state, s_last * torch.ones((state.shape[0],) + (1,) * (state.dim() - 1), dtype=dt))
+        collection[-1] = state
+    return state, collection, mets
+
+
+def consistent_langevin_dynamics(apply_fn, sigmas, init: Tensor, epsilon, denoise: bool, noise_fn):
+    """ebm_utils.py:201-271.  noise_fn(i) -> z.  Returns state, metrics (4, L, 1)."""
+    sig = np.asarray(sigmas, np.float32)
+    L = len(sig)
+    dt = init.dtype
+    beta = torch.tensor(np.sqrt(np.float32(1) - (np.float32(1) - np.float32(epsilon) / sig[-1] ** 2) ** 2), dtype=dt)
+    mets = torch.zeros((4, L, 1), dtype=dt)
+    state = init
+    ones = lambda: torch.ones((state.shape[0],) + (1,) * (state.dim() - 1), dtype=dt)
+    for i in range(L):
+        sigma = torch.tensor(sig[i], dtype=dt)
+        nxt_sigma = torch.tensor(sig[i + 1] if i < L - 1 else 0.0, dtype=dt)
+        alpha = torch.tensor(np.float32(epsilon) * (sig[i] / sig[-1]) ** 2, dtype=dt)
+        grad = apply_fn(state, sigma * ones())
+        noise = beta * nxt_sigma * noise_fn(i)
+        mets[0, i, 0] = _axis1_norm(grad); mets[1, i, 0] = _axis1_norm(alpha * grad)
+        mets[2, i, 0] = alpha; mets[3, i, 0] = _axis1_norm(noise)
+        state = state + alpha * grad + noise
+    if denoise:
+        s_last = torch.tensor(sig[-1], dtype=dt)
+        state = state + s_last ** 2 * apply_fn(state, s_last * ones())
+    return state, mets
 
 
 # ----------------------------------------------------------------------------

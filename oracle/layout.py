@@ -32,7 +32,7 @@ def param_shapes(arch: str = "TransformerDDPM", num_layers: int = 6, num_heads: 
         add("post_ln.scale", E); add("post_ln.bias", E)                 # models/ncsn.py:170-171
         add("post.kernel", E, M); add("post.bias", M)
         K = num_mlp_layers
-    elif arch == "DenseDDPM":
+    elif arch in ("DenseDDPM", "DenseNCSN"):                            # (DenseNCSN: models/ncsn.py:83-98, same tree)
         add("in.kernel", C, M); add("in.bias", M)                       # models/ncsn.py:129
         K = num_layers
     else:
@@ -85,7 +85,7 @@ def flops_fwd_per_sample(arch: str = "TransformerDDPM", num_layers: int = 6, num
                          mlp_dims: int = 2048, channels: int = 42, seq_len: int = 32, **_ignored) -> float:
     """Algorithmic forward FLOPs per sample."""
     S, C, M = seq_len, channels, mlp_dims
-    if arch == "DenseDDPM":
+    if arch in ("DenseDDPM", "DenseNCSN"):
         K = num_layers
         mac_tok, S = C * M + K * 2 * M * M + M * C, 1
     else:

@@ -97,7 +97,7 @@ using namespace smd;
 // outside the graph can wait on them after the graph has been launched.
 static int grads_impl(smd_plan* p, const float* params, const float* x0, const float* used_alpha, const float* eps,
                       const float* const* ind, int batch, int global_batch, float* grads, float* loss_sum,
-                      cudaStream_t st, bool capturing) {
+                      cudaStream_t st, bool capturing, int objective) {
   const unsigned ext = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
   TrainState& ts = p->train;
   uint8_t* ws = p->ws;
@@ -160,18 +160,20 @@ static int grads_impl(smd_plan* p, const float* params, const float* x0, const f
   // ---------------- forward (keeps every activation) ----------------
   float* cond = p->buf<float>("tvec");
   float* pred = p->buf<float>("eps_hat");
-  launch_q_sample(x0, eps, used_alpha, xt, cond, batch, per, st, ind); CNT();
-  int rc = run_forward(p, params, xt, cond, 0, batch, pred, st, &ts);
+  launch_q_sample(x0, eps, used_alpha, xt, cond, batch, per, st, ind, objective); CNT();
+  int rc = run_forward(p, params, xt, cond, 0, batch, pred, st, &ts, /*raw_out=*/true);
   if (rc) return rc;
   SMD_CUDA(cudaStreamWaitEvent(st, p->ev_gz, 0));   // gradient arena zeroed (long done by now)
 
   // ---------------- objective ----------------
-  const float gscale = 1.0f / (static_cast<float>(global_batch) * static_cast<float>(per));
+  // ddpm: mean over (S, C) and the global batch; dsm: sum over (S, C) (x 0.5), mean over the global batch
+  const float gscale = objective == 1 ? 1.0f / static_cast<float>(global_batch)
+                                      : 1.0f / (static_cast<float>(global_batch) * static_cast<float>(per));
   float* dpred32 = F32(ts.off_dpred32);
   __nv_bfloat16* dpred16 = B16(ts.off_dpred16);
   ddpm_loss_bwd_kernel<<<batch, 256, 0, st>>>(eps, pred, F32(ts.off_loss), loss_sum, ts.at<unsigned int>(ws, ts.off_loss_ctr),
                                               1.0f / static_cast<float>(global_batch), dpred32, dpred16, gscale, S, C, Cp,
-                                              ind);
+                                              ind, objective);
   CNT();
   SMD_CUDA(fork_dw());
   launch_colsum<float>(dpred32, C, G("out.bias"), M, C, dws); CNT();
@@ -391,37 +393,38 @@ static void drop_train_graph(smd_plan* p) {
   p->tg_valid = false;
 }
 
-extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0, const float* used_alpha,
-                              const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
-                              smd_stream_t stream) {
+static int grads_entry(smd_plan* p, const float* params, const float* x0, const float* used_alpha,
+                       const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
+                       smd_stream_t stream, int objective) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!p->cfg.training) { set_error("plan was not created with training = 1"); return SMD_ERR_STATE; }
   if (!p->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
   if (batch < 1 || batch > p->cfg.max_batch || global_batch < batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
   const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
   if (!train_graph_enabled() || !capturable)
-    return grads_impl(p, params, x0, used_alpha, eps, nullptr, batch, global_batch, grads, loss_sum, st, false);
+    return grads_impl(p, params, x0, used_alpha, eps, nullptr, batch, global_batch, grads, loss_sum, st, false, objective);
   // Graph replay: the pass's ~150 launches on three streams (dX chain, weight-gradient GEMMs, FiLM generator) are
   // captured once into one CUDA graph with the same fork / join structure.  The per-step inputs (x0, used_alpha, eps)
   // reach the kernels through a 3-pointer device table, so new input tensors do not force a re-capture; the events a
   // data-parallel caller waits on (smd_wait_tail_grads) are external event-record nodes of the graph.
   const bool same = p->tg_valid && p->tg_params == params && p->tg_grads == grads && p->tg_loss == loss_sum &&
-                    p->tg_batch == batch && p->tg_global == global_batch;
+                    p->tg_batch == batch && p->tg_global == global_batch && p->tg_objective == objective;
   const float** ind = p->buf<const float*>("t.ind");
   if (!same) {
-    const bool warm = p->tg_warm && p->tg_params == params && p->tg_batch == batch;
+    const bool warm = p->tg_warm && p->tg_params == params && p->tg_batch == batch && p->tg_objective == objective;
     drop_train_graph(p);
     p->tg_params = params; p->tg_grads = grads; p->tg_loss = loss_sum; p->tg_batch = batch; p->tg_global = global_batch;
+    p->tg_objective = objective;
     if (!warm) {
       // first use of this configuration runs eagerly: lazy one-time calls (function attributes, stream / event
       // creation) stay out of the capture
       p->tg_warm = true;
-      return grads_impl(p, params, x0, used_alpha, eps, nullptr, batch, global_batch, grads, loss_sum, st, false);
+      return grads_impl(p, params, x0, used_alpha, eps, nullptr, batch, global_batch, grads, loss_sum, st, false, objective);
     }
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
     SMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = grads_impl(p, params, nullptr, nullptr, nullptr, ind, batch, global_batch, grads, loss_sum, st, true);
+    int rc = grads_impl(p, params, nullptr, nullptr, nullptr, ind, batch, global_batch, grads, loss_sum, st, true, objective);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     p->tg_nodes = g_launches.load() - before;
     g_launches.store(before);   // captured launches are counted per replay
@@ -438,4 +441,19 @@ extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0,
   SMD_CUDA(cudaGraphLaunch(p->tg_exec, st));
   g_launches.fetch_add(p->tg_nodes, std::memory_order_relaxed);
   return SMD_OK;
+}
+
+extern "C" int smd_ddpm_grads(smd_plan* p, const float* params, const float* x0, const float* used_alpha,
+                              const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
+                              smd_stream_t stream) {
+  return grads_entry(p, params, x0, used_alpha, eps, batch, global_batch, grads, loss_sum, stream, 0);
+}
+
+// denoising score matching (utils/losses.py:129-179): the same pass with x~ = x0 + sigma eps, the network conditioned on
+// sigma and the 0.5 (net + eps)^2 objective (for a network whose output is divided by sigma -- SMD_ARCH_DENSE_NCSN)
+extern "C" int smd_dsm_grads(smd_plan* p, const float* params, const float* x0, const float* used_sigma,
+                             const float* eps, int batch, int global_batch, float* grads, float* loss_sum,
+                             smd_stream_t stream) {
+  if (p->cfg.arch != SMD_ARCH_DENSE_NCSN) { set_error("smd_dsm_grads needs a score network (SMD_ARCH_DENSE_NCSN)"); return SMD_ERR_INVALID; }
+  return grads_entry(p, params, x0, used_sigma, eps, batch, global_batch, grads, loss_sum, stream, 1);
 }

@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__(256)
 ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
                      float* __restrict__ loss_sum, unsigned int* __restrict__ done_counter, float inv_global_batch,
                      float* __restrict__ dpred32, __nv_bfloat16* __restrict__ dpred16, float gscale, int S, int C, int Cp,
-                     const float* const* __restrict__ ind) {
+                     const float* const* __restrict__ ind, int objective) {
   pdl_trigger();
   if (ind) eps = ind[2];
   const int b = blockIdx.x;
@@ -1032,9 +1032,11 @@ ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pr
   const size_t base = static_cast<size_t>(b) * per;
   float s = 0.f;
   for (int i = threadIdx.x; i < per; i += blockDim.x) {
-    const float d = eps[base + i] - pred[base + i];
+    // ddpm (utils/losses.py:304-306): (eps - pred)^2, d/dpred = -2 (eps - pred).  dsm (:166-177) with pred = the RAW network
+    // output (score * sigma): 0.5 (pred + eps)^2 summed, d/dpred = pred + eps.
+    const float d = objective == 1 ? pred[base + i] + eps[base + i] : eps[base + i] - pred[base + i];
     s += d * d;
-    const float gval = -2.0f * d * gscale;
+    const float gval = (objective == 1 ? d : -2.0f * d) * gscale;
     dpred32[base + i] = gval;
     const int row = i / C, c = i % C;
     dpred16[(static_cast<size_t>(b) * S + row) * Cp + c] = __float2bfloat16_rn(gval);
@@ -1047,7 +1049,7 @@ ddpm_loss_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ pr
   if (threadIdx.x == 0) {
     float v = 0.f;
     for (int j = 0; j < 8; ++j) v += red[j];
-    v /= static_cast<float>(per);
+    v = objective == 1 ? 0.5f * v : v / static_cast<float>(per);
     loss[b] = v;
     last = false;
     if (loss_sum) {

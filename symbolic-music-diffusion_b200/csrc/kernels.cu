@@ -11,10 +11,22 @@ namespace smd {
 // the train step reads its per-step inputs through it, so new input tensors do not force a re-capture
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ eps,
                                 const float* __restrict__ ua, float* __restrict__ xt, float* __restrict__ cond, int B,
-                                int per_sample, const float* const* __restrict__ ind) {
+                                int per_sample, const float* const* __restrict__ ind, int mode) {
   pdl_trigger();
   pdl_wait();
   if (ind) { x0 = ind[0]; ua = ind[1]; eps = ind[2]; }
+  if (mode == 1) {
+    // denoising score matching (utils/losses.py:163-165): x~ = x + sigma * eps, conditioned on sigma itself
+    const size_t total1 = static_cast<size_t>(B) * per_sample;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total1;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const int b = static_cast<int>(i / per_sample);
+      const float sg = ua[b];
+      xt[i] = __fadd_rn(x0[i], __fmul_rn(sg, eps[i]));
+      if (i % per_sample == 0) cond[b] = sg;
+    }
+    return;
+  }
   const size_t total = static_cast<size_t>(B) * per_sample;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -26,11 +38,11 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
   }
 }
 void launch_q_sample(const float* x0, const float* eps, const float* used_alpha, float* xt, float* cond, int B,
-                     int per_sample, cudaStream_t st, const float* const* ind) {
+                     int per_sample, cudaStream_t st, const float* const* ind, int mode) {
   const size_t total = static_cast<size_t>(B) * per_sample;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl_g(kPdlMisc, q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample, ind);
+  launch_pdl_g(kPdlMisc, q_sample_kernel, dim3(blocks), dim3(256), 0, st, x0, eps, used_alpha, xt, cond, B, per_sample, ind, mode);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -779,12 +791,21 @@ void launch_fill_cond(const float* coef, const int* t_ptr, float* cond, int n, c
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ddpm_loss_kernel(const float* __restrict__ eps, const float* __restrict__ pred, float* __restrict__ loss,
-                 float* __restrict__ dpred, float gscale, int per_sample) {
+                 float* __restrict__ dpred, float gscale, int per_sample, const float* __restrict__ sigma) {
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x;
   const size_t base = static_cast<size_t>(b) * per_sample;
   float s = 0.f;
+  if (sigma != nullptr) {
+    // denoising score matching (utils/losses.py:166-177): target = -eps / sigma, loss = 0.5 sum((score - target)^2) sigma^2
+    const float sg = sigma[b];
+    for (int i = threadIdx.x; i < per_sample; i += blockDim.x) {
+      const float d = __fmul_rn(__fadd_rn(pred[base + i], __fdiv_rn(eps[base + i], sg)), sg);   // (score - target) * sigma
+      s += d * d;
+    }
+    s *= 0.5f * static_cast<float>(per_sample);     // (the common tail divides by per_sample)
+  } else
   for (int i = threadIdx.x; i < per_sample; i += blockDim.x) {
     const float d = eps[base + i] - pred[base + i];
     s += d * d;
@@ -801,8 +822,74 @@ ddpm_loss_kernel(const float* __restrict__ eps, const float* __restrict__ pred, 
   }
 }
 void launch_ddpm_loss(const float* eps, const float* pred, float* loss_per_example, float* dpred_or_null,
-                      float gscale, int B, int per_sample, cudaStream_t st) {
-  launch_pdl_g(kPdlMisc, ddpm_loss_kernel, dim3(B), dim3(256), 0, st, eps, pred, loss_per_example, dpred_or_null, gscale, per_sample);
+                      float gscale, int B, int per_sample, cudaStream_t st, const float* sigma) {
+  launch_pdl_g(kPdlMisc, ddpm_loss_kernel, dim3(B), dim3(256), 0, st, eps, pred, loss_per_example, dpred_or_null, gscale,
+               per_sample, sigma);
+}
+
+// y[b, :] /= sigma[b]   (DenseNCSN: `output = x / sigmas`, models/ncsn.py:97)
+__global__ void scale_rows_kernel(float* __restrict__ y, const float* __restrict__ sigma, int bcast, int B, int per) {
+  const size_t total = static_cast<size_t>(B) * per;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = __fdiv_rn(y[i], sigma[bcast ? 0 : i / per]);
+}
+void launch_scale_rows(float* y, const float* sigma, int bcast, int B, int per, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * per;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scale_rows_kernel<<<blocks, 256, 0, st>>>(y, sigma, bcast, B, per);
+}
+
+// One Langevin update after the network call (annealed: utils/ebm_utils.py:139-175; consistent: :231-253):
+//   next = x + alpha * grad + noise_coef * z ;  infill blend with y = infill_x + infill_sigma * z_infill ;
+//   metrics (mean over samples of sqrt(sum_axis1(.)^2 + 1e-10)): grad, alpha * grad, noise ; alpha itself.
+// thread = (sample n, channel c) looping over the S positions (axis 1), like the DDPM step kernel.
+__global__ void __launch_bounds__(256) langevin_step_kernel(const LangevinStepArgs a) {
+  const int NC = a.N * a.C;
+  const uint32_t total = static_cast<uint32_t>(a.N) * a.S * a.C;
+  float m_g = 0.f, m_s = 0.f, m_n = 0.f;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < NC) {
+    const int n = i / a.C, c = i % a.C;
+    float g2 = 0.f, s2 = 0.f, n2 = 0.f;
+    for (int s = 0; s < a.S; ++s) {
+      const uint32_t idx = (static_cast<uint32_t>(n) * a.S + s) * a.C + c;
+      const float x = a.x[idx], g = a.grad[idx];
+      const float z = a.z ? a.z[idx] : jax_normal_from_bits(jax_random_bits(a.key0, a.key1, idx, total));
+      const float noise = __fmul_rn(a.noise_coef, z);
+      const float stp = __fmul_rn(a.alpha, g);
+      float nx = __fadd_rn(__fadd_rn(x, stp), noise);
+      if (a.infill_mask) {
+        const float iz = a.infill_z ? a.infill_z[idx] : jax_normal_from_bits(jax_random_bits(a.ikey0, a.ikey1, idx, total));
+        const float y = __fadd_rn(a.infill_x[idx], __fmul_rn(a.infill_sigma, iz));
+        const float mk = a.infill_mask[idx];
+        nx = nx * (1.0f - mk) + y * mk;
+      }
+      g2 += g * g; s2 += stp * stp; n2 += noise * noise;
+      a.x_next[idx] = nx;
+      if (a.collection_slot) a.collection_slot[idx] = nx;
+    }
+    m_g = sqrtf(g2 + 1e-10f); m_s = sqrtf(s2 + 1e-10f); m_n = sqrtf(n2 + 1e-10f);
+  }
+  if (a.metrics) {
+    __shared__ float red[3][8];
+    m_g = warp_sum(m_g); m_s = warp_sum(m_s); m_n = warp_sum(m_n);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = m_g; red[1][w] = m_s; red[2][w] = m_n; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float v = 0.f;
+      for (int j = 0; j < (blockDim.x >> 5); ++j) v += red[threadIdx.x][j];
+      const int rowi = (threadIdx.x == 0) ? 0 : (threadIdx.x == 1 ? 1 : 3);   // grad_norm, step_norm, (alpha), noise_norm
+      atomicAdd(a.metrics + rowi, v / static_cast<float>(NC));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 3) a.metrics[2] = a.alpha;
+  }
+}
+void launch_langevin_step(const LangevinStepArgs& a, cudaStream_t st) {
+  const int NC = a.N * a.C;
+  langevin_step_kernel<<<(NC + 255) / 256, 256, 0, st>>>(a);
 }
 
 }  // namespace smd

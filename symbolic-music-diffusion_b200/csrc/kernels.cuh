@@ -143,7 +143,8 @@ __device__ __forceinline__ float jax_normal_from_bits(uint32_t bits) {
 // ---------------------------------------------------------------------------------------------------
 // x_t = sqrt(ua[b]) * x0 + sqrt(1 - ua[b]) * eps ; cond[b] = sqrt(ua[b])        (utils/losses.py:295-300)
 void launch_q_sample(const float* x0, const float* eps, const float* used_alpha, float* xt, float* cond, int B,
-                     int per_sample, cudaStream_t st, const float* const* ind = nullptr);
+                     int per_sample, cudaStream_t st, const float* const* ind = nullptr, int mode = 0);
+// mode 1 (denoising score matching, utils/losses.py:163-165): xt = x0 + sigma[b] * eps ; cond[b] = sigma[b]
 
 // h[m,:] = x[m,:] @ W_in + b_in + posenc[m % S,:]; a[m,:] = bf16(LN(h[m,:]; g, b))   (models/ncsn.py:155-160)
 void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
@@ -215,6 +216,19 @@ void launch_fill_cond(const float* coef, const int* t_ptr, float* cond, int n, c
 
 // loss[b] = mean_{s,c} (eps - pred)^2 ; dpred = -2 (eps - pred) * gscale                (utils/losses.py:304-308)
 void launch_ddpm_loss(const float* eps, const float* pred, float* loss_per_example, float* dpred_or_null,
-                      float gscale, int B, int per_sample, cudaStream_t st);
+                      float gscale, int B, int per_sample, cudaStream_t st, const float* dsm_sigma = nullptr);
+// dsm_sigma != null: denoising score matching, loss[b] = 0.5 sum((pred + eps / sigma)^2) sigma^2 with pred = score
+
+void launch_scale_rows(float* y, const float* sigma, int bcast, int B, int per, cudaStream_t st);
+
+struct LangevinStepArgs {
+  const float* x; const float* grad; const float* z;   // z: supplied N(0,1) or null -> threefry(key)
+  uint32_t key0, key1, ikey0, ikey1;
+  float alpha, noise_coef, infill_sigma;
+  const float* infill_x; const float* infill_mask; const float* infill_z;
+  float* x_next; float* collection_slot; float* metrics;   // metrics: 4 floats (accumulated; zero them first)
+  int N, S, C;
+};
+void launch_langevin_step(const LangevinStepArgs& a, cudaStream_t st);
 
 }  // namespace smd

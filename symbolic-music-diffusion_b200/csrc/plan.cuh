@@ -80,6 +80,7 @@ struct smd_plan {
   // sampler
   int T = 0;
   int T_obj = 0;  // schedule length of the training objective
+  int L_dsm = 0;  // length of the sigma schedule of the denoising-score-matching objective (smd_dsm_setup)
   // FiLM table of the sampler: [K][T][2*Md]; when film_tab_on, run_forward skips the generator and the tail reads
   // row film_row (host) or *film_row_dev (graph replay) of the table
   bool film_tab_ready = false, film_tab_on = false;
@@ -113,7 +114,7 @@ struct smd_plan {
   const float* tg_params = nullptr;
   float* tg_grads = nullptr;
   float* tg_loss = nullptr;
-  int tg_batch = 0, tg_global = 0;
+  int tg_batch = 0, tg_global = 0, tg_objective = 0;
 
   template <typename Tp>
   Tp* buf(const std::string& n) const { return reinterpret_cast<Tp*>(ws + ws_off.at(n)); }
@@ -127,8 +128,9 @@ inline GemmEpilogue epi() {
   memset(&e, 0, sizeof(e));
   return e;
 }
+// raw_out: DenseNCSN only -- leave out the final division by sigma (the training path differentiates through it itself)
 int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
-                float* y, cudaStream_t st, TrainState* save);
+                float* y, cudaStream_t st, TrainState* save, bool raw_out = false);
 int train_bind(smd_plan* p);
 int ensure_side_stream(smd_plan* p);
 void add_pack_job_ptr(smd_plan* p, const std::string& src, void* dst, int K, int N, int mode, int ld);

@@ -138,6 +138,7 @@ static void build_workspace(smd_plan* p) {
   ws_add(p, "slots", kMaxT * 4);
   ws_add(p, "t_ptr", 64);
   ws_add(p, "abar", (kMaxT + 1) * 4);
+  ws_add(p, "sigmas", kMaxT * 4);
   ws_add(p, "packjobs", 256 * sizeof(PackJob));
   ws_add(p, "packmap", 65536 * 8);
   if (c.sampler_T > 0) {
@@ -459,7 +460,7 @@ static int run_tail(smd_plan* p, const float* params, int M, int S, int t_broadc
 }
 
 int run_forward(smd_plan* p, const float* params, const float* x, const float* t, int t_broadcast, int batch,
-                float* y, cudaStream_t st, smd::TrainState* save) {
+                float* y, cudaStream_t st, smd::TrainState* save, bool raw_out) {
   const smd_config& c = p->cfg;
   if (!p->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
   if (!p->packed) { set_error("smd_pack_weights has not been called"); return SMD_ERR_STATE; }
@@ -585,7 +586,13 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
   }
   SMD_LAUNCH_CHECK("trunk");
   if (film_on_side) SMD_CUDA(cudaStreamWaitEvent(st, p->ev_film, 0));
-  return run_tail(p, params, M, S, t_broadcast, y, st, save, fuse_tail, fuse_post);
+  rc = run_tail(p, params, M, S, t_broadcast, y, st, save, fuse_tail, fuse_post);
+  if (rc) return rc;
+  if (c.arch == SMD_ARCH_DENSE_NCSN && !raw_out) {   // models/ncsn.py:97: output = x / sigmas
+    launch_scale_rows(y, t, t_broadcast, batch, S * C, st); CNT();
+    SMD_LAUNCH_CHECK("ncsn output scale");
+  }
+  return SMD_OK;
 }
 
 // host threefry (same block function as the device one)
@@ -615,9 +622,11 @@ static void h_split(const uint32_t key[2], int num, uint32_t* out) {
 // lo = abar[l-1], hi = abar[l]   (utils/losses.py:272-286; minlabel = int(continuous_noise), and for label 0 the
 // index -1 wraps to the last entry exactly as jnp indexing does).  Rows [first, first + n) of a GLOBAL batch of B
 // examples: threefry is counter based, so a data-parallel rank generates exactly its slice of the global stream.
-__global__ void ddpm_draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint32_t nk1, const float* __restrict__ abar,
-                                  int T, int B, int first, int n, int minlabel, float* __restrict__ used,
-                                  int* __restrict__ labels) {
+// (shared with denoising score matching, utils/losses.py:146-160: table = sigmas, span = L - int(continuous), and the
+// uniform draw only when continuous -- otherwise used = table[label])
+__global__ void draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint32_t nk1, const float* __restrict__ abar,
+                             int wrap_index, int span_i, int B, int first, int n, int minlabel, int continuous,
+                             float* __restrict__ used, int* __restrict__ labels) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int i = first + j;
@@ -628,13 +637,14 @@ __global__ void ddpm_draws_kernel(uint32_t lk0, uint32_t lk1, uint32_t nk0, uint
   const uint32_t k1_0 = a0, k1_1 = a1, k2_0 = b0, k2_1 = b1;
   const uint32_t hi = jax_random_bits(k1_0, k1_1, i, B);
   const uint32_t lo = jax_random_bits(k2_0, k2_1, i, B);
-  const uint32_t span = static_cast<uint32_t>(T);
+  const uint32_t span = static_cast<uint32_t>(span_i);
   uint32_t mult = 65536u % span;
   mult = static_cast<uint32_t>((static_cast<uint64_t>(mult) * mult) % span);
   const uint32_t off = static_cast<uint32_t>((static_cast<uint64_t>(hi % span) * mult + (lo % span)) % span);
   const int label = minlabel + static_cast<int>(off);
   if (labels) labels[j] = label;
-  const float minv = abar[label > 0 ? label - 1 : T], maxv = abar[label];
+  if (!continuous) { used[j] = abar[label]; return; }
+  const float minv = abar[label > 0 ? label - 1 : wrap_index], maxv = abar[label];
   const uint32_t bits = jax_random_bits(nk0, nk1, i, B);
   const float u01 = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
   used[j] = fmaxf(minv, __fadd_rn(__fmul_rn(u01, __fsub_rn(maxv, minv)), minv));
@@ -697,7 +707,7 @@ long long smd_launch_count(void) { return g_launches.load(); }
 int smd_plan_create(const smd_config* cfg, smd_plan** out) {
   if (!cfg || !out) { set_error("null argument"); return SMD_ERR_INVALID; }
   smd_config c = *cfg;
-  if (c.arch != SMD_ARCH_TRANSFORMER_DDPM && c.arch != SMD_ARCH_DENSE_DDPM) { set_error("unknown arch"); return SMD_ERR_INVALID; }
+  if (c.arch != SMD_ARCH_TRANSFORMER_DDPM && c.arch != SMD_ARCH_DENSE_DDPM && c.arch != SMD_ARCH_DENSE_NCSN) { set_error("unknown arch"); return SMD_ERR_INVALID; }
   if (c.cta_group == 0) c.cta_group = 1;
   if (c.cta_group != 1 && c.cta_group != 2) { set_error("cta_group must be 1 or 2"); return SMD_ERR_INVALID; }
   if (c.mlp_dims < 256 || c.mlp_dims % 256 != 0 || c.mlp_dims > 4096) { set_error("mlp_dims must be a multiple of 256 in [256, 4096]"); return SMD_ERR_INVALID; }
@@ -847,6 +857,79 @@ int smd_ddpm_loss(smd_plan* plan, const float* params, const float* x0, const fl
   return SMD_OK;
 }
 
+int smd_dsm_loss(smd_plan* plan, const float* params, const float* x0, const float* used_sigma, const float* eps,
+                 int batch, float* loss_per_example, float* pred_or_null, smd_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan->cfg.arch != SMD_ARCH_DENSE_NCSN) { set_error("smd_dsm_loss needs a score network (SMD_ARCH_DENSE_NCSN)"); return SMD_ERR_INVALID; }
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (batch < 1 || batch > plan->cfg.max_batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  const int per = plan->cfg.seq_len * plan->cfg.channels;
+  float* xt = plan->buf<float>("xt");
+  float* cond = plan->buf<float>("tvec");
+  float* pred = pred_or_null ? pred_or_null : plan->buf<float>("eps_hat");
+  launch_q_sample(x0, eps, used_sigma, xt, cond, batch, per, st, nullptr, 1); CNT();
+  int rc = run_forward(plan, params, xt, cond, 0, batch, pred, st, nullptr);
+  if (rc) return rc;
+  launch_ddpm_loss(eps, pred, loss_per_example, nullptr, 0.f, batch, per, st, used_sigma); CNT();
+  SMD_LAUNCH_CHECK("dsm_loss");
+  return SMD_OK;
+}
+
+int smd_dsm_setup(smd_plan* plan, const float* host_sigmas, int L, smd_stream_t stream) {
+  if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
+  if (L < 2 || L > kMaxT) { set_error("schedule length out of range"); return SMD_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SMD_CUDA(cudaMemcpyAsync(plan->buf<float>("sigmas"), host_sigmas, static_cast<size_t>(L) * 4, cudaMemcpyHostToDevice, st));
+  SMD_CUDA(cudaStreamSynchronize(st));
+  plan->L_dsm = L;
+  return SMD_OK;
+}
+
+int smd_dsm_draws(smd_plan* plan, const uint32_t host_key[2], int global_batch, int first_row, int batch,
+                  int continuous_noise, float* used_sigma, float* eps, int* labels_or_null, smd_stream_t stream) {
+  if (plan->L_dsm <= 0) { set_error("smd_dsm_setup has not been called"); return SMD_ERR_STATE; }
+  if (batch < 1 || first_row < 0 || global_batch < first_row + batch) { set_error("batch out of range"); return SMD_ERR_INVALID; }
+  const long long per = static_cast<long long>(plan->cfg.seq_len) * plan->cfg.channels;
+  if (static_cast<long long>(global_batch) * per > 0xFFFFFFFFll) { set_error("global batch too large"); return SMD_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = plan->L_dsm, cn = continuous_noise ? 1 : 0;
+  uint32_t k3[6], k2[4] = {0, 0, 0, 0};
+  h_split(host_key, 3, k3);               // rng, label_rng, sample_rng          (utils/losses.py:146)
+  if (cn) { const uint32_t rng[2] = {k3[0], k3[1]}; h_split(rng, 2, k2); }        // rng, noise_rng (:152-153)
+  // labels = randint(label_rng, minval = int(continuous), maxval = L): span L - cn; table index label - 1 wraps for 0
+  draws_kernel<<<(batch + 127) / 128, 128, 0, st>>>(k3[2], k3[3], k2[2], k2[3], plan->buf<float>("sigmas"), L - 1, L - cn,
+                                                    global_batch, first_row, batch, cn, cn, used_sigma, labels_or_null);
+  CNT();
+  const long long n = static_cast<long long>(batch) * per;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  threefry_normal_kernel<<<blocks, 256, 0, st>>>(k3[4], k3[5], eps, static_cast<uint32_t>(n),
+                                                 static_cast<uint32_t>(first_row * per),
+                                                 static_cast<uint32_t>(global_batch * per));
+  CNT();
+  SMD_LAUNCH_CHECK("dsm_draws");
+  return SMD_OK;
+}
+
+int smd_langevin_step(smd_plan* plan, const float* x, const float* grad, int n, float alpha, float noise_coef,
+                      const uint32_t step_key[2], const float* z, const float* infill_x, const float* infill_mask,
+                      float infill_sigma, const uint32_t infill_key[2], const float* infill_z, float* x_next,
+                      float* collection_slot, float* metrics4, smd_stream_t stream) {
+  if (!plan || n < 1) { set_error("bad arguments"); return SMD_ERR_INVALID; }
+  LangevinStepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.grad = grad; a.z = z;
+  if (step_key) { a.key0 = step_key[0]; a.key1 = step_key[1]; }
+  if (infill_key) { a.ikey0 = infill_key[0]; a.ikey1 = infill_key[1]; }
+  a.alpha = alpha; a.noise_coef = noise_coef; a.infill_sigma = infill_sigma;
+  a.infill_x = infill_x; a.infill_mask = infill_mask; a.infill_z = infill_z;
+  a.x_next = x_next; a.collection_slot = collection_slot; a.metrics = metrics4;
+  a.N = n; a.S = plan->cfg.seq_len; a.C = plan->cfg.channels;
+  launch_langevin_step(a, static_cast<cudaStream_t>(stream)); CNT();
+  SMD_LAUNCH_CHECK("langevin_step");
+  return SMD_OK;
+}
+
 int smd_objective_setup(smd_plan* plan, const float* host_betas, int T, smd_stream_t stream) {
   if (!plan->ws) { set_error("workspace not bound"); return SMD_ERR_STATE; }
   if (T < 1 || T > kMaxT) { set_error("T out of range"); return SMD_ERR_INVALID; }
@@ -873,9 +956,10 @@ int smd_ddpm_draws_sharded(smd_plan* plan, const uint32_t host_key[2], int globa
   h_split(host_key, 3, k3);               // rng, label_rng, sample_rng
   const uint32_t rng[2] = {k3[0], k3[1]};
   h_split(rng, 2, k2);                    // rng, noise_rng
-  ddpm_draws_kernel<<<(batch + 127) / 128, 128, 0, st>>>(k3[2], k3[3], k2[2], k2[3], plan->buf<float>("abar"),
-                                                         plan->T_obj, global_batch, first_row, batch,
-                                                         continuous_noise ? 1 : 0, used_alpha, labels_or_null);
+  // ddpm: labels = randint(int(continuous), T + int(continuous)) -> span T; alphas_prod has T + 1 entries (leading 1)
+  draws_kernel<<<(batch + 127) / 128, 128, 0, st>>>(k3[2], k3[3], k2[2], k2[3], plan->buf<float>("abar"), plan->T_obj,
+                                                    plan->T_obj, global_batch, first_row, batch, continuous_noise ? 1 : 0, 1,
+                                                    used_alpha, labels_or_null);
   CNT();
   const long long n = static_cast<long long>(batch) * per;
   int blocks = static_cast<int>((n + 255) / 256);

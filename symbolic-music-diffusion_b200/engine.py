@@ -15,7 +15,7 @@ import torch
 
 from . import lib as _lib
 
-ARCHS = {"TransformerDDPM": 0, "TransformerDDPM4": 0, "DenseDDPM": 1}
+ARCHS = {"TransformerDDPM": 0, "TransformerDDPM4": 0, "DenseDDPM": 1, "DenseNCSN": 2}
 PRECISIONS = {"bf16": 0, "bf16x3": 1}
 
 
@@ -232,6 +232,54 @@ class Engine:
                                                    1 if continuous_noise else 0, used.data_ptr(), eps.data_ptr(),
                                                    _ptr(labels), self._stream()))
         return (used, eps, labels) if want_labels else (used, eps)
+
+    # ------------------------------------------------------------------ NCSN family
+    def dsm_setup(self, sigmas: np.ndarray) -> None:
+        self._ensure_ws()
+        s = np.ascontiguousarray(sigmas, np.float32)
+        _lib.check(self.lib.smd_dsm_setup(self._plan, s.ctypes.data_as(C.POINTER(C.c_float)), len(s), self._stream()))
+
+    def dsm_draws(self, key, batch: int, want_labels: bool = False, global_batch: Optional[int] = None,
+                  first_row: int = 0, continuous_noise: bool = False):
+        """(used_sigma (B,), eps[, labels]) of denoising_score_matching_loss (utils/losses.py:146-164) on device."""
+        dev = self._ws.device
+        shape = (batch, self.seq_len, self.cfg.channels) if ARCHS[self.cfg.arch] == 0 else (batch, self.cfg.channels)
+        used = torch.empty((batch,), dtype=torch.float32, device=dev)
+        eps = torch.empty(shape, dtype=torch.float32, device=dev)
+        labels = torch.empty((batch,), dtype=torch.int32, device=dev) if want_labels else None
+        k = (C.c_uint32 * 2)(int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF)
+        _lib.check(self.lib.smd_dsm_draws(self._plan, k, int(global_batch or batch), int(first_row), batch,
+                                          1 if continuous_noise else 0, used.data_ptr(), eps.data_ptr(), _ptr(labels),
+                                          self._stream()))
+        return (used, eps, labels) if want_labels else (used, eps)
+
+    def dsm_loss(self, x0: torch.Tensor, used_sigma: torch.Tensor, eps: torch.Tensor, want_pred: bool = False):
+        x0 = _f32c(x0, "x0"); eps = _f32c(eps, "eps"); us = _f32c(used_sigma.reshape(-1), "used_sigma")
+        batch = x0.shape[0]
+        loss = torch.empty((batch,), dtype=torch.float32, device=x0.device)
+        pred = torch.empty_like(x0) if want_pred else None
+        _lib.check(self.lib.smd_dsm_loss(self._plan, self.params.data_ptr(), x0.data_ptr(), us.data_ptr(), eps.data_ptr(),
+                                         batch, loss.data_ptr(), _ptr(pred), self._stream()))
+        return (loss, pred) if want_pred else loss
+
+    def compute_dsm_grads(self, x0, used_sigma, eps, global_batch: Optional[int] = None) -> None:
+        x0 = _f32c(x0, "x0"); eps = _f32c(eps, "eps"); us = _f32c(used_sigma.reshape(-1), "used_sigma")
+        batch = x0.shape[0]
+        _lib.check(self.lib.smd_dsm_grads(self._plan, self.params.data_ptr(), x0.data_ptr(), us.data_ptr(), eps.data_ptr(),
+                                          batch, int(global_batch or batch), self.grads.data_ptr(),
+                                          self._grads_buf[self.arena_floats:].data_ptr(), self._stream()))
+
+    def langevin_step(self, x, grad, alpha: float, noise_coef: float, step_key=None, z=None, infill_x=None,
+                      infill_mask=None, infill_sigma: float = 0.0, infill_key=None, infill_z=None, x_next=None,
+                      collection_slot=None, metrics4=None):
+        x = _f32c(x, "x"); grad = _f32c(grad, "grad")
+        x_next = torch.empty_like(x) if x_next is None else x_next
+        mk = lambda k: None if k is None else (C.c_uint32 * 2)(int(k[0]) & 0xFFFFFFFF, int(k[1]) & 0xFFFFFFFF)
+        _lib.check(self.lib.smd_langevin_step(self._plan, x.data_ptr(), grad.data_ptr(), x.shape[0], float(alpha),
+                                              float(noise_coef), mk(step_key), _ptr(z), _ptr(infill_x), _ptr(infill_mask),
+                                              float(infill_sigma), mk(infill_key), _ptr(infill_z), x_next.data_ptr(),
+                                              _ptr(collection_slot), _ptr(metrics4), self._stream()))
+        return x_next
 
     # ------------------------------------------------------------------ optimizer step (train_ncsn.py:260-288)
     def init_train_state(self, ema: bool = False) -> None:

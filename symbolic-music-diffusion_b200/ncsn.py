@@ -12,3 +12,6 @@ from .nn import ModuleSpec
 TransformerDDPM = ModuleSpec("TransformerDDPM")
 TransformerDDPM4 = ModuleSpec("TransformerDDPM4")
 DenseDDPM = ModuleSpec("DenseDDPM")
+# models/ncsn.py:83-98.  Upstream's apply() reads an undefined `t` (broken as released); here it is the
+# evident intent -- the DenseDDPM stack conditioned on `sigmas`, output divided by sigma (a score network).
+DenseNCSN = ModuleSpec("DenseNCSN")

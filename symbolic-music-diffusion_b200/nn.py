@@ -36,10 +36,10 @@ class ModuleSpec:
 
     def model_config(self, input_shape: Sequence[int]) -> ModelConfig:
         kw = self.kwargs
-        dense = ARCHS[self.arch] == 1
+        dense = ARCHS[self.arch] in (1, 2)
         if dense:
             if len(input_shape) != 1:
-                raise ValueError("DenseDDPM expects inputs of shape (batch, z_dims)")
+                raise ValueError(f"{self.arch} expects inputs of shape (batch, z_dims)")
             # models/ncsn.py:125 signature default is 3; train_ncsn.py passes FLAGS.num_layers
             return ModelConfig(arch=self.arch, num_layers=int(kw.get("num_layers", 3)),
                                mlp_dims=int(kw.get("mlp_dims", 2048)), seq_len=1, channels=int(input_shape[-1]))

@@ -16,7 +16,7 @@ import torch
 from absl import app, flags, logging
 
 from smd_b200 import checkpoints, ebm_utils, input_pipeline, jrandom as random, ncsn, nn, optim, parallel, train_utils
-from smd_b200.losses import diffusion_loss
+from smd_b200.losses import denoising_score_matching_loss, diffusion_loss
 
 FLAGS = flags.FLAGS
 _D = flags.DEFINE_integer, flags.DEFINE_float, flags.DEFINE_bool, flags.DEFINE_string, flags.DEFINE_enum
@@ -99,8 +99,12 @@ def create_model(rng, input_shape, model_kwargs, batch_size=32, verbose=False):
 def _objective():
     if FLAGS.loss == "ddpm":
         return diffusion_loss
-    if FLAGS.loss in ("dsm", "ssm"):
-        raise ValueError(f"--loss={FLAGS.loss}: the NCSN objectives are outside the B200 hot path (use --loss=ddpm)")
+    if FLAGS.loss == "dsm":
+        return denoising_score_matching_loss
+    if FLAGS.loss == "ssm":
+        # sliced score matching (utils/losses.py:182-247) differentiates through the score network's Jacobian-vector
+        # product: it needs a second-order backward pass that is not written
+        raise ValueError("--loss=ssm needs a double-backward pass that is not implemented (use dsm or ddpm)")
     raise ValueError(f"Unsupported objective {FLAGS.loss}")
 
 
@@ -129,24 +133,34 @@ def lr_at(step: int) -> float:
 
 def train_step(objective, batch, optimizer, sigmas, rng, learning_rate, ema=None):
     """train_ncsn.py:260-288 on this rank's shard: grads -> all-reduce -> clip -> Adam (one fused pass)."""
-    if objective is not diffusion_loss:
-        raise ValueError("only the DDPM objective has a hand-written backward")
+    if objective not in (diffusion_loss, denoising_score_matching_loss):
+        raise ValueError("only the ddpm and dsm objectives have a hand-written backward")
+    dsm = objective is denoising_score_matching_loss
     model = optimizer.target
     world, rank = parallel.world_size(), parallel.rank()
     x0 = nn._as_device_f32(batch)
     local = x0.shape[0]
     eng = model.engine(local, training=True)
     betas = np.asarray(sigmas, np.float32)
-    if getattr(eng, "_obj_betas", None) is None or not np.array_equal(eng._obj_betas, betas):
+    if dsm:
+        if getattr(eng, "_dsm_sigmas", None) is None or not np.array_equal(eng._dsm_sigmas, betas):
+            eng.dsm_setup(betas)
+            eng._dsm_sigmas = betas.copy()
+    elif getattr(eng, "_obj_betas", None) is None or not np.array_equal(eng._obj_betas, betas):
         eng.objective_setup(betas)
         eng._obj_betas = betas.copy()
     if not hasattr(eng, "grads"):
         eng.init_train_state(ema=False)
     # every rank holds the SAME key and consumes rows [rank*local, (rank+1)*local) of the global batch's threefry
     # streams (labels, alpha-bar, eps): an N-GPU run with seed s sees exactly the noise of the 1-GPU run with seed s
-    used, eps = eng.draws((int(rng[0]), int(rng[1])), local, global_batch=local * world, first_row=rank * local,
-                          continuous_noise=FLAGS.continuous_noise)
-    eng.compute_grads(x0, used, eps, global_batch=local * world)
+    if dsm:
+        used, eps = eng.dsm_draws((int(rng[0]), int(rng[1])), local, global_batch=local * world, first_row=rank * local,
+                                  continuous_noise=FLAGS.continuous_noise)
+        eng.compute_dsm_grads(x0, used, eps, global_batch=local * world)
+    else:
+        used, eps = eng.draws((int(rng[0]), int(rng[1])), local, global_batch=local * world, first_row=rank * local,
+                              continuous_noise=FLAGS.continuous_noise)
+        eng.compute_grads(x0, used, eps, global_batch=local * world)
     eng.reduce_grads(world)     # tail gradients are reduced underneath the trunk backward
     optimizer.apply_gradient(eng.grads, learning_rate=learning_rate, max_norm=FLAGS.grad_clip, ema=ema, mu=FLAGS.mu,
                              engine=eng)
@@ -233,11 +247,19 @@ def sample(scorenet, sigmas, rng, sample_shape, num_samples=2400, sampling="ald"
     num_samples-sample run -- its slice of the initial normal draw and of every step's noise stream."""
     if sampling == "ddpm":
         algorithm = ebm_utils.diffusion_dynamics
-    elif sampling in ("ald", "cas"):
-        raise ValueError(f"--sampling={sampling}: the NCSN samplers are outside the B200 hot path (use ddpm)")
+    elif sampling == "ald":
+        algorithm = ebm_utils.annealed_langevin_dynamics
+    elif sampling == "cas":
+        algorithm = ebm_utils.consistent_langevin_dynamics
     else:
         raise ValueError(f"Unknown sampling algorithm: {sampling}")
     init_rng, ld_rng = random.split(rng)
+    if sampling != "ddpm":
+        # train_ncsn.py:541-547: uniform start with zero mean / unit variance; no data-parallel sharding of this family
+        rho = float(np.sqrt(np.float32(12)) / 2)
+        init = random.uniform(init_rng, (num_samples, *sample_shape), -rho, rho)
+        generated, collection, ld_metrics = algorithm(ld_rng, scorenet, sigmas, init, epsilon, steps, denoise, False)
+        return generated, collection, ebm_utils.collate_sampling_metrics(ld_metrics)
     if shard is None or shard[1] <= 1:
         init = random.normal(init_rng, (num_samples, *sample_shape))
         generated, collection, ld_metrics = algorithm(ld_rng, scorenet, sigmas, init, epsilon, steps, denoise, False)

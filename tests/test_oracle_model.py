@@ -125,3 +125,42 @@ def test_golden_fixture_matches_oracle():
     y = O.transformer_ddpm(params_torch(eng, flat, torch.float64), torch.from_numpy(g["x"]).double(),
                            torch.from_numpy(g["t"]).double(), **oracle_kwargs(eng.cfg))
     assert rel_l2(y, torch.from_numpy(g["y64"])) < 1e-12
+
+
+def test_dsm_oracle_semantics():
+    """utils/losses.py:146-179: with a decreasing schedule the `continuous` uniform(minval=sigmas[l-1], maxval=sigmas[l])
+    has minval > maxval and collapses to sigmas[l-1] (jax 0.2.8 max(minval, ...)); a perfect score network
+    (score = -noise / sigma^2) has zero loss; the loss of the zero network is 0.5 * |eps|^2."""
+    from oracle import threefry as tf
+    sigmas = O.create_noise_schedule(1.0, 0.01, 15, "geometric")
+    assert sigmas[0] > sigmas[-1]
+    key = tf.prng_key(1)
+    labels, used, eps = O.dsm_draws(key, (32, 8), sigmas, continuous_noise=True)
+    assert labels.min() >= 1 and labels.max() <= 14
+    np.testing.assert_array_equal(used, sigmas[labels - 1])
+    labels0, used0, _ = O.dsm_draws(key, (32, 8), sigmas, continuous_noise=False)
+    assert labels0.min() >= 0 and labels0.max() <= 14
+    np.testing.assert_array_equal(used0, sigmas[labels0])
+    x = torch.zeros(32, 8)
+    e = torch.from_numpy(eps)
+    us = torch.from_numpy(used)
+    perfect = lambda a, s: -(a - x) / (s ** 2)
+    loss, _ = O.dsm_loss_tensors(perfect, x, us, e, "none")
+    assert float(loss.abs().max()) < 1e-8
+    zero = lambda a, s: torch.zeros_like(a)
+    loss0, _ = O.dsm_loss_tensors(zero, x, us, e, "none")
+    np.testing.assert_allclose(loss0.numpy(), 0.5 * (e ** 2).sum(-1).numpy(), rtol=1e-5)
+
+
+def test_langevin_oracles_with_a_zero_score():
+    """With score == 0 and no noise both samplers leave the state untouched; the collection / metrics shapes are those of
+    utils/ebm_utils.py:123-129,196-198 and :265-271."""
+    sig = O.create_noise_schedule(1.0, 0.05, 4, "geometric")
+    init = torch.ones(3, 5)
+    z0 = lambda *a: (torch.zeros(3, 5), torch.zeros(3, 5))
+    st, coll, m = O.annealed_langevin_dynamics(lambda a, s: torch.zeros_like(a), sig, init, 1e-4, 3, True, z0)
+    assert torch.equal(st, init) and coll.shape == (102, 3, 5) and m.shape == (4, 4, 3)
+    assert torch.equal(coll[0], init) and torch.equal(coll[-1], init)
+    np.testing.assert_allclose(m[2, :, 0].numpy(), 1e-4 * (sig / sig[-1]) ** 2, rtol=1e-6)
+    st, m = O.consistent_langevin_dynamics(lambda a, s: torch.zeros_like(a), sig, init, 1e-4, True, lambda i: torch.zeros(3, 5))
+    assert torch.equal(st, init) and m.shape == (4, 4, 1)
