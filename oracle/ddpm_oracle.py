@@ -394,7 +394,11 @@ def annealed_langevin_dynamics(apply_fn, sigmas, init: Tensor, epsilon, T: int, 
             image_idx = si * T + i + 1
             mask = idx_tab == image_idx
             if mask.any():
-                collection[int(np.sum(np.arange(len(idx_tab)) * mask) + 1)] = nxt
+                # (with fewer than 100 total steps linspace repeats indices and the summed slot leaves the buffer: XLA's
+                # scatter drops such an update)
+                slot = int(np.sum(np.arange(len(idx_tab)) * mask) + 1)
+                if slot < collection.shape[0]:
+                    collection[slot] = nxt
             mets[0, si, i] = _axis1_norm(grad); mets[1, si, i] = _axis1_norm(alpha * grad)
             mets[2, si, i] = alpha; mets[3, si, i] = _axis1_norm(noise)
             state = nxt

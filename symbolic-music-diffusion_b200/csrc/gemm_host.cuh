@@ -137,7 +137,7 @@ inline int stats_slots_for(const GemmOp& op, const GemmEpilogue& ep) {
 
 template <int kCG, uint32_t kF, int kEW = 8>
 inline cudaError_t launch_gemm_inst(const GemmOp& op, int M, const GemmEpilogue& ep, cudaStream_t st) {
-  using SM = GemmSmem<kCG, kEW, lnf_kind(kF)>;
+  using SM = GemmSmem<kCG, kEW, lnf_kind(kF), scr_floats(kF)>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCG, kF, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -188,8 +188,12 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
     // LN-fused two-pass epilogue (the caller arms it only for full, aligned tiles; see smd_api.cu::arm_lnf)
     if (!epi_clean(op, ep) || op.N % op.BN != 0 || op.BN % 64 != 0 || op.k_splits > 1) return cudaErrorInvalidValue;
     if constexpr (kCG == 2) {   // (the 64 KB parking buffer only fits next to the 32 KB pipeline slots of CTA pairs)
-      if (ep.residual != nullptr || ep.out_f32 != nullptr) return launch_gemm_inst<kCG, kEpiLnfB>(op, M, ep, st);
-      return launch_gemm_inst<kCG, kEpiLnfA>(op, M, ep, st);
+      // epilogue warps per kind: SMD_LNF_WARPS_A / _B = 8 | 12 (12: three warps per TMEM quadrant, <= 128 registers)
+      static const int wa = [] { const char* v = getenv("SMD_LNF_WARPS_A"); return (v && atoi(v) == 8) ? 8 : 12; }();
+      static const int wb = [] { const char* v = getenv("SMD_LNF_WARPS_B"); return (v && atoi(v) == 12) ? 12 : 8; }();
+      if (ep.residual != nullptr || ep.out_f32 != nullptr)
+        return wb == 12 ? launch_gemm_inst<kCG, kEpiLnfB, 12>(op, M, ep, st) : launch_gemm_inst<kCG, kEpiLnfB, 8>(op, M, ep, st);
+      return wa == 12 ? launch_gemm_inst<kCG, kEpiLnfA, 12>(op, M, ep, st) : launch_gemm_inst<kCG, kEpiLnfA, 8>(op, M, ep, st);
     } else {
       return cudaErrorInvalidValue;
     }

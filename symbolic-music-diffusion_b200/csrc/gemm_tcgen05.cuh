@@ -88,7 +88,7 @@ static constexpr int kAccCols = 256;
 // kEW = number of epilogue warps (8: two per TMEM lane quadrant; 12: three, for epilogue-bound small-K GEMMs).
 // The pipeline depth is whatever fits next to the epilogue scratch in the 227 KB of shared memory.
 // kPark: the LN-fused epilogue (F_LNF) parks the tile as bf16 [128][256] in shared memory between its two passes.
-template <int kCG, int kEW = 8, bool kPark = false>
+template <int kCG, int kEW = 8, bool kPark = false, int kScrFloats = 32 * 33>
 struct GemmSmem {
   static constexpr int kBRowsMax = 256 / kCG;
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB
@@ -96,7 +96,8 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kEpiWarps = kEW;
-  static constexpr int kScratchBytes = kEpiWarps * 32 * 33 * 4;            // per-epilogue-warp transpose scratch
+  static constexpr int kScrPerWarp = kScrFloats;                           // floats of scratch per epilogue warp
+  static constexpr int kScratchBytes = kEpiWarps * kScrFloats * 4;         // per-epilogue-warp transpose scratch
   static constexpr int kParkBytes = kPark ? kBM * 256 * 2 : 0;             // 64 KB
   static constexpr int kMaxSmem = 232448;                                  // 227 KB
   static constexpr int kStages = (kMaxSmem - 1024 - kBarBytes - kScratchBytes - kParkBytes) / kStageBytes;
@@ -104,6 +105,10 @@ struct GemmSmem {
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
 };
 static constexpr bool lnf_kind(uint32_t kF) { return (kF & F_LNF) != 0 && (kF & F_RAGGED) == 0; }
+// LN-fused kinds without residual / fp32 output need no 32x33 transpose tile, only the staged coefficients
+static constexpr int scr_floats(uint32_t kF) {
+  return (lnf_kind(kF) && (kF & (F_RES | F_F32)) == 0) ? 384 : 32 * 33;
+}
 
 // MUFU.TANH (abs error ~5e-4, far below the bf16 rounding of everything that consumes it)
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -158,7 +163,7 @@ template <int kCG, uint32_t kF, int kEW = 8>
 __global__ void __launch_bounds__(128 + 32 * kEW, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape sh, const GemmEpilogue ep) {
-  using SM = GemmSmem<kCG, kEW, lnf_kind(kF)>;
+  using SM = GemmSmem<kCG, kEW, lnf_kind(kF), scr_floats(kF)>;
   static_assert(SM::kStages >= 3, "pipeline too shallow");
   static_assert(!((kF & F_LN) && !(kF & F_RAGGED)) || kEW == 8, "the paired LayerNorm epilogue needs 8 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
@@ -302,7 +307,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr bool H_LNF = (kF & F_LNF) != 0 && !H_RAGGED;
     const uint32_t q = warp & 3u;                      // TMEM lane quadrant this warp may access
     const int eg = static_cast<int>(warp - 4u) >> 2;   // column group 0/1: the two warps of a quadrant split the chunks
-    float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * (32 * 33);
+    float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * SM::kScrPerWarp;
     uint32_t* scrw = reinterpret_cast<uint32_t*>(scr);
     const int f_r = static_cast<int>(lane >> 3), f_c = static_cast<int>(lane & 7u) * 4;  // fp32: 4 rows x 128 B / instr
     const int h_r = static_cast<int>(lane >> 2), h_c = static_cast<int>(lane & 3u) * 8;  // bf16: 8 rows x 64 B / instr
@@ -336,8 +341,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       //     are those of the fp32 v.)
       // Deadlock freedom: tiles are visited in increasing index by co-resident persistent CTAs; a wait only targets
       // pass 1 of tiles of the same round, which never waits on anything (launch one such kernel at a time).
-      static_assert(kEW == 8, "the LN-fused epilogue is written for 8 epilogue warps");
-      const int nslots = num_n * 2;
+      constexpr int G = kEW / 4;          // epilogue warps per TMEM lane quadrant: they split the tile's 32-column chunks
+      const int nslots = num_n * G;
       const float inv_n = 1.0f / static_cast<float>(sh.N);
       const int act2 = ep.act2;
       uint8_t* park = smem + SM::kStages * SM::kStageBytes + SM::kBarBytes + SM::kScratchBytes;   // [128 rows][512 B]
@@ -372,7 +377,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         };
         prefetch(eg * 32);
         // ---------------- pass 1 ----------------
-        for (int c0 = eg * 32; c0 < BN; c0 += 64) {
+        for (int c0 = eg * 32; c0 < BN; c0 += 32 * G) {
           __syncwarp();
           uint32_t r[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
@@ -398,7 +403,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 float* d = scr + (it * 4 + f_r) * 33 + f_c;
                 d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
               }
-              if (c0 + 64 < BN) prefetch(c0 + 64);
+              if (c0 + 32 * G < BN) prefetch(c0 + 32 * G);
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
@@ -430,7 +435,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ---------------- exchange ----------------
         uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
         {
-          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * 2 + eg);
+          float2* slot = reinterpret_cast<float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots + (n_idx * G + eg);
           __stcg(slot, make_float2(s1, s2));
           __threadfence();
           __syncwarp();
@@ -439,7 +444,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if constexpr (H_F32) {
           if (has_f32) {
             tmem_st_wait();
-            for (int c0 = eg * 32; c0 < BN; c0 += 64) {
+            for (int c0 = eg * 32; c0 < BN; c0 += 32 * G) {
               __syncwarp();
               uint32_t r[32];
               tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
@@ -473,12 +478,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // the pre-LayerNorm copy the backward pass wants (bf16 [M][N]) comes straight from the parked tile
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int chunk = ((eg * 32 + 64 * j) >> 3) + static_cast<int>(lane & 3u);
+              const int c0 = (eg + G * j) * 32;
+              const int chunk = (c0 >> 3) + static_cast<int>(lane & 3u);
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const int rr = it * 8 + h_r, grow = row_base + rr;
-                if (64 * j + eg * 32 < BN && grow < sh.M)
-                  *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + n0 + eg * 32 + 64 * j + h_c) =
+                if (c0 < BN && grow < sh.M)
+                  *reinterpret_cast<uint4*>(ep.out_bf16_pre + static_cast<size_t>(grow) * ep.ld_bf16 + n0 + c0 + h_c) =
                       *reinterpret_cast<const uint4*>(park_ptr(rr, chunk));
               }
             }
@@ -493,7 +499,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int c0 = eg * 32 + 64 * j;
+            const int c0 = (eg + G * j) * 32;
             if (c0 < BN) {
               const int col = n0 + c0 + 4 * static_cast<int>(lane & 7u);
               if (lane < 8) {
@@ -521,10 +527,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
         {
           float t1 = 0.f, t2 = 0.f;
-          const float4* pp = reinterpret_cast<const float4*>(ep.lnf_part + static_cast<size_t>(row) * nslots * 2);
-          for (int s = 0; s < nslots / 2; ++s) {     // fixed order: the statistics are bit-reproducible
-            const float4 p = __ldcg(pp + s);
-            t1 += p.x; t2 += p.y; t1 += p.z; t2 += p.w;
+          const float2* pp = reinterpret_cast<const float2*>(ep.lnf_part) + static_cast<size_t>(row) * nslots;
+          for (int s = 0; s < nslots; ++s) {         // fixed order: the statistics are bit-reproducible
+            const float2 p = __ldcg(pp + s);
+            t1 += p.x; t2 += p.y;
           }
           const float mean_l = t1 * inv_n;
           const float rstd_l = rsqrtf(t2 * inv_n - mean_l * mean_l + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
@@ -538,7 +544,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         constexpr bool kSwish = decltype(swish_tag)::value;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int c0 = eg * 32 + 64 * j;
+          const int c0 = (eg + G * j) * 32;
           if (c0 < BN) {
             const int col0 = n0 + c0;
             float A[8], Bc[8];

@@ -925,6 +925,7 @@ int smd_langevin_step(smd_plan* plan, const float* x, const float* grad, int n, 
   a.infill_x = infill_x; a.infill_mask = infill_mask; a.infill_z = infill_z;
   a.x_next = x_next; a.collection_slot = collection_slot; a.metrics = metrics4;
   a.N = n; a.S = plan->cfg.seq_len; a.C = plan->cfg.channels;
+  if (plan->cfg.arch != SMD_ARCH_TRANSFORMER_DDPM) { a.S = plan->cfg.channels; a.C = 1; }   // (N, D) states: axis 1 = D
   launch_langevin_step(a, static_cast<cudaStream_t>(stream)); CNT();
   SMD_LAUNCH_CHECK("langevin_step");
   return SMD_OK;
@@ -1105,6 +1106,8 @@ static int reverse_step_impl(smd_plan* plan, const float* params, const float* x
   a.infill_x = infill_x; a.infill_mask = infill_mask; a.infill_z = infill_z;
   a.x_next = x_next; a.collection = collection; a.metrics = metrics;
   a.N = n; a.S = plan->cfg.seq_len; a.C = plan->cfg.channels; a.T = plan->T;
+  // 2-D states (N, D) of the dense networks: the metrics' axis 1 (utils/ebm_utils.py:380-384) is D itself
+  if (plan->cfg.arch != SMD_ARCH_TRANSFORMER_DDPM) { a.S = plan->cfg.channels; a.C = 1; }
   if (plan->shard_total_rows > 0) {
     const long long per = static_cast<long long>(a.S) * a.C;
     a.rng_first = static_cast<uint32_t>(plan->shard_first_row * per);

@@ -121,6 +121,8 @@ def annealed_langevin_dynamics(rng, model, sigmas, init, epsilon, T, denoise, in
             key, step_key, infill_key = random.split(key, 3)
             eng.forward(x, sigma_dev, out=grad)                                 # model(state, sigma)
             slot = slot_of(si * T + i + 1)
+            if slot >= collection.shape[0]:
+                slot = -1       # repeated linspace indices (fewer than 100 steps in total): XLA's scatter drops the update
             eng.langevin_step(x, grad, float(alpha), float(np.sqrt(np.float32(2) * alpha)), step_key=step_key,
                               infill_x=ix, infill_mask=im, infill_sigma=float(s), infill_key=infill_key, x_next=x,
                               collection_slot=collection[slot] if slot >= 0 else None, metrics4=metrics[si, i])
