@@ -1,0 +1,351 @@
+// Fused self-attention block for sm_100a (inference):
+//   h_mid = SelfAttention(a) + h_in ;  a2 = LayerNorm(h_mid)
+// (models/ncsn.py:160-164 in the reference: LayerNorm -> nn.SelfAttention -> + shortcut, followed by the FFN's
+// LayerNorm; flax.nn.SelfAttention = q/k/v DenseGeneral, q / sqrt(depth), softmax(q k^T) v, out DenseGeneral).
+// Replaces three launches (QKV GEMM -> attention -> out-projection GEMM) whose fp32 q/k/v round trip through HBM
+// (1536 B written + 1536 B read per token) was the whole cost: here q, k, v never leave the SM.
+//
+// One CTA pair (cta_group::2) owns 256 tokens = 8 samples of 32 positions; each CTA holds 4 samples, one per TMEM lane
+// quadrant, so a warp's 32 TMEM lanes are exactly the 32 positions of one sample.
+//   GEMM qkv : D[0:384) (TMEM) = A[256 x 128] . Wqkv[128 x 384]          (three N = 128 MMAs per k-step, K = 128)
+//   attention: 16 epilogue warps (4 per quadrant); a warp handles H/4 heads of its sample, one at a time: q/k/v head
+//              slices TMEM -> registers (+ bias, q / sqrt(dh)); k and v rows go to a per-warp shared-memory tile and are
+//              read back as broadcasts (every lane = one query position walks the 32 keys); fp32 softmax with the
+//              reference's max-subtracted exp / sum; o head slice -> bf16 -> written straight into the canonical
+//              K-major SWIZZLE_128B operand layout of the next GEMM
+//   GEMM out : D[384:512) = O[256 x 128] . Wo[128 x 128]
+//   epilogue : + bo + residual -> h_mid (fp32) ; single-pass LayerNorm -> a2 (bf16)
+// The weights (Wq|Wk|Wv|Wo, 64 KB per CTA) are fetched once per CTA and stay in shared memory for all its tiles.
+//
+// Warp roles (640 threads): 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4..19 epilogue.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace smd {
+
+struct AttnBlockArgs {
+  const float* b_qkv;            // [384] = bq | bk | bv
+  const float* b_o;              // [128]
+  const float* residual;         // fp32 [M][128] (may alias out_f32)
+  float* out_f32;                // fp32 [M][128]
+  const float* ln_gamma;         // [128] LayerNorm of the new residual stream -> out_bf16
+  const float* ln_beta;
+  __nv_bfloat16* out_bf16;       // bf16 [M][128]
+  int M, H;                      // tokens; heads (dh = 128 / H in {8, 16})
+};
+
+struct AttnSmem {
+  static constexpr int kA = 32768;          // [2 k-blocks][128 rows][128 B]
+  static constexpr int kW = 16384;          // per-CTA half of a 128-column weight block: [2 k-blocks][64 k][64 n]
+  static constexpr int kO = 32768;          // attention output as the out-projection's A operand
+  static constexpr int offA = 0;
+  static constexpr int offW = offA + kA;                 // q, k, v, o blocks
+  static constexpr int offO = offW + 4 * kW;
+  static constexpr int offBar = offO + kO;
+  static constexpr int kBarBytes = 256;
+  static constexpr int offScr = offBar + kBarBytes;
+  static constexpr int kEpiWarps = 16;
+  static constexpr int kKvFloats = 2 * 32 * 20;          // k and v tiles of one head: [32][dh + 4], dh <= 16
+  static constexpr int kScrPerWarp = kKvFloats;          // (also holds the 2 x 32 LayerNorm partials of the final epilogue)
+  static constexpr int kScrBytes = kEpiWarps * kScrPerWarp * 4;
+  static constexpr int kTotal = offScr + kScrBytes + 1024;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+};
+
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <int DH>
+__device__ __forceinline__ void tmem_ld_head(uint32_t taddr, float (&out)[DH]) {
+  if constexpr (DH == 16) {
+    uint32_t r[16];
+    tmem_ld_32x16(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(r[i]);
+  } else {
+    uint32_t r[8];
+    tmem_ld_32x8(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = __uint_as_float(r[i]);
+  }
+}
+
+template <int DH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AttnSmem::kThreads, 1)
+attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWqkv,
+                  const __grid_constant__ CUtensorMap tmWo, const AttnBlockArgs p) {
+  using S = AttnSmem;
+  constexpr int PITCH = DH + 4;
+  extern __shared__ uint8_t attn_smem_raw[];
+  uint8_t* smem = attn_smem_raw + ((1024u - (smem_u32(attn_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::offBar);
+  uint64_t* w_full = bars + 0;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = bars + 2;
+  uint64_t* qkv_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint64_t* d2_full = bars + 5;
+  uint64_t* d2_empty = bars + 6;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = (p.M + 255) / 256;
+  const int group = blockIdx.x / 2, num_groups = gridDim.x / 2;
+
+  pdl_trigger();
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmWqkv);
+    tma_prefetch_desc(&tmWo);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(qkv_full, 1);
+    mbar_init(o_full, 2 * S::kEpiWarps);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, 2 * S::kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_ptr_smem, 512);
+    tmem_relinquish<2>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      // weights once: block b (q, k, v) = columns [128 b, 128 b + 128) of Wqkv [K = 128][N = 384]; this CTA's 64 columns
+      if (leader) mbar_arrive_expect_tx(w_full, 2u * 4u * S::kW);
+      const uint32_t w_bar = mapa_shared(smem_u32(w_full), 0);
+      for (int b = 0; b < 3; ++b)
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d_2sm(&tmWqkv, w_bar, smem + S::offW + b * S::kW + kb * 8192, b * 128 + static_cast<int>(rank) * 64, 64 * kb);
+      for (int kb = 0; kb < 2; ++kb)
+        tma_load_2d_2sm(&tmWo, w_bar, smem + S::offW + 3 * S::kW + kb * 8192, static_cast<int>(rank) * 64, 64 * kb);
+      const uint32_t a_full_l = mapa_shared(smem_u32(a_full), 0);
+      uint32_t nt = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
+        const int m_row0 = tile * 256 + static_cast<int>(rank) * 128;
+        mbar_wait(a_empty, (nt & 1u) ^ 1u);
+        if (leader) mbar_arrive_expect_tx(a_full, 2u * S::kA);
+        for (int kb = 0; kb < 2; ++kb) tma_load_2d_2sm(&tmA, a_full_l, smem + S::offA + kb * 16384, 64 * kb, m_row0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one lane) =====================
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(256, 128, 0, 1);   // A / O K-major, weights MN-major
+      const uint32_t sA = smem_u32(smem + S::offA), sO = smem_u32(smem + S::offO);
+      mbar_wait(w_full, 0);
+      uint32_t nt = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
+        mbar_wait(a_full, nt & 1u);
+        // (the q/k/v accumulators of the previous tile were drained before its o_full arrived, which this thread
+        // waited for below)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const uint32_t sW = smem_u32(smem + S::offW + b * S::kW);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(sA + kb * 16384 + k * 32, 0u, 1024u);
+              const uint64_t bd = make_smem_desc_sw128(sW + kb * 8192 + k * 2048, 8192u, 1024u);
+              umma_bf16<2>(tmem_base + b * 128u, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+        }
+        umma_commit<2>(a_empty);      // the A tile may be refilled
+        umma_commit<2>(qkv_full);
+        mbar_wait_cluster(o_full, nt & 1u);
+        mbar_wait_cluster(d2_empty, (nt & 1u) ^ 1u);
+        tcgen05_fence_after();
+        {
+          const uint32_t sW = smem_u32(smem + S::offW + 3 * S::kW);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(sO + kb * 16384 + k * 32, 0u, 1024u);
+              const uint64_t bd = make_smem_desc_sw128(sW + kb * 8192 + k * 2048, 8192u, 1024u);
+              umma_bf16<2>(tmem_base + 384u, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+        }
+        umma_commit<2>(d2_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const uint32_t q = warp & 3u;                      // TMEM lane quadrant = sample within this CTA
+    const int eg = static_cast<int>(warp - 4u) >> 2;   // 0..3: head group / 32-column quarter of the output
+    float* scr_all = reinterpret_cast<float*>(smem + S::offScr);
+    float* scr = scr_all + (warp - 4u) * S::kScrPerWarp;
+    float* sK = scr;                 // [32][PITCH]
+    float* sV = scr + 32 * PITCH;    // [32][PITCH]
+    const uint32_t o_full_l = mapa_shared(smem_u32(o_full), 0);
+    const uint32_t d2_empty_l = mapa_shared(smem_u32(d2_empty), 0);
+    const uint32_t r_in_tile = q * 32u + lane;         // row of this thread inside the CTA's 128-row tile
+    const uint32_t swz = r_in_tile & 7u;
+    const int heads_per_warp = p.H / 4;
+    const float qscale = rsqrtf(static_cast<float>(DH));
+    const uint32_t lane_base = tmem_base + ((q * 32u) << 16);
+    uint32_t nt = 0;
+    for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
+      const int row = tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(r_in_tile);
+      const bool row_ok = row < p.M;
+      mbar_wait(qkv_full, nt & 1u);
+      tcgen05_fence_after();
+      for (int hh = 0; hh < heads_per_warp; ++hh) {
+        const int h = eg * heads_per_warp + hh;
+        const int hc = h * DH;                         // first column of this head inside a 128-wide block
+        __syncwarp();
+        float qv[DH], kv[DH], vv[DH];
+        tmem_ld_head<DH>(lane_base + static_cast<uint32_t>(hc), qv);
+        tmem_ld_head<DH>(lane_base + 128u + static_cast<uint32_t>(hc), kv);
+        tmem_ld_head<DH>(lane_base + 256u + static_cast<uint32_t>(hc), vv);
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p.b_qkv + hc + d));
+          const float4 bk = __ldg(reinterpret_cast<const float4*>(p.b_qkv + 128 + hc + d));
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.b_qkv + 256 + hc + d));
+          qv[d] = (qv[d] + bq.x) * qscale; qv[d + 1] = (qv[d + 1] + bq.y) * qscale;     // flax: query / sqrt(depth)
+          qv[d + 2] = (qv[d + 2] + bq.z) * qscale; qv[d + 3] = (qv[d + 3] + bq.w) * qscale;
+          kv[d] += bk.x; kv[d + 1] += bk.y; kv[d + 2] += bk.z; kv[d + 3] += bk.w;
+          vv[d] += bv.x; vv[d + 1] += bv.y; vv[d + 2] += bv.z; vv[d + 3] += bv.w;
+          *reinterpret_cast<float4*>(sK + lane * PITCH + d) = make_float4(kv[d], kv[d + 1], kv[d + 2], kv[d + 3]);
+          *reinterpret_cast<float4*>(sV + lane * PITCH + d) = make_float4(vv[d], vv[d + 1], vv[d + 2], vv[d + 3]);
+        }
+        __syncwarp();
+        // scores of this lane's query against the 32 keys (broadcast reads), max-subtracted softmax
+        float sc[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float s = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(sK + j * PITCH + d);
+            s = fmaf(qv[d], k4.x, s); s = fmaf(qv[d + 1], k4.y, s); s = fmaf(qv[d + 2], k4.z, s); s = fmaf(qv[d + 3], k4.w, s);
+          }
+          sc[j] = s;
+          mx = fmaxf(mx, s);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+        const float inv = 1.0f / sum;
+        float acc[DH];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pj = sc[j] * inv;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(sV + j * PITCH + d);
+            acc[d] = fmaf(pj, v4.x, acc[d]); acc[d + 1] = fmaf(pj, v4.y, acc[d + 1]);
+            acc[d + 2] = fmaf(pj, v4.z, acc[d + 2]); acc[d + 3] = fmaf(pj, v4.w, acc[d + 3]);
+          }
+        }
+        // o head slice -> bf16 -> canonical K-major SWIZZLE_128B operand: 16-byte chunk c of row r lives at
+        // r * 128 + ((c ^ (r & 7)) << 4) inside k-block (column / 64)
+        uint8_t* orow = smem + S::offO + (hc >> 6) * 16384 + r_in_tile * 128u;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          const uint32_t ch = static_cast<uint32_t>(((hc & 63) >> 3) + c);
+          *reinterpret_cast<uint4*>(orow + ((ch ^ swz) << 4)) =
+              make_uint4(pack_bf16x2(acc[8 * c], acc[8 * c + 1]), pack_bf16x2(acc[8 * c + 2], acc[8 * c + 3]),
+                         pack_bf16x2(acc[8 * c + 4], acc[8 * c + 5]), pack_bf16x2(acc[8 * c + 6], acc[8 * c + 7]));
+        }
+      }
+      // q/k/v accumulators drained and this warp's part of O written
+      tcgen05_fence_before();
+      fence_proxy_async_smem();    // O stores become visible to the tensor core's (async proxy) reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(o_full_l);
+      // ---------------- final epilogue: D2 + bo + residual -> LayerNorm ----------------
+      const int c0 = eg * 32;
+      mbar_wait(d2_full, nt & 1u);
+      tcgen05_fence_after();
+      __syncwarp();
+      uint32_t r[32];
+      tmem_ld_32x32(lane_base + 384u + static_cast<uint32_t>(c0), r);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(d2_empty_l);
+      float xv[32];
+      float s1 = 0.f, s2 = 0.f;
+      {
+        const float4* b4 = reinterpret_cast<const float4*>(p.b_o + c0);
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row_ok ? row : 0) * 128 + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + i);
+          const float4 rr = row_ok ? r4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[4 * i] = __uint_as_float(r[4 * i]) + bb.x + rr.x;
+          xv[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y + rr.y;
+          xv[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z + rr.z;
+          xv[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w + rr.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { s1 += xv[i]; s2 += xv[i] * xv[i]; }
+      if (row_ok) {
+        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * 128 + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(xv[4 * i], xv[4 * i + 1], xv[4 * i + 2], xv[4 * i + 3]);
+      }
+      // row statistics: each of the four warps of a quadrant saw 32 of the 128 columns
+      scr[lane * 2] = s1; scr[lane * 2 + 1] = s2;
+      asm volatile("bar.sync %0, 128;" ::"r"(1u + q) : "memory");
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const float* sp = scr_all + (static_cast<uint32_t>(g4) * 4u + q) * S::kScrPerWarp + lane * 2;
+        t1 += sp[0]; t2 += sp[1];
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1u + q) : "memory");
+      const float mean = t1 * (1.0f / 128.0f);
+      const float rstd = rsqrtf(t2 * (1.0f / 128.0f) - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
+      if (row_ok) {
+        const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + c0);
+        const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + c0);
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * 128 + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 g0 = __ldg(g4 + 2 * i), g1 = __ldg(g4 + 2 * i + 1), e0 = __ldg(b4 + 2 * i), e1 = __ldg(b4 + 2 * i + 1);
+          const float* x = &xv[8 * i];
+          dst[i] = make_uint4(pack_bf16x2((x[0] - mean) * (rstd * g0.x) + e0.x, (x[1] - mean) * (rstd * g0.y) + e0.y),
+                              pack_bf16x2((x[2] - mean) * (rstd * g0.z) + e0.z, (x[3] - mean) * (rstd * g0.w) + e0.w),
+                              pack_bf16x2((x[4] - mean) * (rstd * g1.x) + e1.x, (x[5] - mean) * (rstd * g1.y) + e1.y),
+                              pack_bf16x2((x[6] - mean) * (rstd * g1.z) + e1.z, (x[7] - mean) * (rstd * g1.w) + e1.w));
+        }
+      }
+    }
+  }
+
+  // ===================== teardown =====================
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+}  // namespace smd

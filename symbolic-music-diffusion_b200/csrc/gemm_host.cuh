@@ -9,6 +9,7 @@
 #include <string>
 #include "gemm_tcgen05.cuh"
 #include "ffn_fused.cuh"
+#include "attn_block.cuh"
 #include "pdl_launch.cuh"
 
 namespace smd {
@@ -123,7 +124,7 @@ inline bool epi_clean(const GemmOp& op, const GemmEpilogue& e) {
 // Number of epilogue warps of the instantiation launch_gemm will pick (mirrors launch_gemm_cg): the per-tile statistics
 // partials (GemmEpilogue::stats_part) have (epi warps / 4) slots per n-tile.
 inline int epi_warps_for(const GemmOp& op, const GemmEpilogue& ep) {
-  if (ep.lnf_part != nullptr || !epi_clean(op, ep)) return 8;
+  if (ep.lnf_part != nullptr || ep.lo_delta != 0 || !epi_clean(op, ep)) return 8;
   const uint32_t need = epi_needs(ep);
   const bool short_k = op.K <= 256;
   if ((need & ~kEpiF32) == 0) return short_k ? 12 : 8;
@@ -188,8 +189,9 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
     // LN-fused two-pass epilogue (the caller arms it only for full, aligned tiles; see smd_api.cu::arm_lnf)
     if (!epi_clean(op, ep) || op.N % op.BN != 0 || op.BN % 64 != 0 || op.k_splits > 1) return cudaErrorInvalidValue;
     if constexpr (kCG == 2) {   // (the 64 KB parking buffer only fits next to the 32 KB pipeline slots of CTA pairs)
-      // epilogue warps per kind: SMD_LNF_WARPS_A / _B = 8 | 12 (12: three warps per TMEM quadrant, <= 128 registers)
-      static const int wa = [] { const char* v = getenv("SMD_LNF_WARPS_A"); return (v && atoi(v) == 8) ? 8 : 12; }();
+      // epilogue warps per kind: SMD_LNF_WARPS_A / _B = 8 (default) | 12 (three warps per TMEM quadrant, <= 128 registers;
+      // measured slower: 280 / 371 us against 217 / 298 us per launch at 32000 tokens)
+      static const int wa = [] { const char* v = getenv("SMD_LNF_WARPS_A"); return (v && atoi(v) == 12) ? 12 : 8; }();
       static const int wb = [] { const char* v = getenv("SMD_LNF_WARPS_B"); return (v && atoi(v) == 12) ? 12 : 8; }();
       if (ep.residual != nullptr || ep.out_f32 != nullptr)
         return wb == 12 ? launch_gemm_inst<kCG, kEpiLnfB, 12>(op, M, ep, st) : launch_gemm_inst<kCG, kEpiLnfB, 8>(op, M, ep, st);
@@ -198,6 +200,7 @@ inline cudaError_t launch_gemm_cg(const GemmOp& op, int M, const GemmEpilogue& e
       return cudaErrorInvalidValue;
     }
   }
+  if (ep.lo_delta != 0) return launch_gemm_inst<kCG, kEpiStrict>(op, M, ep, st);   // strict-precision mode (bf16x3)
   const uint32_t need = epi_needs(ep);
   if (epi_clean(op, ep)) {
     auto fits = [&](uint32_t kind) { return (need & ~kind) == 0; };
@@ -267,6 +270,55 @@ inline cudaError_t launch_ffn_fused(const FfnOp& op, const FfnFusedArgs& a, cuda
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (a.hidden_pre != nullptr || a.hidden != nullptr) return cudaLaunchKernelEx(&cfg, ffn_fused_kernel<true>, op.tmA, op.tmW1, op.tmW2, a);
   return cudaLaunchKernelEx(&cfg, ffn_fused_kernel<false>, op.tmA, op.tmW1, op.tmW2, a);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// fused attention block (attn_block.cuh)
+// ---------------------------------------------------------------------------------------------------
+struct AttnOp {
+  CUtensorMap tmA, tmWqkv, tmWo;
+  bool ok = false;
+};
+// A: bf16 [rows][128] K-major; Wqkv: bf16 (128, 384) row-major; Wo: bf16 (128, 128) row-major (MN-major B operands)
+inline bool make_attn_op(AttnOp* op, const void* A, uint64_t rows, const void* Wqkv, const void* Wo) {
+  op->ok = make_tmap_bf16(&op->tmA, A, rows, 128, 128) && make_tmap_bf16(&op->tmWqkv, Wqkv, 128, 384, 64) &&
+           make_tmap_bf16(&op->tmWo, Wo, 128, 128, 64);
+  return op->ok;
+}
+// SMD_ATTN_BLOCK=0 keeps the three-launch path (QKV GEMM, attention kernel, out-projection GEMM)
+inline bool attn_block_enabled() {
+  static const bool on = [] { const char* v = getenv("SMD_ATTN_BLOCK"); return !(v && v[0] == '0'); }();
+  return on;
+}
+inline cudaError_t launch_attn_block(const AttnOp& op, const AttnBlockArgs& a, cudaStream_t st) {
+  const int dh = 128 / a.H;
+  if (dh != 8 && dh != 16) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_block_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = (a.M + 255) / 256;
+  int pairs = device_sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+  cfg.blockDim = dim3(AttnSmem::kThreads);
+  cfg.dynamicSmemBytes = AttnSmem::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (dh == 16) return cudaLaunchKernelEx(&cfg, attn_block_kernel<16>, op.tmA, op.tmWqkv, op.tmWo, a);
+  return cudaLaunchKernelEx(&cfg, attn_block_kernel<8>, op.tmA, op.tmWqkv, op.tmWo, a);
 }
 
 }  // namespace smd

@@ -23,9 +23,13 @@ enum : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SWISH = 2 };
 // instruction fetch).  kEpiGeneric keeps every feature, the ragged / unaligned row-per-thread path included.
 enum : uint32_t {
   F_BIAS = 1u, F_RES = 2u, F_F32 = 4u, F_BF16 = 8u, F_PRE = 16u, F_STATS = 32u, F_LN = 64u, F_GG = 128u,
-  F_ATOMIC = 256u, F_ACT = 512u, F_RAGGED = 1024u, F_SCALE = 2048u, F_LNF = 4096u
+  F_ATOMIC = 256u, F_ACT = 512u, F_RAGGED = 1024u, F_SCALE = 2048u, F_LNF = 4096u, F_STRICT = 8192u
 };
 static constexpr uint32_t kEpiGeneric = 0xFFFu;
+// strict-precision mode (bf16x3): the generic epilogue plus lo-half stores and exact activations.  A separate
+// instantiation on purpose: carrying that code as a runtime branch in the specialised kinds cost the FFN-up / dX GEMMs
+// a factor of 2.6 (register pressure and instruction fetch in the bf16 store path).
+static constexpr uint32_t kEpiStrict = kEpiGeneric | F_STRICT;
 // Two-pass epilogues that finish the NEXT layer's LayerNorm -> FiLM -> swish inside this GEMM (see the F_LNF branch):
 static constexpr uint32_t kEpiLnfA = F_LNF | F_BIAS | F_BF16 | F_PRE | F_STATS;            // res-block a (+ bf16 pre-LN save)
 static constexpr uint32_t kEpiLnfB = F_LNF | F_BIAS | F_RES | F_F32 | F_BF16 | F_STATS;    // res-block b / post / in
@@ -305,6 +309,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr bool H_LN = (kF & F_LN) != 0, H_GG = (kF & F_GG) != 0, H_ATOMIC = (kF & F_ATOMIC) != 0;
     constexpr bool H_ACT = (kF & F_ACT) != 0, H_RAGGED = (kF & F_RAGGED) != 0, H_SCALE = (kF & F_SCALE) != 0;
     constexpr bool H_LNF = (kF & F_LNF) != 0 && !H_RAGGED;
+    constexpr bool H_STRICT = (kF & F_STRICT) != 0;
+    const long long lo_delta = H_STRICT ? ep.lo_delta : 0;
     const uint32_t q = warp & 3u;                      // TMEM lane quadrant this warp may access
     const int eg = static_cast<int>(warp - 4u) >> 2;   // column group 0/1: the two warps of a quadrant split the chunks
     float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * SM::kScrPerWarp;
@@ -672,7 +678,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const float mean = t1 * inv_n;
         const float rstd = rsqrtf(t2 * inv_n - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
         if (has_bf16) {
-          for (int half = 0; half < (ep.lo_delta ? 2 : 1); ++half) {   // strict mode: a second sweep writes the lo halves
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (j < nchunk) {
@@ -686,13 +691,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const float w1 = (vv[j][4 * i + 1] - mean) * (rstd * g.y) + b.y;
                 const float w2 = (vv[j][4 * i + 2] - mean) * (rstd * g.z) + b.z;
                 const float w3 = (vv[j][4 * i + 3] - mean) * (rstd * g.w) + b.w;
-                if (half == 0) {
-                  scrw[lane * 33 + 2 * i] = pack_bf16x2(w0, w1);
-                  scrw[lane * 33 + 2 * i + 1] = pack_bf16x2(w2, w3);
-                } else {
-                  scrw[lane * 33 + 2 * i] = pack_bf16x2_lo(w0, w1);
-                  scrw[lane * 33 + 2 * i + 1] = pack_bf16x2_lo(w2, w3);
-                }
+                scrw[lane * 33 + 2 * i] = pack_bf16x2(w0, w1);
+                scrw[lane * 33 + 2 * i + 1] = pack_bf16x2(w2, w3);
               }
               __syncwarp();
 #pragma unroll
@@ -700,13 +700,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int rr = it * 8 + h_r, grow = row_base + rr;
                 if (grow < sh.M) {
                   const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                  *reinterpret_cast<uint4*>(ep.out_bf16 + (half ? ep.lo_delta : 0) + static_cast<size_t>(grow) * ep.ld_bf16 + c0 + h_c) =
+                  *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ld_bf16 + c0 + h_c) =
                       make_uint4(sp[0], sp[1], sp[2], sp[3]);
                 }
               }
               __syncwarp();
             }
-          }
           }
         }
       }
@@ -920,7 +919,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if constexpr (H_BF16) {
               if (write_bf16) {
-                for (int half = 0; half < (ep.lo_delta ? 2 : 1); ++half) {   // strict mode: second sweep = lo halves
+                for (int half = 0; half < ((H_STRICT && lo_delta) ? 2 : 1); ++half) {   // strict mode: second sweep = lo halves
                 if (H_LN && do_ln) {
                   const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + col0);
                   const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + col0);
@@ -934,7 +933,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     scrw[lane * 33 + 2 * i] = half ? pack_bf16x2_lo(w0, w1) : pack_bf16x2(w0, w1);
                     scrw[lane * 33 + 2 * i + 1] = half ? pack_bf16x2_lo(w2, w3) : pack_bf16x2(w2, w3);
                   }
-                } else if (ep.lo_delta) {
+                } else if (H_STRICT && lo_delta) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     const float y0 = act_apply_exact(v[2 * j], act), y1 = act_apply_exact(v[2 * j + 1], act);
@@ -953,7 +952,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   const int rr = it * 8 + h_r, grow = row_base + rr;
                   if (grow < sh.M) {
                     const uint32_t* sp = scrw + rr * 33 + (h_c >> 1);
-                    *reinterpret_cast<uint4*>(ep.out_bf16 + (half ? ep.lo_delta : 0) + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
+                    *reinterpret_cast<uint4*>(ep.out_bf16 + (half ? lo_delta : 0) + static_cast<size_t>(grow) * ep.ld_bf16 + col0 + h_c) =
                         make_uint4(sp[0], sp[1], sp[2], sp[3]);
                   }
                 }
@@ -1020,9 +1019,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (i < ncols && col0 + i < sh.N) {
                   float w;
                   if (do_ln) w = (v[i] - mean) * (rstd * __ldg(ep.ln_gamma + col0 + i)) + __ldg(ep.ln_beta + col0 + i);
-                  else w = ep.lo_delta ? act_apply_exact(v[i], act) : act_apply(v[i], act);
+                  else w = (H_STRICT && lo_delta) ? act_apply_exact(v[i], act) : act_apply(v[i], act);
                   op[i] = __float2bfloat16_rn(w);
-                  if (ep.lo_delta) op[i + ep.lo_delta] = __float2bfloat16_rn(w - __bfloat162float(__float2bfloat16_rn(w)));
+                  if (H_STRICT && lo_delta) op[i + lo_delta] = __float2bfloat16_rn(w - __bfloat162float(__float2bfloat16_rn(w)));
                 }
               }
             }

@@ -76,6 +76,7 @@ struct smd_plan {
   // ---- GEMM ops ----
   std::vector<GemmOp> op_qkv, op_o, op_ffn1, op_ffn2, op_a, op_b, op_b2;
   std::vector<FfnOp> op_ffn;   // fused FFN (cta_group 2, mlp_dims % 128 == 0)
+  std::vector<AttnOp> op_attn; // fused attention block (cta_group 2, head dim 8 / 16, inference)
   GemmOp op_post, op_out, op_in;
   // sampler
   int T = 0;

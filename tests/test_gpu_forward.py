@@ -112,3 +112,16 @@ def test_fused_ffn_kernel(lib):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "fused_ffn_worker.py")], env=env, cwd=root,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "fused-ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("post", ["0", "1"])
+def test_ln_fused_epilogue(lib, post):
+    """The LN-fused GEMM epilogue (csrc/gemm_tcgen05.cuh, F_LNF) is opt-in (SMD_LNF=1, read once per process): parity,
+    bit-reproducibility and gradient checks run in a worker process; SMD_LNF_POST=1 also fuses the K = 128 post GEMM."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SMD_LNF="1", SMD_LNF_POST=post)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "lnf_worker.py")], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "lnf-ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
