@@ -9,10 +9,10 @@
 // quadrant, so a warp's 32 TMEM lanes are exactly the 32 positions of one sample.
 //   GEMM qkv : D[0:384) (TMEM) = A[256 x 128] . Wqkv[128 x 384]          (three N = 128 MMAs per k-step, K = 128)
 //   attention: 16 epilogue warps (4 per quadrant); a warp handles H/4 heads of its sample, one at a time: q/k/v head
-//              slices TMEM -> registers (+ bias, q / sqrt(dh)); k and v rows go to a per-warp shared-memory tile and are
-//              read back as broadcasts (every lane = one query position walks the 32 keys); fp32 softmax with the
-//              reference's max-subtracted exp / sum; o head slice -> bf16 -> written straight into the canonical
-//              K-major SWIZZLE_128B operand layout of the next GEMM
+//              slices TMEM -> registers (+ bias, q / sqrt(dh)) -> tf32 rows in a per-warp shared-memory tile -> Q K^T and
+//              P V on mma.sync m16n8k8 tf32 (a 32x32x16 problem per head is far below a tcgen05 tile), fp32 softmax
+//              with the reference's max-subtracted exp / sum on the accumulator fragments; o head slice -> bf16 ->
+//              written straight into the canonical K-major SWIZZLE_128B operand layout of the next GEMM
 //   GEMM out : D[384:512) = O[256 x 128] . Wo[128 x 128]
 //   epilogue : + bo + residual -> h_mid (fp32) ; single-pass LayerNorm -> a2 (bf16)
 // The weights (Wq|Wk|Wv|Wo, 64 KB per CTA) are fetched once per CTA and stay in shared memory for all its tiles.
@@ -20,6 +20,7 @@
 // Warp roles (640 threads): 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4..19 epilogue.
 #pragma once
 #include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
 
 namespace smd {
 
@@ -195,12 +196,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int eg = static_cast<int>(warp - 4u) >> 2;   // 0..3: head group / 32-column quarter of the output
     float* scr_all = reinterpret_cast<float*>(smem + S::offScr);
     float* scr = scr_all + (warp - 4u) * S::kScrPerWarp;
-    float* sK = scr;                 // [32][PITCH]
-    float* sV = scr + 32 * PITCH;    // [32][PITCH]
+    uint32_t* sA = reinterpret_cast<uint32_t*>(scr);                 // [32][PITCH] tf32: q rows, later v rows
+    uint32_t* sB = reinterpret_cast<uint32_t*>(scr) + 32 * PITCH;    // [32][PITCH] tf32: k rows
+    const int g = static_cast<int>(lane >> 2), t = static_cast<int>(lane & 3u);   // mma.sync fragment coordinates
     const uint32_t o_full_l = mapa_shared(smem_u32(o_full), 0);
     const uint32_t d2_empty_l = mapa_shared(smem_u32(d2_empty), 0);
     const uint32_t r_in_tile = q * 32u + lane;         // row of this thread inside the CTA's 128-row tile
-    const uint32_t swz = r_in_tile & 7u;
     const int heads_per_warp = p.H / 4;
     const float qscale = rsqrtf(static_cast<float>(DH));
     const uint32_t lane_base = tmem_base + ((q * 32u) << 16);
@@ -218,60 +219,114 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_head<DH>(lane_base + static_cast<uint32_t>(hc), qv);
         tmem_ld_head<DH>(lane_base + 128u + static_cast<uint32_t>(hc), kv);
         tmem_ld_head<DH>(lane_base + 256u + static_cast<uint32_t>(hc), vv);
+        // + bias, q / sqrt(depth) (flax), rounded to tf32 once; q and k rows -> this warp's two [32][DH + 4] tiles
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           const float4 bq = __ldg(reinterpret_cast<const float4*>(p.b_qkv + hc + d));
           const float4 bk = __ldg(reinterpret_cast<const float4*>(p.b_qkv + 128 + hc + d));
           const float4 bv = __ldg(reinterpret_cast<const float4*>(p.b_qkv + 256 + hc + d));
-          qv[d] = (qv[d] + bq.x) * qscale; qv[d + 1] = (qv[d + 1] + bq.y) * qscale;     // flax: query / sqrt(depth)
-          qv[d + 2] = (qv[d + 2] + bq.z) * qscale; qv[d + 3] = (qv[d + 3] + bq.w) * qscale;
-          kv[d] += bk.x; kv[d + 1] += bk.y; kv[d + 2] += bk.z; kv[d + 3] += bk.w;
+          *reinterpret_cast<uint4*>(sA + lane * PITCH + d) =
+              make_uint4(to_tf32((qv[d] + bq.x) * qscale), to_tf32((qv[d + 1] + bq.y) * qscale),
+                         to_tf32((qv[d + 2] + bq.z) * qscale), to_tf32((qv[d + 3] + bq.w) * qscale));
+          *reinterpret_cast<uint4*>(sB + lane * PITCH + d) =
+              make_uint4(to_tf32(kv[d] + bk.x), to_tf32(kv[d + 1] + bk.y), to_tf32(kv[d + 2] + bk.z), to_tf32(kv[d + 3] + bk.w));
           vv[d] += bv.x; vv[d + 1] += bv.y; vv[d + 2] += bv.z; vv[d + 3] += bv.w;
-          *reinterpret_cast<float4*>(sK + lane * PITCH + d) = make_float4(kv[d], kv[d + 1], kv[d + 2], kv[d + 3]);
-          *reinterpret_cast<float4*>(sV + lane * PITCH + d) = make_float4(vv[d], vv[d + 1], vv[d + 2], vv[d + 3]);
         }
         __syncwarp();
-        // scores of this lane's query against the 32 keys (broadcast reads), max-subtracted softmax
-        float sc[32];
-        float mx = -INFINITY;
+        // ---- S = (Q / sqrt(dh)) K^T on mma.sync m16n8k8 tf32: 2 m-tiles x 4 n-tiles, DH / 8 k-steps
+        float sc[2][4][4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float s = 0.f;
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int d = 0; d < DH; d += 4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(sK + j * PITCH + d);
-            s = fmaf(qv[d], k4.x, s); s = fmaf(qv[d + 1], k4.y, s); s = fmaf(qv[d + 2], k4.z, s); s = fmaf(qv[d + 3], k4.w, s);
+          for (int nt2 = 0; nt2 < 4; ++nt2)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sc[mt][nt2][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < DH / 8; ++ks) {
+          uint32_t a[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t* q0 = sA + (16 * mt + g) * PITCH + 8 * ks + t;
+            a[mt][0] = q0[0]; a[mt][1] = q0[8 * PITCH]; a[mt][2] = q0[4]; a[mt][3] = q0[8 * PITCH + 4];
           }
-          sc[j] = s;
-          mx = fmaxf(mx, s);
-        }
-        float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
-        const float inv = 1.0f / sum;
-        float acc[DH];
-#pragma unroll
-        for (int d = 0; d < DH; ++d) acc[d] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pj = sc[j] * inv;
-#pragma unroll
-          for (int d = 0; d < DH; d += 4) {
-            const float4 v4 = *reinterpret_cast<const float4*>(sV + j * PITCH + d);
-            acc[d] = fmaf(pj, v4.x, acc[d]); acc[d + 1] = fmaf(pj, v4.y, acc[d + 1]);
-            acc[d + 2] = fmaf(pj, v4.z, acc[d + 2]); acc[d + 3] = fmaf(pj, v4.w, acc[d + 3]);
+          for (int nt2 = 0; nt2 < 4; ++nt2) {
+            const uint32_t* k0 = sB + (8 * nt2 + g) * PITCH + 8 * ks + t;
+            const uint32_t b0 = k0[0], b1 = k0[4];
+            mma_tf32_16x8x8(sc[0][nt2], a[0], b0, b1);
+            mma_tf32_16x8x8(sc[1][nt2], a[1], b0, b1);
           }
         }
-        // o head slice -> bf16 -> canonical K-major SWIZZLE_128B operand: 16-byte chunk c of row r lives at
-        // r * 128 + ((c ^ (r & 7)) << 4) inside k-block (column / 64)
-        uint8_t* orow = smem + S::offO + (hc >> 6) * 16384 + r_in_tile * 128u;
+        __syncwarp();
+        // v rows take over the q tile (q is no longer needed)
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          const uint32_t ch = static_cast<uint32_t>(((hc & 63) >> 3) + c);
-          *reinterpret_cast<uint4*>(orow + ((ch ^ swz) << 4)) =
-              make_uint4(pack_bf16x2(acc[8 * c], acc[8 * c + 1]), pack_bf16x2(acc[8 * c + 2], acc[8 * c + 3]),
-                         pack_bf16x2(acc[8 * c + 4], acc[8 * c + 5]), pack_bf16x2(acc[8 * c + 6], acc[8 * c + 7]));
+        for (int d = 0; d < DH; d += 4)
+          *reinterpret_cast<uint4*>(sA + lane * PITCH + d) = make_uint4(to_tf32(vv[d]), to_tf32(vv[d + 1]), to_tf32(vv[d + 2]), to_tf32(vv[d + 3]));
+        // ---- row softmax (max-subtracted exp / sum, fp32): a row lives in the 4 lanes of a quad, 8 values per lane
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt2 = 0; nt2 < 4; ++nt2) mx = fmaxf(mx, fmaxf(sc[mt][nt2][2 * hr], sc[mt][nt2][2 * hr + 1]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt2 = 0; nt2 < 4; ++nt2) {
+              const float e0 = __expf(sc[mt][nt2][2 * hr] - mx), e1 = __expf(sc[mt][nt2][2 * hr + 1] - mx);
+              sc[mt][nt2][2 * hr] = e0; sc[mt][nt2][2 * hr + 1] = e1;
+              sum += e0 + e1;
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int nt2 = 0; nt2 < 4; ++nt2) { sc[mt][nt2][2 * hr] *= inv; sc[mt][nt2][2 * hr + 1] *= inv; }
+          }
         }
+        __syncwarp();
+        // ---- O = P V: the probabilities feed the second product straight from the accumulator registers (within a
+        // block of 8 keys, k-slot t holds key 2t and slot t + 4 key 2t + 1; the V fragment is read with the same
+        // permutation -- a sum over keys does not care about their order)
+        float acc[2][DH / 8][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int n2 = 0; n2 < DH / 8; ++n2)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][n2][i] = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          uint32_t a[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            a[mt][0] = to_tf32(sc[mt][kb][0]); a[mt][1] = to_tf32(sc[mt][kb][2]);
+            a[mt][2] = to_tf32(sc[mt][kb][1]); a[mt][3] = to_tf32(sc[mt][kb][3]);
+          }
+#pragma unroll
+          for (int n2 = 0; n2 < DH / 8; ++n2) {
+            const uint32_t* v0 = sA + (8 * kb + 2 * t) * PITCH + 8 * n2 + g;
+            const uint32_t b0 = v0[0], b1 = v0[PITCH];
+            mma_tf32_16x8x8(acc[0][n2], a[0], b0, b1);
+            mma_tf32_16x8x8(acc[1][n2], a[1], b0, b1);
+          }
+        }
+        // o head slice -> bf16 -> canonical K-major SWIZZLE_128B operand of the out-projection: 16-byte chunk c of row r
+        // lives at r * 128 + ((c ^ (r & 7)) << 4) inside k-block (column / 64); a lane owns column pairs of 4 rows
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int n2 = 0; n2 < DH / 8; ++n2)
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+              const uint32_t rr = q * 32u + static_cast<uint32_t>(16 * mt + g + 8 * hr);
+              const int col = hc + 8 * n2 + 2 * t;
+              uint8_t* dst = smem + S::offO + (col >> 6) * 16384 + rr * 128u +
+                             (((static_cast<uint32_t>(col & 63) >> 3) ^ (rr & 7u)) << 4) + static_cast<uint32_t>(col & 7) * 2u;
+              *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[mt][n2][2 * hr], acc[mt][n2][2 * hr + 1]);
+            }
       }
       // q/k/v accumulators drained and this warp's part of O written
       tcgen05_fence_before();
