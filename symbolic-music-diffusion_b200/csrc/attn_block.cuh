@@ -21,6 +21,7 @@
 #pragma once
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
+#include "row_epilogue.cuh"
 
 namespace smd {
 
@@ -47,7 +48,8 @@ struct AttnSmem {
   static constexpr int offScr = offBar + kBarBytes;
   static constexpr int kEpiWarps = 16;
   static constexpr int kKvFloats = 2 * 32 * 20;          // k and v tiles of one head: [32][dh + 4], dh <= 16
-  static constexpr int kScrPerWarp = kKvFloats;          // (also holds the 2 x 32 LayerNorm partials of the final epilogue)
+  static constexpr int kScrPerWarp = kKvFloats;          // later the 32 x 32 transpose tile + 2 x 32 LayerNorm partials of the final epilogue
+  static_assert(kScrPerWarp >= 1024 + 64, "scratch too small for the final epilogue");
   static constexpr int kScrBytes = kEpiWarps * kScrPerWarp * 4;
   static constexpr int kTotal = offScr + kScrBytes + 1024;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
@@ -208,7 +210,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t nt = 0;
     for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
       const int row = tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(r_in_tile);
-      const bool row_ok = row < p.M;
+      [[maybe_unused]] const bool row_ok = row < p.M;
       mbar_wait(qkv_full, nt & 1u);
       tcgen05_fence_after();
       for (int hh = 0; hh < heads_per_warp; ++hh) {
@@ -333,64 +335,24 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       fence_proxy_async_smem();    // O stores become visible to the tensor core's (async proxy) reads
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(o_full_l);
-      // ---------------- final epilogue: D2 + bo + residual -> LayerNorm ----------------
-      const int c0 = eg * 32;
-      mbar_wait(d2_full, nt & 1u);
-      tcgen05_fence_after();
-      __syncwarp();
-      uint32_t r[32];
-      tmem_ld_32x32(lane_base + 384u + static_cast<uint32_t>(c0), r);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(d2_empty_l);
-      float xv[32];
-      float s1 = 0.f, s2 = 0.f;
+      // ---------------- final epilogue: D2 + bo + residual -> LayerNorm (csrc/row_epilogue.cuh) ----------------
       {
-        const float4* b4 = reinterpret_cast<const float4*>(p.b_o + c0);
-        const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row_ok ? row : 0) * 128 + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + i);
-          const float4 rr = row_ok ? r4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-          xv[4 * i] = __uint_as_float(r[4 * i]) + bb.x + rr.x;
-          xv[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y + rr.y;
-          xv[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z + rr.z;
-          xv[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w + rr.w;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { s1 += xv[i]; s2 += xv[i] * xv[i]; }
-      if (row_ok) {
-        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * 128 + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o4[i] = make_float4(xv[4 * i], xv[4 * i + 1], xv[4 * i + 2], xv[4 * i + 3]);
-      }
-      // row statistics: each of the four warps of a quadrant saw 32 of the 128 columns
-      scr[lane * 2] = s1; scr[lane * 2 + 1] = s2;
-      asm volatile("bar.sync %0, 128;" ::"r"(1u + q) : "memory");
-      float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const float* sp = scr_all + (static_cast<uint32_t>(g4) * 4u + q) * S::kScrPerWarp + lane * 2;
-        t1 += sp[0]; t2 += sp[1];
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1u + q) : "memory");
-      const float mean = t1 * (1.0f / 128.0f);
-      const float rstd = rsqrtf(t2 * (1.0f / 128.0f) - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
-      if (row_ok) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + c0);
-        const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + c0);
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * 128 + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 g0 = __ldg(g4 + 2 * i), g1 = __ldg(g4 + 2 * i + 1), e0 = __ldg(b4 + 2 * i), e1 = __ldg(b4 + 2 * i + 1);
-          const float* x = &xv[8 * i];
-          dst[i] = make_uint4(pack_bf16x2((x[0] - mean) * (rstd * g0.x) + e0.x, (x[1] - mean) * (rstd * g0.y) + e0.y),
-                              pack_bf16x2((x[2] - mean) * (rstd * g0.z) + e0.z, (x[3] - mean) * (rstd * g0.w) + e0.w),
-                              pack_bf16x2((x[4] - mean) * (rstd * g1.x) + e1.x, (x[5] - mean) * (rstd * g1.y) + e1.y),
-                              pack_bf16x2((x[6] - mean) * (rstd * g1.z) + e1.z, (x[7] - mean) * (rstd * g1.w) + e1.w));
-        }
+        const int c0 = eg * 32;
+        const RowEpiArgs ea{p.b_o, p.residual, p.out_f32, p.ln_gamma, p.ln_beta, p.out_bf16, p.M};
+        const int row0 = tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(q) * 32;
+        float4 pre[8];
+        row_epi_prefetch(ea, row0, c0, lane, pre);
+        mbar_wait(d2_full, nt & 1u);
+        tcgen05_fence_after();
+        __syncwarp();
+        row_epi_stage(pre, scr, lane);         // the warp's q/k/v tiles are dead: the scratch becomes its transpose tile
+        uint32_t r[32];
+        tmem_ld_32x32(lane_base + 384u + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(d2_empty_l);
+        row_epi_finish(ea, r, scr, scr + 1024, scr_all + 1024, S::kScrPerWarp, q, row0, c0, lane);
       }
     }
   }

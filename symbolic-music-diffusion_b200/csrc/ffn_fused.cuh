@@ -13,12 +13,13 @@
 // full-row LayerNorm (partials exchanged between the two warps of a TMEM lane quadrant), fp32 residual stream and
 // bf16 operand for the next GEMM.
 //
-// Warp roles (640 threads): 0 TMA producer (A tile once per tile; W1 chunks 3-deep, W2 chunks 2-deep rings; each
+// Warp roles (640 threads): 0 / 3 TMA producers (A tile once per tile and W1 chunks, 4-deep ring / W2 chunks, 3-deep; each
 // CTA stages its own 128 A rows and its half of every weight chunk), 1 MMA issuer (leader CTA), 2 TMEM allocator,
-// 4..19 epilogue (four per TMEM lane quadrant, 32 columns of every chunk each).  Every cross-CTA hand-off is an mbarrier: tcgen05.commit multicasts "slot free / accumulator
+// 4..19 epilogue: two groups of 8 (two per TMEM lane quadrant, 64 columns each); group g converts chunks j = g (mod 2).  Every cross-CTA hand-off is an mbarrier: tcgen05.commit multicasts "slot free / accumulator
 // ready" to both CTAs, epilogue warps of both CTAs arrive remotely on the leader's "D1 drained / H written" barriers.
 #pragma once
 #include "gemm_tcgen05.cuh"
+#include "row_epilogue.cuh"
 
 namespace smd {
 
@@ -38,7 +39,7 @@ struct FfnFusedArgs {
 struct FfnSmem {
   static constexpr int kA = 32768;          // [2 k-blocks][128 rows][128 B]
   static constexpr int kW = 16384;          // per-CTA half of a weight chunk: [2 k-blocks][64 k][64 n]
-  static constexpr int kW1Stages = 3, kW2Stages = 2, kHStages = 2;
+  static constexpr int kW1Stages = 4, kW2Stages = 3, kHStages = 2;
   static constexpr int kH = 32768;          // [2 k-blocks][128 rows][128 B]
   static constexpr int offA = 0;
   static constexpr int offW1 = offA + kA;
@@ -64,17 +65,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::offBar);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
-  uint64_t* w1_full = bars + 2;     // [3]
-  uint64_t* w1_empty = bars + 5;    // [3]
-  uint64_t* w2_full = bars + 8;     // [2]
-  uint64_t* w2_empty = bars + 10;   // [2]
-  uint64_t* d1_full = bars + 12;    // [2]
-  uint64_t* d1_empty = bars + 14;   // [2]
-  uint64_t* h_full = bars + 16;     // [2]
-  uint64_t* h_empty = bars + 18;    // [2]
-  uint64_t* d2_full = bars + 20;
-  uint64_t* d2_empty = bars + 21;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* d2_full = bars + 2;
+  uint64_t* d2_empty = bars + 3;
+  uint64_t* d1_full = bars + 4;     // [2]
+  uint64_t* d1_empty = bars + 6;    // [2]
+  uint64_t* h_full = bars + 8;      // [2]
+  uint64_t* h_empty = bars + 10;    // [2]
+  uint64_t* w1_full = bars + 12;    // [kW1Stages]
+  uint64_t* w1_empty = w1_full + S::kW1Stages;
+  uint64_t* w2_full = w1_empty + S::kW1Stages;
+  uint64_t* w2_empty = w2_full + S::kW2Stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w2_empty + S::kW2Stages);
+  static_assert((12 + 2 * S::kW1Stages + 2 * S::kW2Stages) * 8 + 8 <= S::kBarBytes, "barrier block too small");
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -92,11 +94,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && elect_one()) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+    for (int i = 0; i < S::kW1Stages; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+    for (int i = 0; i < S::kW2Stages; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1);
-      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 2 * S::kEpiWarps);
-      mbar_init(&h_full[i], 2 * S::kEpiWarps); mbar_init(&h_empty[i], 1);
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], S::kEpiWarps);   // one 8-warp group per CTA serves a buffer
+      mbar_init(&h_full[i], S::kEpiWarps); mbar_init(&h_empty[i], 1);
     }
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, 2 * S::kEpiWarps);
@@ -113,36 +115,39 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: A tiles and W1 chunks =====================
     if (elect_one()) {
       const uint32_t a_full_l = mapa_shared(smem_u32(a_full), 0);
-      uint32_t n1 = 0, n2 = 0, nt = 0;
+      uint32_t n1 = 0, nt = 0;
       for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
         const int m_row0 = tile * 256 + static_cast<int>(rank) * 128;
         mbar_wait(a_empty, (nt & 1u) ^ 1u);
         if (leader) mbar_arrive_expect_tx(a_full, 2u * S::kA);
         for (int kb = 0; kb < 2; ++kb) tma_load_2d_2sm(&tmA, a_full_l, smem + S::offA + kb * 16384, 64 * kb, m_row0);
-        for (int j = 0; j < nchunks; ++j) {
-          {
-            const uint32_t s = n1 % 3u;
-            mbar_wait(&w1_empty[s], ((n1 / 3u) & 1u) ^ 1u);
-            if (leader) mbar_arrive_expect_tx(&w1_full[s], 2u * S::kW);
-            const uint32_t bar = mapa_shared(smem_u32(&w1_full[s]), 0);
-            uint8_t* dst = smem + S::offW1 + s * S::kW;
-            for (int kb = 0; kb < 2; ++kb)   // W1 is [K = 128][N = Md]: box = 64 n x 64 k
-              tma_load_2d_2sm(&tmW1, bar, dst + kb * 8192, j * 128 + static_cast<int>(rank) * 64, 64 * kb);
-            ++n1;
-          }
-          {
-            const uint32_t s = n2 % 2u;
-            mbar_wait(&w2_empty[s], ((n2 / 2u) & 1u) ^ 1u);
-            if (leader) mbar_arrive_expect_tx(&w2_full[s], 2u * S::kW);
-            const uint32_t bar = mapa_shared(smem_u32(&w2_full[s]), 0);
-            uint8_t* dst = smem + S::offW2 + s * S::kW;
-            for (int kb = 0; kb < 2; ++kb)   // W2 is [K = Md][N = 128]
-              tma_load_2d_2sm(&tmW2, bar, dst + kb * 8192, static_cast<int>(rank) * 64, j * 128 + 64 * kb);
-            ++n2;
-          }
+        for (int j = 0; j < nchunks; ++j, ++n1) {
+          const uint32_t s = n1 % S::kW1Stages;
+          mbar_wait(&w1_empty[s], ((n1 / S::kW1Stages) & 1u) ^ 1u);
+          if (leader) mbar_arrive_expect_tx(&w1_full[s], 2u * S::kW);
+          const uint32_t bar = mapa_shared(smem_u32(&w1_full[s]), 0);
+          uint8_t* dst = smem + S::offW1 + s * S::kW;
+          for (int kb = 0; kb < 2; ++kb)   // W1 is [K = 128][N = Md]: box = 64 n x 64 k
+            tma_load_2d_2sm(&tmW1, bar, dst + kb * 8192, j * 128 + static_cast<int>(rank) * 64, 64 * kb);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer: W2 chunks (its own thread, so a full W2 ring never holds W1 back) ==========
+    if (elect_one()) {
+      uint32_t n2 = 0;
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        for (int j = 0; j < nchunks; ++j, ++n2) {
+          const uint32_t s = n2 % S::kW2Stages;
+          mbar_wait(&w2_empty[s], ((n2 / S::kW2Stages) & 1u) ^ 1u);
+          if (leader) mbar_arrive_expect_tx(&w2_full[s], 2u * S::kW);
+          const uint32_t bar = mapa_shared(smem_u32(&w2_full[s]), 0);
+          uint8_t* dst = smem + S::offW2 + s * S::kW;
+          for (int kb = 0; kb < 2; ++kb)   // W2 is [K = Md][N = 128]
+            tma_load_2d_2sm(&tmW2, bar, dst + kb * 8192, static_cast<int>(rank) * 64, j * 128 + 64 * kb);
         }
       }
     }
@@ -155,8 +160,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
         mbar_wait(a_full, nt & 1u);
         auto gemm1 = [&](bool last) {
-          const uint32_t s = n1 % 3u, b = nd1 & 1u;
-          mbar_wait(&w1_full[s], (n1 / 3u) & 1u);
+          const uint32_t s = n1 % S::kW1Stages, b = nd1 & 1u;
+          mbar_wait(&w1_full[s], (n1 / S::kW1Stages) & 1u);
           mbar_wait_cluster(&d1_empty[b], ((nd1 >> 1) & 1u) ^ 1u);
           tcgen05_fence_after();
           const uint32_t sW = smem_u32(smem + S::offW1 + s * S::kW);
@@ -174,11 +179,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ++n1; ++nd1;
         };
         gemm1(nchunks == 1);
+        if (nchunks > 1) gemm1(nchunks == 2);
         for (int j = 0; j < nchunks; ++j) {
-          if (j + 1 < nchunks) gemm1(j + 2 == nchunks);
-          const uint32_t hb = nh & 1u, s2 = n2 % 2u;
+          if (j + 2 < nchunks) gemm1(j + 3 == nchunks);   // waits only for chunk j's accumulator drain, not for its H
+          const uint32_t hb = nh & 1u, s2 = n2 % S::kW2Stages;
           mbar_wait_cluster(&h_full[hb], (nh >> 1) & 1u);
-          mbar_wait(&w2_full[s2], (n2 / 2u) & 1u);
+          mbar_wait(&w2_full[s2], (n2 / S::kW2Stages) & 1u);
           if (j == 0) mbar_wait_cluster(d2_empty, (nt & 1u) ^ 1u);
           tcgen05_fence_after();
           const uint32_t sH = smem_u32(smem + S::offH + hb * S::kH);
@@ -201,7 +207,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
     const uint32_t q = warp & 3u;                      // TMEM lane quadrant
-    const int eg = static_cast<int>(warp - 4u) >> 2;   // which 32-column quarter of a 128-column chunk
+    const int eg = static_cast<int>(warp - 4u) >> 2;   // final epilogue: which 32-column quarter of the 128-wide output
+    const int grp = eg >> 1, half = eg & 1;            // chunk loop: group (chunk parity) and 64-column half of a chunk
     float* scr_all = reinterpret_cast<float*>(smem + S::offScr);
     float* scr = scr_all + (warp - 4u) * 64;
     const uint32_t d1_empty_l0 = mapa_shared(smem_u32(&d1_empty[0]), 0), d1_empty_l1 = mapa_shared(smem_u32(&d1_empty[1]), 0);
@@ -210,133 +217,105 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t r_in_tile = q * 32u + lane;         // row of this thread inside the CTA's 128-row tile
     const uint32_t swz = r_in_tile & 7u;
     const int c0 = eg * 32;                            // this warp's columns inside a chunk / inside the 128-wide output
-    uint32_t nd1 = 0, nh = 0, nt = 0;
+    uint32_t ng = 0, nt = 0;
     for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
       const int row = tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(r_in_tile);
-      const bool row_ok = row < p.M;
-      for (int j = 0; j < nchunks; ++j) {
-        const uint32_t b = nd1 & 1u, hb = nh & 1u;
-        const int gcol = j * 128 + c0;                 // hidden-unit index
-        float4 bq[8];
-        {
-          const float4* b4 = reinterpret_cast<const float4*>(p.b1 + gcol);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bq[i] = __ldg(b4 + i);
-        }
-        mbar_wait(&d1_full[b], (nd1 >> 1) & 1u);
+      [[maybe_unused]] const bool row_ok = row < p.M;
+      // chunk j belongs to warp group j & 1 (D1 buffer and H buffer j & 1 as well): while one group converts its chunk
+      // the other is half a period away, so TMEM-load / barrier latencies of one hide under the math of the other
+      for (int jj = 0; jj < nchunks / 2; ++jj, ++ng) {
+        const int j = 2 * jj + grp;
+        const uint32_t ph = ng & 1u;
+        uint8_t* hrow = smem + S::offH + grp * S::kH + half * 16384 + r_in_tile * 128u;
+        mbar_wait(&d1_full[grp], ph);
         tcgen05_fence_after();
         __syncwarp();
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + b * 128u + static_cast<uint32_t>(c0), r);
-        mbar_wait(&h_empty[hb], ((nh >> 1) & 1u) ^ 1u);
-        tmem_ld_wait();
-        // D1[b] is in registers: hand the accumulator back before the math
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(b ? d1_empty_l1 : d1_empty_l0);
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[4 * i] = __uint_as_float(r[4 * i]) + bq[i].x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
-          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
-        }
-        if (kTrain && p.hidden_pre != nullptr && row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.hidden_pre + static_cast<size_t>(row) * p.Md + gcol);
+        for (int ps = 0; ps < 2; ++ps) {
+          const int cc = half * 64 + ps * 32;          // column inside the chunk
+          const int gcol = j * 128 + cc;               // hidden-unit index
+          float4 bq[8];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(p.b1 + gcol);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bq[i] = __ldg(b4 + i);
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + grp * 128u + static_cast<uint32_t>(cc), r);
+          tmem_ld_wait();
+          if (ps == 1) {
+            // D1 is in registers: hand the accumulator back before the math
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(grp ? d1_empty_l1 : d1_empty_l0);
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[4 * i] = __uint_as_float(r[4 * i]) + bq[i].x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
+          }
+          if (kTrain && p.hidden_pre != nullptr && row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.hidden_pre + static_cast<size_t>(row) * p.Md + gcol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                  *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            }
+          }
+          uint4 pk[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-            dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(act_apply(v[8 * i], ACT_GELU_TANH), act_apply(v[8 * i + 1], ACT_GELU_TANH));
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(act_apply(v[8 * i + 2], ACT_GELU_TANH), act_apply(v[8 * i + 3], ACT_GELU_TANH));
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(act_apply(v[8 * i + 4], ACT_GELU_TANH), act_apply(v[8 * i + 5], ACT_GELU_TANH));
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(act_apply(v[8 * i + 6], ACT_GELU_TANH), act_apply(v[8 * i + 7], ACT_GELU_TANH));
+            pk[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
           }
-        }
-        uint4 pk[4];
+          // the previous chunk of this buffer (two chunks back) must have been consumed by its second GEMM
+          if (ps == 0) mbar_wait(&h_empty[grp], ph ^ 1u);
+          // canonical K-major SWIZZLE_128B: 16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4);
+          // columns [cc, cc + 32) of the chunk are k-block cc / 64 (= half), 16-byte chunks (cc % 64) / 8 .. + 3
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(act_apply(v[8 * i], ACT_GELU_TANH), act_apply(v[8 * i + 1], ACT_GELU_TANH));
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(act_apply(v[8 * i + 2], ACT_GELU_TANH), act_apply(v[8 * i + 3], ACT_GELU_TANH));
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(act_apply(v[8 * i + 4], ACT_GELU_TANH), act_apply(v[8 * i + 5], ACT_GELU_TANH));
-          __nv_bfloat162 p3 = __floats2bfloat162_rn(act_apply(v[8 * i + 6], ACT_GELU_TANH), act_apply(v[8 * i + 7], ACT_GELU_TANH));
-          pk[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-        }
-        // canonical K-major SWIZZLE_128B: 16-byte chunk c of row r lives at r * 128 + ((c ^ (r & 7)) << 4);
-        // columns [c0, c0 + 32) of the chunk are k-block c0 / 64, 16-byte chunks (c0 % 64) / 8 .. + 3
-        uint8_t* hrow = smem + S::offH + hb * S::kH + (eg >> 1) * 16384 + r_in_tile * 128u;
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t ch = static_cast<uint32_t>(ps * 4 + i);
+            *reinterpret_cast<uint4*>(hrow + ((ch ^ swz) << 4)) = pk[i];
+          }
+          if (kTrain && p.hidden != nullptr && row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.hidden + static_cast<size_t>(row) * p.Md + gcol);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t ch = static_cast<uint32_t>((eg & 1) * 4 + i);
-          *reinterpret_cast<uint4*>(hrow + ((ch ^ swz) << 4)) = pk[i];
+            for (int i = 0; i < 4; ++i) dst[i] = pk[i];
+          }
         }
         fence_proxy_async_smem();    // this thread's H stores become visible to the tensor core's (async proxy) reads
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(hb ? h_full_l1 : h_full_l0);
-        if (kTrain && p.hidden != nullptr && row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.hidden + static_cast<size_t>(row) * p.Md + gcol);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = pk[i];
-        }
-        ++nd1; ++nh;
+        if (lane == 0) mbar_arrive_cluster(grp ? h_full_l1 : h_full_l0);
       }
-      // ---------------- final epilogue: D2 + b2 + residual -> LayerNorm ----------------
-      mbar_wait(d2_full, nt & 1u);
-      tcgen05_fence_after();
-      __syncwarp();
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + 256u + static_cast<uint32_t>(c0), r);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(d2_empty_l);
-      float vv[32];
-      float s1 = 0.f, s2 = 0.f;
+      // ---------------- final epilogue: D2 + b2 + residual -> LayerNorm (csrc/row_epilogue.cuh) ----------------
+      // the H region is idle between this tile's last second GEMM (d2_full) and the next tile's first chunk: every
+      // warp borrows 4 KB of it as its transpose tile
       {
-        const float4* b4 = reinterpret_cast<const float4*>(p.b2 + c0);
-        const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row_ok ? row : 0) * 128 + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + i);
-          const float4 rr = row_ok ? r4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-          vv[4 * i] = __uint_as_float(r[4 * i]) + bb.x + rr.x;
-          vv[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y + rr.y;
-          vv[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z + rr.z;
-          vv[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w + rr.w;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { s1 += vv[i]; s2 += vv[i] * vv[i]; }
-      if (row_ok) {
-        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * 128 + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o4[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
-      }
-      // row statistics: each of the four warps of a quadrant saw 32 of the 128 columns
-      scr[lane * 2] = s1; scr[lane * 2 + 1] = s2;
-      asm volatile("bar.sync %0, 128;" ::"r"(1u + q) : "memory");
-      float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const float* sp = scr_all + (static_cast<uint32_t>(g4) * 4u + q) * 64 + lane * 2;
-        t1 += sp[0]; t2 += sp[1];
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1u + q) : "memory");
-      const float mean = t1 * (1.0f / 128.0f);
-      const float rstd = rsqrtf(t2 * (1.0f / 128.0f) - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
-      if (row_ok) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + c0);
-        const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + c0);
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row) * 128 + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 g0 = __ldg(g4 + 2 * i), g1 = __ldg(g4 + 2 * i + 1), e0 = __ldg(b4 + 2 * i), e1 = __ldg(b4 + 2 * i + 1);
-          const float* x = &vv[8 * i];
-          __nv_bfloat162 p0 = __floats2bfloat162_rn((x[0] - mean) * (rstd * g0.x) + e0.x, (x[1] - mean) * (rstd * g0.y) + e0.y);
-          __nv_bfloat162 p1 = __floats2bfloat162_rn((x[2] - mean) * (rstd * g0.z) + e0.z, (x[3] - mean) * (rstd * g0.w) + e0.w);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn((x[4] - mean) * (rstd * g1.x) + e1.x, (x[5] - mean) * (rstd * g1.y) + e1.y);
-          __nv_bfloat162 p3 = __floats2bfloat162_rn((x[6] - mean) * (rstd * g1.z) + e1.z, (x[7] - mean) * (rstd * g1.w) + e1.w);
-          dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                              *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-        }
+        const RowEpiArgs ea{p.b2, p.residual, p.out_f32, p.ln_gamma, p.ln_beta, p.out_bf16, p.M};
+        const int row0 = tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(q) * 32;
+        float* tsc = reinterpret_cast<float*>(smem + S::offH) + (warp - 4u) * 1024u;
+        float4 pre[8];
+        row_epi_prefetch(ea, row0, c0, lane, pre);
+        mbar_wait(d2_full, nt & 1u);
+        tcgen05_fence_after();
+        __syncwarp();
+        row_epi_stage(pre, tsc, lane);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + 256u + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(d2_empty_l);
+        row_epi_finish(ea, r, tsc, scr, scr_all, 64, q, row0, c0, lane);
+        // the next tile's H stores of any warp may land in any warp's transpose tile
+        asm volatile("bar.sync 5, %0;" ::"n"(32 * S::kEpiWarps) : "memory");
       }
     }
   }
