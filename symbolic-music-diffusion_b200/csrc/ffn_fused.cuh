@@ -249,31 +249,38 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(grp ? d1_empty_l1 : d1_empty_l0);
           }
-          float v[32];
+          // bias add and GELU on packed fp32 pairs (FADD2 / FMUL2 / FFMA2): half the issue slots of the scalar form
+          uint64_t v2[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            v[4 * i] = __uint_as_float(r[4 * i]) + bq[i].x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq[i].y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq[i].z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq[i].w;
+            v2[2 * i] = f32x2_add(f32x2_pack(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), f32x2_pack(bq[i].x, bq[i].y));
+            v2[2 * i + 1] = f32x2_add(f32x2_pack(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), f32x2_pack(bq[i].z, bq[i].w));
           }
           if (kTrain && p.hidden_pre != nullptr && row_ok) {
             uint4* dst = reinterpret_cast<uint4*>(p.hidden_pre + static_cast<size_t>(row) * p.Md + gcol);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                  *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float a, b;
+                f32x2_unpack(v2[4 * i + k], a, b);
+                w[k] = pack_bf16x2(a, b);
+              }
+              dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
           uint4 pk[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(act_apply(v[8 * i], ACT_GELU_TANH), act_apply(v[8 * i + 1], ACT_GELU_TANH));
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(act_apply(v[8 * i + 2], ACT_GELU_TANH), act_apply(v[8 * i + 3], ACT_GELU_TANH));
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(act_apply(v[8 * i + 4], ACT_GELU_TANH), act_apply(v[8 * i + 5], ACT_GELU_TANH));
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(act_apply(v[8 * i + 6], ACT_GELU_TANH), act_apply(v[8 * i + 7], ACT_GELU_TANH));
-            pk[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float a, b;
+              f32x2_unpack(gelu_tanh_x2(v2[4 * i + k]), a, b);
+              w[k] = pack_bf16x2(a, b);
+            }
+            pk[i] = make_uint4(w[0], w[1], w[2], w[3]);
           }
           // the previous chunk of this buffer (two chunks back) must have been consumed by its second GEMM
           if (ps == 0) mbar_wait(&h_empty[grp], ph ^ 1u);

@@ -163,6 +163,41 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot per two elements; every lane op is the same
+// round-to-nearest fp32 operation as the scalar form, so results are bit-identical to act_apply().
+__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// tanh-GELU of the pair v (same operation order as act_apply(ACT_GELU_TANH))
+__device__ __forceinline__ uint64_t gelu_tanh_x2(uint64_t v) {
+  const float c = 0.7978845608028654f, cc = 0.044715f * c;
+  const uint64_t t = f32x2_fma(f32x2_mul(v, v), f32x2_pack(cc, cc), f32x2_pack(c, c));
+  float u0, u1;
+  f32x2_unpack(f32x2_mul(v, t), u0, u1);
+  const uint64_t h = f32x2_mul(v, f32x2_pack(0.5f, 0.5f));
+  return f32x2_fma(h, f32x2_pack(tanh_fast(u0), tanh_fast(u1)), h);
+}
+
 template <int kCG, uint32_t kF, int kEW = 8>
 __global__ void __launch_bounds__(128 + 32 * kEW, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

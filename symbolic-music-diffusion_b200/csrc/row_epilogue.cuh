@@ -3,9 +3,9 @@
 // (models/ncsn.py:160-166: "+ shortcut" followed by the next sub-block's LayerNorm; flax LayerNorm = E[x^2] - E[x]^2,
 // eps 1e-6).  tcgen05.ld hands every thread one ROW of the accumulator, so reading the residual / writing the outputs
 // straight from that layout makes each warp instruction touch 32 different 128-byte lines.  Instead every global
-// access goes through a warp-private 32 x 32 fp32 transpose tile in shared memory (element (r, c) at r * 32 + (c ^ r):
-// conflict-free both for "lane = row" and for "lane = column group" accesses), so a warp instruction covers whole
-// 128-byte rows.
+// access goes through a warp-private 32 x 32 fp32 transpose tile in shared memory (16-byte chunk j of row r at chunk
+// slot j ^ (r & 7): 128-bit accesses are conflict-free both for "lane = row" and for "8 lanes = one row"), so a warp
+// instruction covers whole 128-byte rows.
 #pragma once
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -33,13 +33,14 @@ __device__ __forceinline__ void row_epi_prefetch(const RowEpiArgs& p, int row0, 
   }
 }
 
+// transpose tile addressing: row r is 8 chunks of 4 floats, chunk j of row r lives at float4 index r * 8 + (j ^ (r & 7))
+__device__ __forceinline__ float4* row_epi_chunk(float* tsc, uint32_t r, uint32_t j) {
+  return reinterpret_cast<float4*>(tsc) + (r * 8u + (j ^ (r & 7u)));
+}
+
 __device__ __forceinline__ void row_epi_stage(const float4 (&pre)[8], float* tsc, uint32_t lane) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const uint32_t rr = static_cast<uint32_t>(it) * 4u + (lane >> 3), cc = 4u * (lane & 7u);
-    float* d = tsc + rr * 32u;
-    d[cc ^ rr] = pre[it].x; d[(cc + 1u) ^ rr] = pre[it].y; d[(cc + 2u) ^ rr] = pre[it].z; d[(cc + 3u) ^ rr] = pre[it].w;
-  }
+  for (int it = 0; it < 8; ++it) *row_epi_chunk(tsc, static_cast<uint32_t>(it) * 4u + (lane >> 3), lane & 7u) = pre[it];
   __syncwarp();
 }
 
@@ -55,27 +56,27 @@ __device__ __forceinline__ void row_epi_finish(const RowEpiArgs& p, const uint32
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 bb = __ldg(b4 + i);
-      const float* t = tsc + lane * 32u;
-      v[4 * i] = __uint_as_float(acc[4 * i]) + bb.x + t[(4u * i) ^ lane];
-      v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bb.y + t[(4u * i + 1u) ^ lane];
-      v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bb.z + t[(4u * i + 2u) ^ lane];
-      v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bb.w + t[(4u * i + 3u) ^ lane];
+      const float4 rr = *row_epi_chunk(tsc, lane, static_cast<uint32_t>(i));
+      v[4 * i] = __uint_as_float(acc[4 * i]) + bb.x + rr.x;
+      v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bb.y + rr.y;
+      v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bb.z + rr.z;
+      v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bb.w + rr.w;
     }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) tsc[lane * 32u + (static_cast<uint32_t>(i) ^ lane)] = v[i];
+  for (int i = 0; i < 8; ++i)
+    *row_epi_chunk(tsc, lane, static_cast<uint32_t>(i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const uint32_t rr = static_cast<uint32_t>(it) * 4u + (lane >> 3), cc = 4u * (lane & 7u);
+    const uint32_t rr = static_cast<uint32_t>(it) * 4u + (lane >> 3);
     const int grow = row0 + static_cast<int>(rr);
-    const float* s = tsc + rr * 32u;
     if (grow < p.M)
-      *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(grow) * 128 + c0 + cc) =
-          make_float4(s[cc ^ rr], s[(cc + 1u) ^ rr], s[(cc + 2u) ^ rr], s[(cc + 3u) ^ rr]);
+      *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(grow) * 128 + c0 + 4u * (lane & 7u)) =
+          *row_epi_chunk(tsc, rr, lane & 7u);
   }
   // row statistics: each of the four warps of a quadrant saw 32 of the 128 columns
   stat_mine[lane * 2] = s1; stat_mine[lane * 2 + 1] = s2;
@@ -92,29 +93,25 @@ __device__ __forceinline__ void row_epi_finish(const RowEpiArgs& p, const uint32
   {
     const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + c0);
     const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + c0);
-    float* t = tsc + lane * 32u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 g = __ldg(g4 + i), e = __ldg(b4 + i);
-      t[(4u * i) ^ lane] = (v[4 * i] - mean) * (rstd * g.x) + e.x;
-      t[(4u * i + 1u) ^ lane] = (v[4 * i + 1] - mean) * (rstd * g.y) + e.y;
-      t[(4u * i + 2u) ^ lane] = (v[4 * i + 2] - mean) * (rstd * g.z) + e.z;
-      t[(4u * i + 3u) ^ lane] = (v[4 * i + 3] - mean) * (rstd * g.w) + e.w;
+      *row_epi_chunk(tsc, lane, static_cast<uint32_t>(i)) =
+          make_float4((v[4 * i] - mean) * (rstd * g.x) + e.x, (v[4 * i + 1] - mean) * (rstd * g.y) + e.y,
+                      (v[4 * i + 2] - mean) * (rstd * g.z) + e.z, (v[4 * i + 3] - mean) * (rstd * g.w) + e.w);
     }
   }
   __syncwarp();
-  // bf16 rows are 64 bytes: lane -> row 8 it + lane / 4, columns 8 (lane % 4) .. + 7
+  // bf16 rows are 64 bytes: lane -> row 8 it + lane / 4, columns 8 (lane % 4) .. + 7 (two chunks)
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const uint32_t rr = static_cast<uint32_t>(it) * 8u + (lane >> 2), cb = 8u * (lane & 3u);
+    const uint32_t rr = static_cast<uint32_t>(it) * 8u + (lane >> 2), cj = 2u * (lane & 3u);
     const int grow = row0 + static_cast<int>(rr);
-    const float* s = tsc + rr * 32u;
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(s[cb ^ rr], s[(cb + 1u) ^ rr]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(s[(cb + 2u) ^ rr], s[(cb + 3u) ^ rr]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(s[(cb + 4u) ^ rr], s[(cb + 5u) ^ rr]);
-    __nv_bfloat162 p3 = __floats2bfloat162_rn(s[(cb + 6u) ^ rr], s[(cb + 7u) ^ rr]);
+    const float4 a = *row_epi_chunk(tsc, rr, cj), b = *row_epi_chunk(tsc, rr, cj + 1u);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
     if (grow < p.M)
-      *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(grow) * 128 + c0 + cb) =
+      *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(grow) * 128 + c0 + 4u * cj) =
           make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                      *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
   }
