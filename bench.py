@@ -412,6 +412,12 @@ def run_gpu(args):
         wl = f"sample ddpm-mel-32seq-512.cfg (TransformerDDPM L6 H8 K2 M2048 C42), {B} samples/GPU, 1 reverse step"
     eng = job["eng"]
 
+    # multi-rank runs: NCCL finishes setting up its channels / buffer registrations during the first few dozen
+    # collectives (measured at 2 and 8 GPUs: the first ~25 steps run 5-20 % slower, profiles/r02_dp_warmup_ab.txt), so
+    # a fixed number of extra untimed steps runs before the W warm-up steps; K timed steps stay exactly K
+    settle = 30 if world > 1 else 0
+    for i in range(settle):
+        job["resident"](100000 + i)
     clocks = ClockSampler(ctx.local)
     clocks.start()
     ms_step, launches = ctx.timed(job["resident"], args.steps, args.warmup, eng)
@@ -430,7 +436,8 @@ def run_gpu(args):
                        "step_frac_of_sustained_peak": flops_step / (ms_step / 1e3) / 1e12 / ctx.tsust,
                        "l2": "per-step working set (params+grads+Adam ~400 MB, activations ~1 GB) >> 126 MB L2; no flush",
                        "precision": "bf16 tensor-core operands, fp32 accumulate / master weights / LN / softmax / Adam",
-                       "rng": "device threefry draws (labels, alpha-bar, eps) are inside the timed step"},
+                       "rng": "device threefry draws (labels, alpha-bar, eps) are inside the timed step",
+                       "untimed_settle_steps": settle},
             "clocks": clocks.summary(),
             "e2e": {"value": units * world / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": job["h2d"], "d2h_bytes_per_step": job["d2h"]},

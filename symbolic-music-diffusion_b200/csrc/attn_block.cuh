@@ -8,6 +8,7 @@
 // One CTA pair (cta_group::2) owns 256 tokens = 8 samples of 32 positions; each CTA holds 4 samples, one per TMEM lane
 // quadrant, so a warp's 32 TMEM lanes are exactly the 32 positions of one sample.
 //   GEMM qkv : D[0:384) (TMEM) = A[256 x 128] . Wqkv[128 x 384]          (three N = 128 MMAs per k-step, K = 128)
+//   (kTrain additionally stores q | k | v, the probabilities and the attention output for the backward pass)
 //   attention: 16 epilogue warps (4 per quadrant); a warp handles H/4 heads of its sample, one at a time: q/k/v head
 //              slices TMEM -> registers (+ bias, q / sqrt(dh)) -> tf32 rows in a per-warp shared-memory tile -> Q K^T and
 //              P V on mma.sync m16n8k8 tf32 (a 32x32x16 problem per head is far below a tcgen05 tile), fp32 softmax
@@ -33,6 +34,10 @@ struct AttnBlockArgs {
   const float* ln_gamma;         // [128] LayerNorm of the new residual stream -> out_bf16
   const float* ln_beta;
   __nv_bfloat16* out_bf16;       // bf16 [M][128]
+  // training (kTrain): what the backward pass needs (csrc/backward.cu), in the layouts of the three-launch path
+  float* qkv_out;                // fp32 [M][384] = (q | k | v) + bias, q unscaled
+  float* probs_out;              // fp32 [M / 32][H][32][32] softmax probabilities
+  __nv_bfloat16* o_out;          // bf16 [M][128] attention output (operand of the out-projection's weight gradient)
   int M, H;                      // tokens; heads (dh = 128 / H in {8, 16})
 };
 
@@ -79,7 +84,7 @@ __device__ __forceinline__ void tmem_ld_head(uint32_t taddr, float (&out)[DH]) {
   }
 }
 
-template <int DH>
+template <int DH, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AttnSmem::kThreads, 1)
 attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWqkv,
                   const __grid_constant__ CUtensorMap tmWo, const AttnBlockArgs p) {
@@ -233,6 +238,14 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           *reinterpret_cast<uint4*>(sB + lane * PITCH + d) =
               make_uint4(to_tf32(kv[d] + bk.x), to_tf32(kv[d + 1] + bk.y), to_tf32(kv[d + 2] + bk.z), to_tf32(kv[d + 3] + bk.w));
           vv[d] += bv.x; vv[d + 1] += bv.y; vv[d + 2] += bv.z; vv[d + 3] += bv.w;
+          if constexpr (kTrain) {
+            if (row_ok) {
+              float* qd = p.qkv_out + static_cast<size_t>(row) * 384 + hc + d;
+              *reinterpret_cast<float4*>(qd) = make_float4(qv[d] + bq.x, qv[d + 1] + bq.y, qv[d + 2] + bq.z, qv[d + 3] + bq.w);
+              *reinterpret_cast<float4*>(qd + 128) = make_float4(kv[d] + bk.x, kv[d + 1] + bk.y, kv[d + 2] + bk.z, kv[d + 3] + bk.w);
+              *reinterpret_cast<float4*>(qd + 256) = make_float4(vv[d], vv[d + 1], vv[d + 2], vv[d + 3]);
+            }
+          }
         }
         __syncwarp();
         // ---- S = (Q / sqrt(dh)) K^T on mma.sync m16n8k8 tf32: 2 m-tiles x 4 n-tiles, DH / 8 k-steps
@@ -288,6 +301,20 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int nt2 = 0; nt2 < 4; ++nt2) { sc[mt][nt2][2 * hr] *= inv; sc[mt][nt2][2 * hr + 1] *= inv; }
           }
         }
+        if constexpr (kTrain) {
+          // accumulator layout = the layout attention_bwd_mma_kernel reads back: rows 16 mt + g (+ 8), keys 8 nt + 2t (+ 1)
+          const int smp = (tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(q) * 32) >> 5;
+          if (smp * 32 < p.M) {
+            float* pr = p.probs_out + (static_cast<size_t>(smp) * p.H + hc / DH) * 1024;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int nt2 = 0; nt2 < 4; ++nt2) {
+                *reinterpret_cast<float2*>(pr + (16 * mt + g) * 32 + 8 * nt2 + 2 * t) = make_float2(sc[mt][nt2][0], sc[mt][nt2][1]);
+                *reinterpret_cast<float2*>(pr + (16 * mt + g + 8) * 32 + 8 * nt2 + 2 * t) = make_float2(sc[mt][nt2][2], sc[mt][nt2][3]);
+              }
+          }
+        }
         __syncwarp();
         // ---- O = P V: the probabilities feed the second product straight from the accumulator registers (within a
         // block of 8 keys, k-slot t holds key 2t and slot t + 4 key 2t + 1; the V fragment is read with the same
@@ -327,7 +354,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int col = hc + 8 * n2 + 2 * t;
               uint8_t* dst = smem + S::offO + (col >> 6) * 16384 + rr * 128u +
                              (((static_cast<uint32_t>(col & 63) >> 3) ^ (rr & 7u)) << 4) + static_cast<uint32_t>(col & 7) * 2u;
-              *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[mt][n2][2 * hr], acc[mt][n2][2 * hr + 1]);
+              const uint32_t ob = pack_bf16x2(acc[mt][n2][2 * hr], acc[mt][n2][2 * hr + 1]);
+              *reinterpret_cast<uint32_t*>(dst) = ob;
+              if constexpr (kTrain) {
+                const int grow = tile * 256 + static_cast<int>(rank) * 128 + static_cast<int>(rr);
+                if (grow < p.M) *reinterpret_cast<uint32_t*>(p.o_out + static_cast<size_t>(grow) * 128 + col) = ob;
+              }
             }
       }
       // q/k/v accumulators drained and this warp's part of O written

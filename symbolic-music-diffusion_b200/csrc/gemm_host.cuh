@@ -291,14 +291,25 @@ inline bool attn_block_enabled() {
   static const bool on = [] { const char* v = getenv("SMD_ATTN_BLOCK"); return !(v && v[0] == '0'); }();
   return on;
 }
+// SMD_ATTN_BLOCK_TRAIN=0: training keeps the three-launch path
+inline bool attn_block_train_enabled() {
+  static const bool on = [] { const char* v = getenv("SMD_ATTN_BLOCK_TRAIN"); return !(v && v[0] == '0'); }();
+  return on;
+}
 inline cudaError_t launch_attn_block(const AttnOp& op, const AttnBlockArgs& a, cudaStream_t st) {
   const int dh = 128 / a.H;
   if (dh != 8 && dh != 16) return cudaErrorInvalidValue;
+  const bool train = a.qkv_out != nullptr;
+  if (train && (a.probs_out == nullptr || a.o_out == nullptr)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_block_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(attn_block_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attn_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    e = cudaFuncSetAttribute(attn_block_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_block_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_block_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -317,8 +328,12 @@ inline cudaError_t launch_attn_block(const AttnOp& op, const AttnBlockArgs& a, c
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (dh == 16) return cudaLaunchKernelEx(&cfg, attn_block_kernel<16>, op.tmA, op.tmWqkv, op.tmWo, a);
-  return cudaLaunchKernelEx(&cfg, attn_block_kernel<8>, op.tmA, op.tmWqkv, op.tmWo, a);
+  if (train) {
+    if (dh == 16) return cudaLaunchKernelEx(&cfg, attn_block_kernel<16, true>, op.tmA, op.tmWqkv, op.tmWo, a);
+    return cudaLaunchKernelEx(&cfg, attn_block_kernel<8, true>, op.tmA, op.tmWqkv, op.tmWo, a);
+  }
+  if (dh == 16) return cudaLaunchKernelEx(&cfg, attn_block_kernel<16, false>, op.tmA, op.tmWqkv, op.tmWo, a);
+  return cudaLaunchKernelEx(&cfg, attn_block_kernel<8, false>, op.tmA, op.tmWqkv, op.tmWo, a);
 }
 
 }  // namespace smd

@@ -525,15 +525,19 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
             !retarget_a(&o2, hidden, p->Mp)) return SMD_ERR_CUDA;
       }
       GemmEpilogue e = epi();
-      if (!save && p->lo_bytes == 0 && p->op_attn[l].ok && attn_block_enabled()) {
-        // inference: QKV GEMM -> attention -> out-projection + residual + LayerNorm in ONE launch; q / k / v stay on chip
+      if (p->lo_bytes == 0 && p->op_attn[l].ok && attn_block_enabled() && (!save || attn_block_train_enabled())) {
+        // QKV GEMM -> attention -> out-projection + residual + LayerNorm in ONE launch; q / k / v stay on chip
+        // (training: they are also written out, with the probabilities and the attention output, for the backward pass)
+        AttnOp ao = p->op_attn[l];
+        if (save && !make_tmap_bf16(&ao.tmA, a1, p->Mp, 128, 128)) return SMD_ERR_CUDA;
         AttnBlockArgs aa;
+        aa.qkv_out = save ? qkv : nullptr; aa.probs_out = save ? probs : nullptr; aa.o_out = save ? o : nullptr;
         aa.b_qkv = p->P(params, pre + "attn.qkv.bias"); aa.b_o = p->P(params, pre + "attn.out.bias");
         aa.residual = h_in; aa.out_f32 = h_mid;
         aa.ln_gamma = p->P(params, pre + "ln2.scale"); aa.ln_beta = p->P(params, pre + "ln2.bias");
         aa.out_bf16 = a2;
         aa.M = M; aa.H = c.num_heads;
-        SMD_CUDA(launch_attn_block(p->op_attn[l], aa, st));
+        SMD_CUDA(launch_attn_block(ao, aa, st));
       } else {
       e.bias = p->P(params, pre + "attn.qkv.bias");
       e.out_f32 = qkv; e.ld_f32 = 3 * kE;
