@@ -334,10 +334,18 @@ static int grads_impl(smd_plan* p, const float* params, const float* x0, const f
     SMD_CUDA(gemm_k(ts.dW1[l], 128, Mk, sp, e, dws));
     e = epi();
     e.out_f32 = da32; e.ld_f32 = 128;
-    SMD_CUDA(launch_gemm(ts.dX1[l], M, e, st));
+    const int fsp = ffn_splits(M, ts.dX1[l].cg);
+    const long long fstride = static_cast<long long>(p->Mp < kFfnSplitRows ? p->Mp : kFfnSplitRows) * 128;
+    GemmOp dx1 = ts.dX1[l];
+    if (fsp > 1) {   // K = mlp_dims, 16 output tiles at batch 128: deterministic split-K, ln128_bwd adds the slabs
+      e.out_f32 = p->buf<float>("ffn.slabs"); e.split_stride = fstride;
+      dx1.k_splits = fsp;
+    }
+    SMD_CUDA(launch_gemm(dx1, M, e, st));
     Ln128BwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.g = da32; a.h = ts.h(ws, 2 * l + 1); a.gamma = p->P(params, pre + "ln2.scale");
+    a.g = e.out_f32; a.g_splits = fsp; a.g_stride = fstride;
+    a.h = ts.h(ws, 2 * l + 1); a.gamma = p->P(params, pre + "ln2.scale");
     a.dres = dh32; a.dx32 = dh32; a.dx16 = B16(ts.off_dh16b[l]);
     a.dgamma = G(pre + "ln2.scale"); a.dbeta = G(pre + "ln2.bias");
     a.dbias = G(pre + "attn.out.bias");

@@ -464,7 +464,9 @@ inline void launch_ln_film_act_bwd(const LnFilmBwdArgs& a, cudaStream_t st) {
 // narrow (128-wide) LayerNorm backward, one warp per row; statistics recomputed from the saved input
 // ---------------------------------------------------------------------------------------------------
 struct Ln128BwdArgs {
-  const float* g;       // [M][128] gradient wrt the LayerNorm output
+  const float* g;       // [M][128] gradient wrt the LayerNorm output; with g_splits > 1 the sum of that many slabs
+  int g_splits;         //   g + s * g_stride (deterministic split-K partials of the producing GEMM), 0 / 1: a single array
+  long long g_stride;
   const float* h;       // [M][128] LayerNorm input
   const float* gamma;   // [128]
   const float* dres;    // [M][128] or null (may alias dx32)
@@ -487,7 +489,11 @@ __global__ void __launch_bounds__(256) ln128_bwd_kernel(const Ln128BwdArgs a) {
   float adg[4] = {0, 0, 0, 0}, adb[4] = {0, 0, 0, 0}, abias[4] = {0, 0, 0, 0};
   for (int row = gw; row < a.M; row += nw) {
     const float4 h4 = *reinterpret_cast<const float4*>(a.h + static_cast<size_t>(row) * 128 + c);
-    const float4 g4 = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * 128 + c);
+    float4 g4 = *reinterpret_cast<const float4*>(a.g + static_cast<size_t>(row) * 128 + c);
+    for (int sp = 1; sp < a.g_splits; ++sp) {     // fixed order: bit-reproducible
+      const float4 t = *reinterpret_cast<const float4*>(a.g + sp * a.g_stride + static_cast<size_t>(row) * 128 + c);
+      g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+    }
     const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
     const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
     float s1 = hh[0] + hh[1] + hh[2] + hh[3];

@@ -291,9 +291,11 @@ inline bool attn_block_enabled() {
   static const bool on = [] { const char* v = getenv("SMD_ATTN_BLOCK"); return !(v && v[0] == '0'); }();
   return on;
 }
-// SMD_ATTN_BLOCK_TRAIN=0: training keeps the three-launch path
+// SMD_ATTN_BLOCK_TRAIN=1: the training forward uses the block kernel too (kTrain: q | k | v, probabilities and the
+// attention output are written out for the backward pass).  Off by default: at batch 128 only 16 CTA pairs are busy and
+// the scattered saves make the launch 34 us against 25 us for the three-launch path (profiles/r02_bench_train_attn*.json).
 inline bool attn_block_train_enabled() {
-  static const bool on = [] { const char* v = getenv("SMD_ATTN_BLOCK_TRAIN"); return !(v && v[0] == '0'); }();
+  static const bool on = [] { const char* v = getenv("SMD_ATTN_BLOCK_TRAIN"); return v && v[0] == '1'; }();
   return on;
 }
 inline cudaError_t launch_attn_block(const AttnOp& op, const AttnBlockArgs& a, cudaStream_t st) {

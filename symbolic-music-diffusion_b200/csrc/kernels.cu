@@ -648,6 +648,52 @@ void launch_pack_transpose_bf16(const float* src, __nv_bfloat16* dst, int K, int
   dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
   pack_transpose_bf16_kernel<<<grid, block, 0, st>>>(src, dst, K, N);
 }
+// ---------------------------------------------------------------------------------------------------
+// split-K tail of the FFN-down projection at small token counts: the GEMM leaves `splits` fp32 partial slabs
+// [M][128]; this kernel adds them in a fixed order with bias and residual and emits the next LayerNorm.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln128_reduce_fwd_kernel(const float* __restrict__ slabs, int splits, long long stride, const float* __restrict__ bias,
+                        const float* residual, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* h_out, __nv_bfloat16* __restrict__ a_out, int M) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + c);
+  const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 e4 = *reinterpret_cast<const float4*>(beta + c);
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const size_t off = static_cast<size_t>(row) * 128 + c;
+    float4 v = *reinterpret_cast<const float4*>(slabs + off);
+    for (int s = 1; s < splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(slabs + s * stride + off);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    const float4 r = *reinterpret_cast<const float4*>(residual + off);
+    v.x += b4.x + r.x; v.y += b4.y + r.y; v.z += b4.z + r.z; v.w += b4.w + r.w;
+    *reinterpret_cast<float4*>(h_out + off) = v;
+    float s1 = v.x + v.y + v.z + v.w;
+    float s2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const float mean = s1 * (1.0f / 128.0f);
+    const float rstd = rsqrtf(s2 * (1.0f / 128.0f) - mean * mean + 1e-6f);   // flax LayerNorm: E[x^2] - E[x]^2, eps 1e-6
+    __nv_bfloat162 p0 = __floats2bfloat162_rn((v.x - mean) * (rstd * g4.x) + e4.x, (v.y - mean) * (rstd * g4.y) + e4.y);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn((v.z - mean) * (rstd * g4.z) + e4.z, (v.w - mean) * (rstd * g4.w) + e4.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(a_out + off) = pk;
+  }
+}
+void launch_ln128_reduce_fwd(const float* slabs, int splits, long long stride, const float* bias, const float* residual,
+                             const float* gamma, const float* beta, float* h_out, __nv_bfloat16* a_out, int M,
+                             cudaStream_t st) {
+  int blocks = (M + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  launch_pdl_g(kPdlLn128, ln128_reduce_fwd_kernel, dim3(blocks), dim3(256), 0, st, slabs, splits, stride, bias, residual,
+               gamma, beta, h_out, a_out, M);
+}
+
 // All weight repacks of one optimizer step in ONE launch: blockmap[b] = (job, tile) for every 64x64 tile.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs,
                                                          const int2* __restrict__ blockmap, long long lo_delta) {

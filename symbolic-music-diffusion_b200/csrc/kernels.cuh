@@ -153,6 +153,11 @@ void launch_embed(const float* x, const float* W_in, const float* b_in, const fl
 
 // unmasked multi-head self-attention over S = 32 positions (flax.nn.SelfAttention core, models/ncsn.py:161)
 // qkv fp32 [M][3E] -> o bf16 [M][E];  optionally saves the probabilities P [B][H][32][32] fp32 for backward
+// h_out = residual + bias + sum of `splits` split-K slabs of the FFN-down GEMM (fixed order); a_out = LayerNorm(h_out)
+// as bf16 (models/ncsn.py:164-166 followed by the next sub-block's LayerNorm).  One warp per 128-wide row.
+void launch_ln128_reduce_fwd(const float* slabs, int splits, long long stride, const float* bias, const float* residual,
+                             const float* gamma, const float* beta, float* h_out, __nv_bfloat16* a_out, int M,
+                             cudaStream_t st);
 void launch_attention(const float* qkv, __nv_bfloat16* o, float* probs_or_null, int B, int H, cudaStream_t st,
                       long long lo_delta = 0);
 

@@ -112,6 +112,8 @@ static void build_workspace(smd_plan* p) {
     ws_add(p, "qkv", Mp * 3 * kE * 4);
     ws_add(p, "o", Mp * kE * 2);
     ws_add(p, "hidden", Mp * Md * 2);
+    // fp32 partial slabs of the split-K FFN-down (forward) / FFN-up dX (backward) GEMMs at small token counts
+    ws_add(p, "ffn.slabs", static_cast<size_t>(kFfnSplitMax) * (Mp < kFfnSplitRows ? Mp : kFfnSplitRows) * kE * 4);
   } else {
     ws_add(p, "xb", Mp * ((C + 63) / 64 * 64) * 2);
   }
@@ -573,6 +575,21 @@ int run_forward(smd_plan* p, const float* params, const float* x, const float* t
       e.out_bf16 = hidden; e.ld_bf16 = Md; e.act = ACT_GELU_TANH;
       e.out_bf16_pre = hid_pre;
       SMD_CUDA(gemm(p, o1, M, e, st));
+      const int fsp = p->lo_bytes == 0 ? ffn_splits(M, c.cta_group) : 1;
+      if (fsp > 1) {
+        // few tokens: a 256 x 128 output tile per CTA pair leaves most of the machine idle while each pair streams all
+        // of K = mlp_dims.  Cut K into `fsp` slabs (fp32 partials, no atomics), then one small kernel adds them in a
+        // fixed order with bias + residual and emits the next LayerNorm.
+        float* slabs = p->buf<float>("ffn.slabs");
+        const long long stride = static_cast<long long>(p->Mp < kFfnSplitRows ? p->Mp : kFfnSplitRows) * kE;
+        e = epi();
+        e.out_f32 = slabs; e.ld_f32 = kE; e.split_stride = stride;
+        o2.k_splits = fsp;
+        SMD_CUDA(gemm(p, o2, M, e, st));
+        launch_ln128_reduce_fwd(slabs, fsp, stride, p->P(params, pre + "ffn2.bias"), h_mid, p->P(params, nl + "scale"),
+                                p->P(params, nl + "bias"), h_out, a_next, M, st); CNT();
+        continue;
+      }
       e = epi();
       e.bias = p->P(params, pre + "ffn2.bias");
       e.residual = h_mid; e.ld_res = kE;
