@@ -125,11 +125,14 @@ struct smd_plan {
 
 namespace smd {
 // Split-K of the two K = mlp_dims, N = 128 trunk GEMMs (FFN-down forward, FFN-up dX backward) when the token count
-// leaves most CTA pairs idle: 16 tiles at batch 128 -> 64 tile-splits.  SMD_FFN_SPLITK=0 disables.
+// leaves most CTA pairs idle: 16 tiles at batch 128 -> 64 tile-splits, fp32 slabs added in a fixed order by the
+// consumer.  Opt-in (SMD_FFN_SPLITK=1): the GEMMs themselves drop from 17 to 7-12 us, but the extra reduce launch and
+// the 64 CTA pairs now competing with the weight-gradient stream make the whole step 2 % slower
+// (profiles/r02_bench_train_splitk{0,1}.json).
 static constexpr int kFfnSplitMax = 4;
 static constexpr int kFfnSplitRows = 9728;   // largest token count that still splits (38 tiles x 2 <= 76)
 inline int ffn_splits(int M, int cta_group) {
-  static const bool on = [] { const char* v = getenv("SMD_FFN_SPLITK"); return !(v && v[0] == '0'); }();
+  static const bool on = [] { const char* v = getenv("SMD_FFN_SPLITK"); return v && v[0] == '1'; }();
   if (!on || M > kFfnSplitRows) return 1;
   const int tiles = (M + 128 * cta_group - 1) / (128 * cta_group);
   const int groups = 148 / cta_group;
