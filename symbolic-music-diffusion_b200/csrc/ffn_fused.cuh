@@ -159,48 +159,59 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t n1 = 0, n2 = 0, nd1 = 0, nh = 0, nt = 0;
       for (int tile = group; tile < num_tiles; tile += num_groups, ++nt) {
         mbar_wait(a_full, nt & 1u);
-        auto gemm1 = [&](bool last) {
-          const uint32_t s = n1 % S::kW1Stages, b = nd1 & 1u;
-          mbar_wait(&w1_full[s], (n1 / S::kW1Stages) & 1u);
-          mbar_wait_cluster(&d1_empty[b], ((nd1 >> 1) & 1u) ^ 1u);
-          tcgen05_fence_after();
-          const uint32_t sW = smem_u32(smem + S::offW1 + s * S::kW);
+        // The two chains -- first GEMM of chunk g1 (needs its W1 slot and the accumulator buffer chunk g1 - 2 used) and
+        // second GEMM of chunk g2 (needs the epilogue's H_g2 and its W2 slot) -- are issued in whatever order their
+        // inputs become ready: the two epilogue groups then drift half a period apart instead of the later one waiting
+        // behind the other group's second GEMM every chunk.
+        int g1 = 0, g2 = 0;
+        unsigned long long t0 = global_timer_ns();
+        uint32_t spins = 0;
+        while (g2 < nchunks) {
+          bool moved = false;
+          if (g1 < nchunks) {
+            const uint32_t s = n1 % S::kW1Stages, b = nd1 & 1u;
+            if (mbar_test(&w1_full[s], (n1 / S::kW1Stages) & 1u) && mbar_test_cluster(&d1_empty[b], ((nd1 >> 1) & 1u) ^ 1u)) {
+              tcgen05_fence_after();
+              const uint32_t sW = smem_u32(smem + S::offW1 + s * S::kW);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
+              for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_smem_desc_sw128(sA + kb * 16384 + k * 32, 0u, 1024u);
-              const uint64_t bd = make_smem_desc_sw128(sW + kb * 8192 + k * 2048, 8192u, 1024u);
-              umma_bf16<2>(tmem_base + b * 128u, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = make_smem_desc_sw128(sA + kb * 16384 + k * 32, 0u, 1024u);
+                  const uint64_t bd = make_smem_desc_sw128(sW + kb * 8192 + k * 2048, 8192u, 1024u);
+                  umma_bf16<2>(tmem_base + b * 128u, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+              umma_commit<2>(&w1_empty[s]);
+              umma_commit<2>(&d1_full[b]);
+              if (g1 + 1 == nchunks) umma_commit<2>(a_empty);   // the A tile is no longer needed: the producer may fetch the next one
+              ++n1; ++nd1; ++g1;
+              moved = true;
             }
-          umma_commit<2>(&w1_empty[s]);
-          umma_commit<2>(&d1_full[b]);
-          if (last) umma_commit<2>(a_empty);   // the A tile is no longer needed: the producer may fetch the next one
-          ++n1; ++nd1;
-        };
-        gemm1(nchunks == 1);
-        if (nchunks > 1) gemm1(nchunks == 2);
-        for (int j = 0; j < nchunks; ++j) {
-          if (j + 2 < nchunks) gemm1(j + 3 == nchunks);   // waits only for chunk j's accumulator drain, not for its H
-          const uint32_t hb = nh & 1u, s2 = n2 % S::kW2Stages;
-          mbar_wait_cluster(&h_full[hb], (nh >> 1) & 1u);
-          mbar_wait(&w2_full[s2], (n2 / S::kW2Stages) & 1u);
-          if (j == 0) mbar_wait_cluster(d2_empty, (nt & 1u) ^ 1u);
-          tcgen05_fence_after();
-          const uint32_t sH = smem_u32(smem + S::offH + hb * S::kH);
-          const uint32_t sW = smem_u32(smem + S::offW2 + s2 * S::kW);
+          }
+          if (g2 < g1) {
+            const uint32_t hb = nh & 1u, s2 = n2 % S::kW2Stages;
+            if (mbar_test_cluster(&h_full[hb], (nh >> 1) & 1u) && mbar_test(&w2_full[s2], (n2 / S::kW2Stages) & 1u)) {
+              if (g2 == 0) mbar_wait_cluster(d2_empty, (nt & 1u) ^ 1u);
+              tcgen05_fence_after();
+              const uint32_t sH = smem_u32(smem + S::offH + hb * S::kH);
+              const uint32_t sW = smem_u32(smem + S::offW2 + s2 * S::kW);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
+              for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_smem_desc_sw128(sH + kb * 16384 + k * 32, 0u, 1024u);
-              const uint64_t bd = make_smem_desc_sw128(sW + kb * 8192 + k * 2048, 8192u, 1024u);
-              umma_bf16<2>(tmem_base + 256u, ad, bd, idesc, (j | kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = make_smem_desc_sw128(sH + kb * 16384 + k * 32, 0u, 1024u);
+                  const uint64_t bd = make_smem_desc_sw128(sW + kb * 8192 + k * 2048, 8192u, 1024u);
+                  umma_bf16<2>(tmem_base + 256u, ad, bd, idesc, (g2 | kb | k) != 0 ? 1u : 0u);
+                }
+              umma_commit<2>(&w2_empty[s2]);
+              umma_commit<2>(&h_empty[hb]);
+              if (g2 + 1 == nchunks) umma_commit<2>(d2_full);
+              ++n2; ++nh; ++g2;
+              moved = true;
             }
-          umma_commit<2>(&w2_empty[s2]);
-          umma_commit<2>(&h_empty[hb]);
-          if (j + 1 == nchunks) umma_commit<2>(d2_full);
-          ++n2; ++nh;
+          }
+          if (moved) { spins = 0; t0 = global_timer_ns(); }
+          else if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > SMD_WAIT_LIMIT_NS) __trap();
         }
       }
     }
