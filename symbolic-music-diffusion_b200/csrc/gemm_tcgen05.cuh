@@ -406,6 +406,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(acc * kAccCols);
         float s1 = 0.f, s2 = 0.f;
+        uint64_t s1p = f32x2_pack(0.f, 0.f), s2p = f32x2_pack(0.f, 0.f);
+        auto tsw = [&](int r_, int j_) { return reinterpret_cast<float4*>(scr) + (r_ * 8 + (j_ ^ (r_ & 7))); };
         float4 rpre[H_RES ? 8 : 1];
         auto prefetch = [&](int c) {
           if constexpr (H_RES) {
@@ -432,34 +434,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int i = 0; i < 8; ++i) bq[i] = __ldg(b4 + i);
           }
           tmem_ld_wait();
-          float v[32];
+          // packed fp32 pairs (FADD2 / FFMA2): half the issue slots of the scalar form, same round-to-nearest results
+          uint64_t v2[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i) v2[i] = f32x2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           if (has_bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { v[4 * i] += bq[i].x; v[4 * i + 1] += bq[i].y; v[4 * i + 2] += bq[i].z; v[4 * i + 3] += bq[i].w; }
+            for (int i = 0; i < 8; ++i) {
+              v2[2 * i] = f32x2_add(v2[2 * i], f32x2_pack(bq[i].x, bq[i].y));
+              v2[2 * i + 1] = f32x2_add(v2[2 * i + 1], f32x2_pack(bq[i].z, bq[i].w));
+            }
           }
           if constexpr (H_RES) {
             if (has_res) {
+              // residual block -> 32 x 32 transpose tile (16-byte chunk j of row r at slot j ^ (r & 7)): 128-bit accesses
 #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                float* d = scr + (it * 4 + f_r) * 33 + f_c;
-                d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
-              }
+              for (int it = 0; it < 8; ++it) *tsw(it * 4 + f_r, f_c >> 2) = rpre[it];
               if (c0 + 32 * G < BN) prefetch(c0 + 32 * G);
               __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
+              for (int i = 0; i < 8; ++i) {
+                const float4 t = *tsw(static_cast<int>(lane), i);
+                v2[2 * i] = f32x2_add(v2[2 * i], f32x2_pack(t.x, t.y));
+                v2[2 * i + 1] = f32x2_add(v2[2 * i + 1], f32x2_pack(t.z, t.w));
+              }
               __syncwarp();
             }
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+          for (int i = 0; i < 16; ++i) { s1p = f32x2_add(s1p, v2[i]); s2p = f32x2_fma(v2[i], v2[i], s2p); }
           // park the row's 32 columns as bf16: four 16-byte chunks
           {
             uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) {
+              float a, b;
+              f32x2_unpack(v2[j], a, b);
+              pk[j] = pack_bf16x2(a, b);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(park_ptr(static_cast<int>(lane), (c0 >> 3) + j)) =
@@ -470,10 +482,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               // v goes back to TMEM: the fp32 store sweep runs AFTER the partials are published, so the fence of the
               // exchange does not have to drain 16 KB of tile stores per warp
 #pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+              for (int i = 0; i < 16; ++i) {
+                float a, b;
+                f32x2_unpack(v2[i], a, b);
+                r[2 * i] = __float_as_uint(a); r[2 * i + 1] = __float_as_uint(b);
+              }
               tmem_st_32x32(taddr + static_cast<uint32_t>(c0), r);
             }
           }
+        }
+        {
+          float a, b;
+          f32x2_unpack(s1p, a, b); s1 = a + b;
+          f32x2_unpack(s2p, a, b); s2 = a + b;
         }
         // ---------------- exchange ----------------
         uint32_t* cnt = ep.lnf_cnt + (row_base >> 5);
@@ -493,16 +514,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), r);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 8; ++i)
+                *tsw(static_cast<int>(lane), i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const int rr = it * 4 + f_r, grow = row_base + rr;
-                if (grow < sh.M) {
-                  const float* sp = scr + rr * 33 + f_c;
-                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + n0 + c0 + f_c) =
-                      make_float4(sp[0], sp[1], sp[2], sp[3]);
-                }
+                if (grow < sh.M)
+                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + n0 + c0 + f_c) = *tsw(rr, f_c >> 2);
               }
             }
             __syncwarp();
@@ -604,13 +624,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               const uint4 raw = *reinterpret_cast<const uint4*>(park_ptr(rr, chunk));
               const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
               const float mean = rowst[2 * rr], rstd = rowst[2 * rr + 1];
+              const float nmr = -mean * rstd;
+              const uint64_t rs2 = f32x2_pack(rstd, rstd), nm2 = f32x2_pack(nmr, nmr);
               uint32_t pk[4];
 #pragma unroll
               for (int k2 = 0; k2 < 4; ++k2) {
                 const float2 f = __bfloat1622float2(hp[k2]);
-                float y0 = fmaf((f.x - mean) * rstd, A[2 * k2], Bc[2 * k2]);
-                float y1 = fmaf((f.y - mean) * rstd, A[2 * k2 + 1], Bc[2 * k2 + 1]);
-                if constexpr (kSwish) { y0 = act_apply(y0, ACT_SWISH); y1 = act_apply(y1, ACT_SWISH); }
+                // xhat = x rstd - mean rstd ; y = xhat (gamma scale) + (beta scale + shift) ; swish(y) = h + h tanh(h), h = y / 2
+                uint64_t y = f32x2_fma(f32x2_fma(f32x2_pack(f.x, f.y), rs2, nm2), f32x2_pack(A[2 * k2], A[2 * k2 + 1]),
+                                       f32x2_pack(Bc[2 * k2], Bc[2 * k2 + 1]));
+                if constexpr (kSwish) {
+                  const uint64_t h = f32x2_mul(y, f32x2_pack(0.5f, 0.5f));
+                  float h0, h1;
+                  f32x2_unpack(h, h0, h1);
+                  y = f32x2_fma(h, f32x2_pack(tanh_fast(h0), tanh_fast(h1)), h);
+                }
+                float y0, y1;
+                f32x2_unpack(y, y0, y1);
                 pk[k2] = pack_bf16x2(y0, y1);
               }
               if (grow < sh.M)
