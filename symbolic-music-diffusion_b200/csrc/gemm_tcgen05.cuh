@@ -352,6 +352,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int eg = static_cast<int>(warp - 4u) >> 2;   // column group 0/1: the two warps of a quadrant split the chunks
     float* scr = reinterpret_cast<float*>(smem + SM::kStages * SM::kStageBytes + SM::kBarBytes) + (warp - 4u) * SM::kScrPerWarp;
     uint32_t* scrw = reinterpret_cast<uint32_t*>(scr);
+    // fp32 transpose tile addressing for the coalesced residual loads / fp32 stores: 16-byte chunk j of row r at chunk
+    // slot r * 8 + (j ^ (r & 7)) -- 128-bit shared accesses, conflict-free for "lane = row" and "8 lanes = one row"
+    auto t4 = [&](int r_, int j_) { return reinterpret_cast<float4*>(scr) + (r_ * 8 + (j_ ^ (r_ & 7))); };
+    auto add_pair = [](float& a, float& b, float x, float y) {   // (a, b) += (x, y) as one packed FADD2
+      f32x2_unpack(f32x2_add(f32x2_pack(a, b), f32x2_pack(x, y)), a, b);
+    };
     const int f_r = static_cast<int>(lane >> 3), f_c = static_cast<int>(lane & 7u) * 4;  // fp32: 4 rows x 128 B / instr
     const int h_r = static_cast<int>(lane >> 2), h_c = static_cast<int>(lane & 3u) * 8;  // bf16: 8 rows x 64 B / instr
     int acc = 0; uint32_t acc_phase = 0;
@@ -695,35 +701,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 b = __ldg(b4 + i);
-                vv[j][4 * i] += b.x; vv[j][4 * i + 1] += b.y; vv[j][4 * i + 2] += b.z; vv[j][4 * i + 3] += b.w;
+                add_pair(vv[j][4 * i], vv[j][4 * i + 1], b.x, b.y);
+                add_pair(vv[j][4 * i + 2], vv[j][4 * i + 3], b.z, b.w);
               }
             }
             if (has_res) {
 #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                float* d = scr + (it * 4 + f_r) * 33 + f_c;
-                d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
-              }
+              for (int it = 0; it < 8; ++it) *t4(it * 4 + f_r, f_c >> 2) = rpre[it];
               if (j + 1 < nchunk) prefetch(eg * 32 + 64 * (j + 1));
               __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) vv[j][i] += scr[lane * 33 + i];
+              for (int i = 0; i < 8; ++i) {
+                const float4 t = *t4(static_cast<int>(lane), i);
+                add_pair(vv[j][4 * i], vv[j][4 * i + 1], t.x, t.y);
+                add_pair(vv[j][4 * i + 2], vv[j][4 * i + 3], t.z, t.w);
+              }
               __syncwarp();
             }
+            {
+              uint64_t a1 = f32x2_pack(0.f, 0.f), a2 = f32x2_pack(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { s1 += vv[j][i]; s2 += vv[j][i] * vv[j][i]; }
+              for (int i = 0; i < 16; ++i) {
+                const uint64_t pv = f32x2_pack(vv[j][2 * i], vv[j][2 * i + 1]);
+                a1 = f32x2_add(a1, pv);
+                a2 = f32x2_fma(pv, pv, a2);
+              }
+              float lo, hi;
+              f32x2_unpack(a1, lo, hi); s1 += lo + hi;
+              f32x2_unpack(a2, lo, hi); s2 += lo + hi;
+            }
             if (has_f32) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = vv[j][i];
+              for (int i = 0; i < 8; ++i)
+                *t4(static_cast<int>(lane), i) = make_float4(vv[j][4 * i], vv[j][4 * i + 1], vv[j][4 * i + 2], vv[j][4 * i + 3]);
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const int rr = it * 4 + f_r, grow = row_base + rr;
-                if (grow < sh.M) {
-                  const float* sp = scr + rr * 33 + f_c;
-                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + c0 + f_c) =
-                      make_float4(sp[0], sp[1], sp[2], sp[3]);
-                }
+                if (grow < sh.M)
+                  *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ld_f32 + c0 + f_c) = *t4(rr, f_c >> 2);
               }
               __syncwarp();
             }
@@ -887,7 +903,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     const float4 b = bq[i];
-                    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                    add_pair(v[4 * i], v[4 * i + 1], b.x, b.y);
+                    add_pair(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
                   }
                 }
               }
@@ -895,10 +912,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if constexpr (H_RES) {
                 if (pre_res) {
 #pragma unroll
-                  for (int it = 0; it < 8; ++it) {
-                    float* d = scr + (it * 4 + f_r) * 33 + f_c;
-                    d[0] = rpre[it].x; d[1] = rpre[it].y; d[2] = rpre[it].z; d[3] = rpre[it].w;
-                  }
+                  for (int it = 0; it < 8; ++it) *t4(it * 4 + f_r, f_c >> 2) = rpre[it];
                 }
               }
               if constexpr (H_GG) {
@@ -916,7 +930,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (pre_res) {
                   __syncwarp();
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] += scr[lane * 33 + i];
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 t = *t4(static_cast<int>(lane), i);
+                    add_pair(v[4 * i], v[4 * i + 1], t.x, t.y);
+                    add_pair(v[4 * i + 2], v[4 * i + 3], t.z, t.w);
+                  }
                   __syncwarp();
                 }
               }
@@ -939,25 +957,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (pass == 0) {
               if constexpr (H_STATS || H_LN) {
                 if (has_stats || do_ln) {
+                  uint64_t a1 = f32x2_pack(0.f, 0.f), a2 = f32x2_pack(0.f, 0.f);   // packed (FADD2 / FFMA2) partial sums
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+                  for (int i = 0; i < 16; ++i) {
+                    const uint64_t pv = f32x2_pack(v[2 * i], v[2 * i + 1]);
+                    a1 = f32x2_add(a1, pv);
+                    a2 = f32x2_fma(pv, pv, a2);
+                  }
+                  float lo, hi;
+                  f32x2_unpack(a1, lo, hi); s1 += lo + hi;
+                  f32x2_unpack(a2, lo, hi); s2 += lo + hi;
                 }
               }
               if constexpr (H_F32) {
                 if (has_f32) {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+                  for (int i = 0; i < 8; ++i)
+                    *t4(static_cast<int>(lane), i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                   __syncwarp();
 #pragma unroll
                   for (int it = 0; it < 8; ++it) {
                     const int rr = it * 4 + f_r, grow = row_base + rr;
                     if (grow < sh.M) {
-                      const float* sp = scr + rr * 33 + f_c;
+                      const float4 sp = *t4(rr, f_c >> 2);
                       float* op = out_f32_s + static_cast<size_t>(grow) * ep.ld_f32 + col0 + f_c;
                       if (H_ATOMIC && atomic_out) {
-                        atomicAdd(op, sp[0]); atomicAdd(op + 1, sp[1]); atomicAdd(op + 2, sp[2]); atomicAdd(op + 3, sp[3]);
+                        atomicAdd(op, sp.x); atomicAdd(op + 1, sp.y); atomicAdd(op + 2, sp.z); atomicAdd(op + 3, sp.w);
                       } else {
-                        *reinterpret_cast<float4*>(op) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        *reinterpret_cast<float4*>(op) = sp;
                       }
                     }
                   }
