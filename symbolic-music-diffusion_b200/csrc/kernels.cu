@@ -92,8 +92,85 @@ embed_kernel(const float* __restrict__ x, const float* __restrict__ W, const flo
     if (lo_delta) a[static_cast<size_t>(m) * 128 + o + lo_delta] = bf16_lo_part(y);
   }
 }
+// Same arithmetic (channels accumulated in the same order -> bit-identical), but the projection matrix sits in shared
+// memory and a warp carries 4 tokens at a time, so every weight read feeds 4 FMAs instead of 1 global load per FMA.
+template <int TPW>
+__global__ void __launch_bounds__(256)
+embed_smem_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                  const float* __restrict__ posenc, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                  float* __restrict__ h, __nv_bfloat16* __restrict__ a, int M, int C, int S, long long lo_delta) {
+  extern __shared__ __align__(16) float emb_w[];   // [C][128]
+  pdl_trigger();
+  // the weights are not written by the preceding kernel: stage them before waiting on it
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x)
+    reinterpret_cast<float4*>(emb_w)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
+  pdl_wait();
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+  float bo[4], go[4], eo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { bo[j] = bias[lane + 32 * j]; go[j] = ln_g[lane + 32 * j]; eo[j] = ln_b[lane + 32 * j]; }
+  for (int m0 = gw * TPW; m0 < M; m0 += nw * TPW) {
+    float acc[TPW][4];
+#pragma unroll
+    for (int t = 0; t < TPW; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      float xl[TPW];
+#pragma unroll
+      for (int t = 0; t < TPW; ++t)
+        xl[t] = (c0 + lane < C && m0 + t < M) ? x[static_cast<size_t>(m0 + t) * C + c0 + lane] : 0.f;
+      const int lim = min(32, C - c0);
+      for (int cc = 0; cc < lim; ++cc) {
+        const float* wr = emb_w + (c0 + cc) * 128 + lane;
+        const float w0 = wr[0], w1 = wr[32], w2 = wr[64], w3 = wr[96];
+#pragma unroll
+        for (int t = 0; t < TPW; ++t) {
+          const float xv = __shfl_sync(0xffffffffu, xl[t], cc);
+          acc[t][0] = fmaf(xv, w0, acc[t][0]); acc[t][1] = fmaf(xv, w1, acc[t][1]);
+          acc[t][2] = fmaf(xv, w2, acc[t][2]); acc[t][3] = fmaf(xv, w3, acc[t][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      const int m = m0 + t;
+      if (m >= M) break;
+      const int s = m % S;
+      float v[4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = lane + 32 * j;
+        v[j] = acc[t][j] + bo[j] + posenc[s * 128 + o];
+        s1 += v[j]; s2 += v[j] * v[j];
+        h[static_cast<size_t>(m) * 128 + o] = v[j];
+      }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      const float mean = s1 * (1.0f / 128.0f);
+      const float var = s2 * (1.0f / 128.0f) - mean * mean;
+      const float rstd = rsqrtf(var + 1e-6f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = lane + 32 * j;
+        const float y = (v[j] - mean) * (rstd * go[j]) + eo[j];
+        a[static_cast<size_t>(m) * 128 + o] = __float2bfloat16_rn(y);
+        if (lo_delta) a[static_cast<size_t>(m) * 128 + o + lo_delta] = bf16_lo_part(y);
+      }
+    }
+  }
+}
 void launch_embed(const float* x, const float* W_in, const float* b_in, const float* posenc, const float* ln_g,
                   const float* ln_b, float* h, __nv_bfloat16* a, int M, int C, int S, cudaStream_t st, long long lo_delta) {
+  if (C <= 64 && (reinterpret_cast<uintptr_t>(W_in) & 15u) == 0) {
+    int blocks = (M + 31) / 32;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    launch_pdl_g(kPdlMisc, embed_smem_kernel<4>, dim3(blocks), dim3(256), static_cast<size_t>(C) * 128 * sizeof(float), st, x, W_in,
+                 b_in, posenc, ln_g, ln_b, h, a, M, C, S, lo_delta);
+    return;
+  }
   const int blocks = (M + 7) / 8;
   launch_pdl_g(kPdlMisc, embed_kernel, dim3(blocks), dim3(256), 0, st, x, W_in, b_in, posenc, ln_g, ln_b, h, a, M, C, S,
                lo_delta);
@@ -769,11 +846,17 @@ reverse_step_kernel(const ReverseStepArgs a) {
   const uint32_t rtotal = a.rng_total ? a.rng_total : total, rfirst = a.rng_total ? a.rng_first : 0u;
   const int slot = (a.slot_tab && a.collection) ? a.slot_tab[t] : -1;
   float m_eps = 0.f, m_step = 0.f, m_noise = 0.f;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // four adjacent lanes share one (sample, channel) column and take a quarter of its S positions each: 4x the
+  // threads and a quarter of the serial threefry chain per thread (the axis-1 norms are folded with two shuffles)
+  constexpr int kSG = 4;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gi / kSG, sg = gi % kSG;
+  float e2 = 0.f, st2 = 0.f, nz2 = 0.f;
   if (i < NC) {
     const int n = i / a.C, c = i % a.C;
-    float e2 = 0.f, st2 = 0.f, nz2 = 0.f;
-    for (int s = 0; s < a.S; ++s) {
+    const int per = (a.S + kSG - 1) / kSG;
+    const int s_end = min(a.S, (sg + 1) * per);
+    for (int s = sg * per; s < s_end; ++s) {
       const uint32_t idx = (static_cast<uint32_t>(n) * a.S + s) * a.C + c;
       const float x = a.x[idx];
       const float eh = a.eps_hat[idx];
@@ -798,8 +881,10 @@ reverse_step_kernel(const ReverseStepArgs a) {
       a.x_next[idx] = nx;
       if (slot >= 0) a.collection[static_cast<size_t>(slot) * total + idx] = nx;
     }
-    m_eps = sqrtf(e2 + 1e-10f); m_step = sqrtf(st2 + 1e-10f); m_noise = sqrtf(nz2 + 1e-10f);
   }
+  e2 += __shfl_xor_sync(0xffffffffu, e2, 1); st2 += __shfl_xor_sync(0xffffffffu, st2, 1); nz2 += __shfl_xor_sync(0xffffffffu, nz2, 1);
+  e2 += __shfl_xor_sync(0xffffffffu, e2, 2); st2 += __shfl_xor_sync(0xffffffffu, st2, 2); nz2 += __shfl_xor_sync(0xffffffffu, nz2, 2);
+  if (i < NC && sg == 0) { m_eps = sqrtf(e2 + 1e-10f); m_step = sqrtf(st2 + 1e-10f); m_noise = sqrtf(nz2 + 1e-10f); }
   if (a.metrics) {
     __shared__ float red[3][8];
     m_eps = warp_sum(m_eps); m_step = warp_sum(m_step); m_noise = warp_sum(m_noise);
@@ -818,7 +903,7 @@ reverse_step_kernel(const ReverseStepArgs a) {
 }
 void launch_reverse_step(const ReverseStepArgs& a, cudaStream_t st) {
   const int NC = a.N * a.C;
-  launch_pdl_g(kPdlMisc, reverse_step_kernel, dim3((NC + 255) / 256), dim3(256), 0, st, a);
+  launch_pdl_g(kPdlMisc, reverse_step_kernel, dim3((4 * NC + 255) / 256), dim3(256), 0, st, a);
 }
 __global__ void step_advance_kernel(int* t_ptr) { *t_ptr -= 1; }
 void launch_step_advance(int* t_ptr, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(t_ptr); }
