@@ -8,15 +8,18 @@
 //   epi1_j  : D1[b] -> +b1 -> gelu -> bf16 -> shared memory, written directly in the canonical K-major SWIZZLE_128B
 //             operand layout (each thread owns one row: 4 x 16-byte chunks per 32 columns, chunk index XOR row&7)
 //   GEMM2_j : D2 (TMEM, 128 cols)    += H_j[256 x 128] . W2[chunk j, :]          (K = 128)
-// software-pipelined by the single MMA-issuing thread as  G1_0, {G1_{j+1}, G2_j}_j  so the tensor pipe works on the
-// next chunk while the 16 epilogue warps convert the current one.  Final epilogue: D2 + b2 + residual, single-pass
-// full-row LayerNorm (partials exchanged between the two warps of a TMEM lane quadrant), fp32 residual stream and
-// bf16 operand for the next GEMM.
+// The single MMA-issuing thread runs the two chains (G1 of the next chunks, G2 of the converted ones) in whatever order
+// their inputs become ready (mbarrier.test_wait polling), so the tensor pipe works ahead while the epilogue warps
+// convert: bias + GELU on packed fp32 pairs (FADD2 / FMUL2 / FFMA2).  Final epilogue (csrc/row_epilogue.cuh):
+// D2 + b2 + residual, single-pass full-row LayerNorm, fp32 residual stream and bf16 operand for the next GEMM, every
+// global access through a warp-private 32 x 32 transpose tile borrowed from the then idle H buffers.
 //
-// Warp roles (640 threads): 0 / 3 TMA producers (A tile once per tile and W1 chunks, 4-deep ring / W2 chunks, 3-deep; each
-// CTA stages its own 128 A rows and its half of every weight chunk), 1 MMA issuer (leader CTA), 2 TMEM allocator,
-// 4..19 epilogue: two groups of 8 (two per TMEM lane quadrant, 64 columns each); group g converts chunks j = g (mod 2).  Every cross-CTA hand-off is an mbarrier: tcgen05.commit multicasts "slot free / accumulator
-// ready" to both CTAs, epilogue warps of both CTAs arrive remotely on the leader's "D1 drained / H written" barriers.
+// Warp roles (640 threads): 0 / 3 TMA producers (A tile once per tile and W1 chunks, 4-deep ring / W2 chunks, 3-deep;
+// each CTA stages its own 128 A rows and its half of every weight chunk), 1 MMA issuer (leader CTA), 2 TMEM allocator,
+// 4..19 epilogue: two groups of 8 (two per TMEM lane quadrant, 64 columns each); group g converts chunks j = g (mod 2),
+// so the groups run half a period apart and one group's TMEM-load / barrier latency hides under the other's math.
+// Every cross-CTA hand-off is an mbarrier: tcgen05.commit multicasts "slot free / accumulator ready" to both CTAs,
+// epilogue warps of both CTAs arrive remotely on the leader's "D1 drained / H written" barriers.
 #pragma once
 #include "gemm_tcgen05.cuh"
 #include "row_epilogue.cuh"
