@@ -138,3 +138,26 @@ def test_reverse_coefficients_match_the_ddpm_posterior_in_float64():
     assert np.allclose(c["mu2"][far], (np.sqrt(alphas) * (1.0 - abar_prev) / (1.0 - abar))[far], rtol=1e-4)
     assert np.allclose(c["sigma"][far] ** 2, (betas * (1.0 - abar_prev) / (1.0 - abar))[far], rtol=2e-4)
     assert far.sum() > 850
+
+
+def test_reverse_step_matches_ancestral_sampling_from_the_paper():
+    """One reverse step of the oracle (utils/ebm_utils.py:327-397) against Algorithm 2 of Ho et al. with the clipped
+    x0-parameterisation, written independently in float64: x0 = clip((x - sqrt(1 - abar) eps) / sqrt(abar), -1, 1),
+    x_{t-1} = posterior_mean(x0, x) + sqrt(beta_tilde) z."""
+    betas32 = O.create_noise_schedule(1e-6, 0.01, 1000, "linear")
+    coef = O.reverse_coefficients(betas32)
+    betas = betas32.astype(np.float64)
+    alphas = 1.0 - betas
+    abar = np.cumprod(alphas)
+    abar_prev = np.concatenate([[1.0], abar[:-1]])
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(5, 32, 42, generator=g, dtype=torch.float64)
+    z = torch.randn(5, 32, 42, generator=g, dtype=torch.float64)
+    eps_hat = torch.randn(5, 32, 42, generator=g, dtype=torch.float64) * 0.7
+    for t in (999, 700, 400, 150):
+        nxt, _, _ = O.reverse_step(lambda s, c: eps_hat, x, t, coef, z)
+        x0 = torch.clamp((x - math.sqrt(1.0 - abar[t]) * eps_hat) / math.sqrt(abar[t]), -1.0, 1.0)
+        mean = (math.sqrt(abar_prev[t]) * betas[t] / (1.0 - abar[t])) * x0 + \
+               (math.sqrt(alphas[t]) * (1.0 - abar_prev[t]) / (1.0 - abar[t])) * x
+        ref = mean + math.sqrt(betas[t] * (1.0 - abar_prev[t]) / (1.0 - abar[t])) * z
+        assert torch.allclose(nxt, ref, rtol=0, atol=2e-4), t
