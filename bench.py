@@ -434,7 +434,10 @@ def run_gpu(args):
                        "cta_group": args.cta_group, "steps_per_s": 1e3 / ms_step,
                        "step_tflops": flops_step * world / (ms_step / 1e3) / 1e12,
                        "step_frac_of_sustained_peak": flops_step / (ms_step / 1e3) / 1e12 / ctx.tsust,
-                       "l2": "per-step working set (params+grads+Adam ~400 MB, activations ~1 GB) >> 126 MB L2; no flush",
+                       "l2": ("per-step working set (params+grads+Adam ~400 MB, activations ~1 GB) >> 126 MB L2; no flush"
+                              if args.workload == "train" else
+                              "per-step working set (bf16 weights 51 MB + activations ~1 GB at 32000 tokens) >> 126 MB L2; "
+                              "no flush"),
                        "precision": "bf16 tensor-core operands, fp32 accumulate / master weights / LN / softmax / Adam",
                        "rng": "device threefry draws (labels, alpha-bar, eps) are inside the timed step",
                        "untimed_settle_steps": settle},
