@@ -161,3 +161,23 @@ def test_reverse_step_matches_ancestral_sampling_from_the_paper():
                (math.sqrt(alphas[t]) * (1.0 - abar_prev[t]) / (1.0 - abar[t])) * x
         ref = mean + math.sqrt(betas[t] * (1.0 - abar_prev[t]) / (1.0 - abar[t])) * z
         assert torch.allclose(nxt, ref, rtol=0, atol=2e-4), t
+
+
+def test_sinusoidal_encodings_match_the_closed_forms():
+    """models/shared.py:33-48 is the timing signal of "Attention is all you need" as tensor2tensor computes it
+    (geometric timescales 1 .. 10000 over channels / 2 - 1 steps, [sin | cos]); models/ncsn.py:25-41 is WaveGrad's
+    noise-level encoding (same frequencies, argument 5000 * noise).  Written here with pow() instead of exp(log())."""
+    S, E = 32, 128
+    half = E // 2
+    inv_timescale = np.power(10000.0, -np.arange(half, dtype=np.float64) / (half - 1))
+    pos = np.arange(S, dtype=np.float64)[:, None] * inv_timescale[None, :]
+    ref = np.concatenate([np.sin(pos), np.cos(pos)], axis=1)
+    got64 = O.transformer_positional_encoding(S, E, torch.float64).numpy()
+    assert np.allclose(got64, ref, rtol=0, atol=1e-12)
+    got32 = O.transformer_positional_encoding(S, E, torch.float32).numpy()
+    assert np.allclose(got32, ref, rtol=0, atol=2e-5)        # fp32 frequencies times positions up to 31
+    noise = np.linspace(0.0026, 1.0, 9)
+    arg = (5000.0 * noise)[:, None] * inv_timescale[None, :]
+    refn = np.concatenate([np.sin(arg), np.cos(arg)], axis=1)
+    gotn = O.noise_encoding(torch.from_numpy(noise), E).numpy()
+    assert np.allclose(gotn, refn, rtol=0, atol=1e-9)
